@@ -1,0 +1,759 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (rank-2, NHWC, bf16 operands, fp32 TMEM accumulators).
+//
+// Replaces cuDNN's convolution forward / backward-data / backward-filter behind nn.Conv2d / nn.ConvTranspose2d for
+// the discriminator (/root/reference/code/GAN/GAN_final.py:167-189 -- 90 % of the step FLOPs) and the >=16-channel
+// generator layers (MONAI Convolution via GAN_final.py:106-114).
+//
+// Formulation ("tap GEMM"): for a tile of 128 output pixels (a tw x th x tn box of the output grid)
+//     out[p, n] = sum_{tap} sum_{c} In[pix(p) + off(tap), c] * W[tap][n][c]
+//  * A operand: one TMA 4-D box (KC channels, tw, th, tn) of the NHWC input per (tap, channel chunk); it lands in
+//    shared memory as 128 rows x KC bf16, K-major, hardware-swizzled (128/64/32 B) -- exactly the canonical UMMA
+//    layout, so the im2col matrix is never materialised.  Zero padding and ragged tile edges come from TMA's
+//    out-of-bounds zero fill (coordinates may be negative).  Stride-2 convolutions read through four "parity"
+//    tensor maps (base offset (ph,pw), element strides doubled), stride-2 backward-data / ConvTranspose writes four
+//    output parity classes, each an ordinary stride-1 tap list.
+//  * B operand: TMA 3-D box (KC, 1 tap, BN) of the packed weights [N][tap][C] (K-major).
+//  * D: 128 x BN fp32 in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of
+//    tile i+1.  Persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer,
+//    warp 2 TMEM allocator, warps 4-7 epilogue (TMEM -> registers -> +bias -> bf16 -> global, plus the batch-norm
+//    partial sums via a register transpose-reduce).
+//  * Weight gradient: D[cy, cx] += dY^T X per tap, both operands MN-major straight from the NHWC tensors
+//    (pixels are the K dimension), accumulators for a group of taps live in TMEM, split over pixel ranges and
+//    reduced with fp32 atomics into the flat gradient buffer.
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace mpgan {
+namespace tc {
+
+constexpr int MAXT = 16;
+constexpr int MAXCLS = 4;
+constexpr int kSmemLimit = 227 * 1024;
+
+struct TapGemmParams {
+  int ncls;
+  int cls_tap_begin[MAXCLS + 1];
+  int cls_oh[MAXCLS], cls_ow[MAXCLS];
+  long long cls_out_off[MAXCLS];
+  signed char tap_map[MAXT];
+  short tap_dh[MAXT], tap_dw[MAXT], tap_slab[MAXT];
+  int nkc;
+  int tiles_w, tiles_h, tiles_n;
+  int tw_log2, th_log2;
+  int nimg;
+  int n_total, n_tiles;
+  long long out_sn, out_sh, out_sw;
+  bf16* out;
+  const float* bias;
+  double* stats;
+};
+
+struct WgradParams {
+  int ntaps;
+  signed char tap_map[MAXT];
+  short tap_dh[MAXT], tap_dw[MAXT];
+  int taps_per_group, ngroups, m_blocks, splits;
+  int tiles_w, tiles_h, tiles_n, tw_log2, th_log2;
+  int cx, cy;
+  float* dw;
+};
+
+template <int KC> struct SwizzleOf;
+template <> struct SwizzleOf<64> { static constexpr uint32_t layout = 2, sbo = 1024; };
+template <> struct SwizzleOf<32> { static constexpr uint32_t layout = 4, sbo = 512; };
+template <> struct SwizzleOf<16> { static constexpr uint32_t layout = 6, sbo = 256; };
+
+template <int BN, int KC> struct TapCfg {
+  static constexpr int A_BYTES = 128 * KC * 2;
+  static constexpr int B_TX = BN * KC * 2;
+  static constexpr int B_BYTES = B_TX < 1024 ? 1024 : B_TX;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int AUX_BYTES = 256 + 2 * 512 * 4;  // barriers + stats[2*n_total<=1024 floats]
+  static constexpr int MAX_STAGES = (kSmemLimit - 1024 - AUX_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + AUX_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static_assert(STAGES >= 2, "pipeline too shallow");
+};
+
+// lane l ends up with sum over the warp's lanes of v[l]
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      float send = upper ? v[j] : v[j + off];
+      float keep = upper ? v[j + off] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(256, 1)
+tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ CUtensorMap tmA0,
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB) {
+  using Cfg = TapCfg<BN, KC>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_stats = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const CUtensorMap* mapsA[4] = {&tmA0, &tmA1, &tmA2, &tmA3};
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < 2 * P.n_total; i += blockDim.x) s_stats[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tn_log2 = 7 - P.tw_log2 - P.th_log2;
+  const int per_cls = P.tiles_n * P.tiles_h * P.tiles_w * P.n_tiles;
+  const int total_tiles = per_cls * P.ncls;
+
+  if (warp == 0) {
+    if (elect_one()) {  // ================= TMA producer =================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int nt = t % P.n_tiles; t /= P.n_tiles;
+        const int twi = t % P.tiles_w; t /= P.tiles_w;
+        const int thi = t % P.tiles_h; t /= P.tiles_h;
+        const int tni = t % P.tiles_n; t /= P.tiles_n;
+        const int cls = t;
+        const int w0 = twi << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
+        for (int tap = P.cls_tap_begin[cls]; tap < P.cls_tap_begin[cls + 1]; ++tap) {
+          const CUtensorMap* mA = mapsA[P.tap_map[tap]];
+          const int cw = w0 + P.tap_dw[tap], chh = h0 + P.tap_dh[tap], slab = P.tap_slab[tap];
+          for (int kc = 0; kc < P.nkc; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sB = sA + Cfg::A_BYTES;
+            mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_TX);
+            tma_load_4d(sA, mA, &full[stage], kc * KC, cw, chh, n0);
+            tma_load_3d(sB, &tmB, &full[stage], kc * KC, slab, nt * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {  // ================= MMA issuer =================
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int cls = tile / per_cls;
+        const int buf = it & 1;
+        const uint32_t par = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tempty[buf], par ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        const int kiters = (P.cls_tap_begin[cls + 1] - P.cls_tap_begin[cls]) * P.nkc;
+        for (int ki = 0; ki < kiters; ++ki) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, SwizzleOf<KC>::sbo, SwizzleOf<KC>::layout);
+            const uint64_t bdesc = make_smem_desc(b_addr + k * 32, 16, SwizzleOf<KC>::sbo, SwizzleOf<KC>::layout);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (ki | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp >= 4) {  // ================= epilogue =================
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int tw_mask = (1 << P.tw_log2) - 1, th_mask = (1 << P.th_log2) - 1;
+    const int lw = row & tw_mask, lh = (row >> P.tw_log2) & th_mask, ln = row >> (P.tw_log2 + P.th_log2);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int t = tile;
+      const int nt = t % P.n_tiles; t /= P.n_tiles;
+      const int twi = t % P.tiles_w; t /= P.tiles_w;
+      const int thi = t % P.tiles_h; t /= P.tiles_h;
+      const int tni = t % P.tiles_n; t /= P.tiles_n;
+      const int cls = t;
+      const int ow = (twi << P.tw_log2) + lw, oh = (thi << P.th_log2) + lh, img = (tni << tn_log2) + ln;
+      const bool valid = img < P.nimg && oh < P.cls_oh[cls] && ow < P.cls_ow[cls];
+      const int nbase = nt * BN;
+      bf16* orow = P.out + P.cls_out_off[cls] + (long long)img * P.out_sn + (long long)oh * P.out_sh +
+                   (long long)ow * P.out_sw + nbase;
+      const int buf = it & 1;
+      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tfull[buf], par);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+      constexpr int CH = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t r[32];
+        if (CH == 32) tmem_ld_32x32(t_addr + c0, r);
+        else tmem_ld_32x16(t_addr + c0, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          float f = __uint_as_float(r[j]);
+          if (P.bias) f += __ldg(&P.bias[nbase + c0 + j]);
+          v[j] = f;
+        }
+        uint32_t packed[CH / 2];
+#pragma unroll
+        for (int j = 0; j < CH / 2; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          packed[j] = *reinterpret_cast<uint32_t*>(&h);
+          if (P.stats) {  // statistics of the values as stored
+            float2 f = __bfloat1622float2(h);
+            v[2 * j] = valid ? f.x : 0.f;
+            v[2 * j + 1] = valid ? f.y : 0.f;
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < CH / 8; ++j)
+            *reinterpret_cast<uint4*>(orow + c0 + j * 8) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+        if (P.stats) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j >= CH) v[j] = 0.f;
+            sq[j] = v[j] * v[j];
+          }
+          float s1 = warp_transpose_reduce32(v, lane);
+          float s2 = warp_transpose_reduce32(sq, lane);
+          if (lane < CH) {
+            atomicAdd(&s_stats[nbase + c0 + lane], s1);
+            atomicAdd(&s_stats[P.n_total + nbase + c0 + lane], s2);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (P.stats) {
+    for (int i = threadIdx.x; i < 2 * P.n_total; i += blockDim.x) {
+      float s = s_stats[i];
+      if (s != 0.f) atomicAdd(&P.stats[i], (double)s);
+    }
+  }
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient:  D_tap[cy(128-block), cx] += sum over 64-pixel tiles  dY^T(tile) * X_tap(tile)
+// ---------------------------------------------------------------------------------------------------------
+template <int NX> struct WgCfg {
+  static constexpr int A_BYTES = 2 * 64 * 128;         // two 64-channel column groups x 64 pixels x 128 B
+  static constexpr int B_BYTES = (NX / 64) * 64 * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int AUX_BYTES = 256;
+  static constexpr int MAX_STAGES = (kSmemLimit - 1024 - AUX_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + AUX_BYTES;
+};
+
+template <int NX>
+__global__ void __launch_bounds__(256, 1)
+wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUtensorMap tmY,
+             const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+             const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmX3) {
+  using Cfg = WgCfg<NX>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const CUtensorMap* mapsX[4] = {&tmX0, &tmX1, &tmX2, &tmX3};
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmY);
+    prefetch_tmap(&tmX0);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int b = blockIdx.x;
+  const int mb = b % P.m_blocks; b /= P.m_blocks;
+  const int grp = b % P.ngroups; b /= P.ngroups;
+  const int split = b;
+  const int tap0 = grp * P.taps_per_group;
+  const int ntap = min(P.taps_per_group, P.ntaps - tap0);
+  const int ptiles = P.tiles_n * P.tiles_h * P.tiles_w;
+  const int tn_log2 = 6 - P.tw_log2 - P.th_log2;
+  const int my_tiles = split < ptiles ? (ptiles - split + P.splits - 1) / P.splits : 0;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = split; pt < ptiles; pt += P.splits) {
+        int t = pt;
+        const int twi = t % P.tiles_w; t /= P.tiles_w;
+        const int thi = t % P.tiles_h; t /= P.tiles_h;
+        const int tni = t;
+        const int w0 = twi << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
+        for (int tl = 0; tl < ntap; ++tl) {
+          const int tap = tap0 + tl;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(sA, &tmY, &full[stage], mb * 128, w0, h0, n0);
+          tma_load_4d(sA + 8192, &tmY, &full[stage], mb * 128 + 64, w0, h0, n0);
+          const CUtensorMap* mX = mapsX[P.tap_map[tap]];
+#pragma unroll
+          for (int i = 0; i < NX / 64; ++i)
+            tma_load_4d(sB + i * 8192, mX, &full[stage], i * 64, w0 + P.tap_dw[tap], h0 + P.tap_dh[tap], n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, NX, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        for (int tl = 0; tl < ntap; ++tl) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(tl * NX);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 64 pixels = 4 x K16; 16 rows of 128 B per step
+            const uint64_t adesc = make_smem_desc(a_addr + k * 2048, 8192, 1024, 2);
+            const uint64_t bdesc = make_smem_desc(b_addr + k * 2048, 8192, 1024, 2);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      umma_commit(tfull);
+    }
+  } else if (warp >= 4 && my_tiles > 0) {
+    const int q = warp - 4;
+    const int m = mb * 128 + q * 32 + lane;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    for (int tl = 0; tl < ntap; ++tl) {
+      const int tap = tap0 + tl;
+      float* drow = P.dw + ((long long)m * P.ntaps + tap) * P.cx;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NX; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * NX + c0), r);
+        tmem_ld_wait();
+        if (m < P.cy) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < P.cx) atomicAdd(drow + c0 + j, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for_bytes(int inner_bytes) {
+  return inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+// bf16 tensor map, `rank` dims (innermost first); strides in elements for dims 1..rank-1
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                      const uint32_t* box) {
+  auto enc = get_encode();
+  MPGAN_REQUIRE(enc != nullptr, MPGAN_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_elems[i] * 2;
+  MPGAN_REQUIRE(((uintptr_t)base & 15) == 0, MPGAN_ERR_SHAPE, "tensor base not 16-byte aligned");
+  for (int i = 0; i < rank - 1; ++i)
+    MPGAN_REQUIRE(gstr[i] % 16 == 0, MPGAN_ERR_SHAPE, "tensor stride %d (=%llu B) not a multiple of 16 B", i,
+                  (unsigned long long)gstr[i]);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes((int)box[0] * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MPGAN_REQUIRE(r == CUDA_SUCCESS, MPGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+struct Geom2 {
+  int n, xh, xw, yh, yw, cx, cy, kh, kw, s, ph, pw;
+};
+
+static int to_geom2(const MpganConvGeom* g, Geom2* o) {
+  MPGAN_REQUIRE(g && g->rank == 2, MPGAN_ERR_UNSUPPORTED, "tcgen05 conv path is rank-2 only");
+  MPGAN_REQUIRE(g->stride[1] == g->stride[2] && (g->stride[1] == 1 || g->stride[1] == 2), MPGAN_ERR_UNSUPPORTED,
+                "tcgen05 conv path supports stride 1 or 2");
+  o->n = g->n; o->xh = g->xs[1]; o->xw = g->xs[2]; o->yh = g->ys[1]; o->yw = g->ys[2];
+  o->cx = g->cx; o->cy = g->cy; o->kh = g->k[1]; o->kw = g->k[2]; o->s = g->stride[1]; o->ph = g->pad[1]; o->pw = g->pad[2];
+  MPGAN_REQUIRE(o->kh * o->kw <= MAXT, MPGAN_ERR_UNSUPPORTED, "too many taps");
+  MPGAN_REQUIRE(o->cx % 16 == 0 && o->cy % 16 == 0, MPGAN_ERR_UNSUPPORTED, "channels must be multiples of 16");
+  MPGAN_REQUIRE(o->yh <= (o->xh + 2 * o->ph - o->kh) / o->s + 1 && o->yw <= (o->xw + 2 * o->pw - o->kw) / o->s + 1,
+                MPGAN_ERR_SHAPE, "Y extent exceeds conv output size");
+  return 0;
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// choose a tw x th x tn = npix tile minimising padded work
+static void choose_tile(int ow, int oh, int nimg, int npix, int* tw_log2, int* th_log2) {
+  double best = 1e300;
+  int bl = 0, bh = 0;
+  for (int lw = 0; lw <= 5; ++lw)
+    for (int lh = 0; lh <= 5; ++lh) {
+      int ln = ilog2(npix) - lw - lh;
+      if (ln < 0 || ln > 4) continue;
+      int tw = 1 << lw, th = 1 << lh, tn = 1 << ln;
+      double work = (double)((ow + tw - 1) / tw * tw) * ((oh + th - 1) / th * th) * ((nimg + tn - 1) / tn * tn);
+      work *= 1.0 + 0.02 * ln + 0.01 * (5 - lw);  // mild preference for wide single-image tiles
+      if (work < best) { best = work; bl = lw; bh = lh; }
+    }
+  *tw_log2 = bl;
+  *th_log2 = bh;
+}
+
+// tensor maps over the gathered activation tensor (spatial h x w, channels c, pixel stride ld):
+// stride 1 -> one map; stride 2 -> four parity maps
+static int make_act_maps(CUtensorMap* maps, const void* base, int nimg, int h, int w, int c, int64_t ld, int s,
+                         const uint32_t* box) {
+  const bf16* b = (const bf16*)base;
+  if (s == 1) {
+    uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)nimg};
+    uint64_t str[3] = {(uint64_t)ld, (uint64_t)ld * w, (uint64_t)ld * w * h};
+    int rc = encode_map(&maps[0], b, 4, dims, str, box);
+    if (rc) return rc;
+    for (int i = 1; i < 4; ++i) maps[i] = maps[0];
+    return 0;
+  }
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      int hh = (h - ph + 1) / 2, ww = (w - pw + 1) / 2;
+      if (hh < 1) hh = 1;
+      if (ww < 1) ww = 1;
+      uint64_t dims[4] = {(uint64_t)c, (uint64_t)ww, (uint64_t)hh, (uint64_t)nimg};
+      uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)ld * w * 2, (uint64_t)ld * w * h};
+      int rc = encode_map(&maps[ph * 2 + pw], b + ((int64_t)ph * w + pw) * ld, 4, dims, str, box);
+      if (rc) return rc;
+    }
+  return 0;
+}
+
+template <int BN, int KC>
+static int launch_tapgemm_t(const TapGemmParams& P, const CUtensorMap* mA, const CUtensorMap& mB, cudaStream_t s) {
+  using Cfg = TapCfg<BN, KC>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    MPGAN_REQUIRE(e == cudaSuccess, MPGAN_ERR_CUDA, "cudaFuncSetAttribute(tapgemm): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const long long total = (long long)P.ncls * P.tiles_n * P.tiles_h * P.tiles_w * P.n_tiles;
+  int grid = (int)(total < num_sms() ? total : num_sms());
+  tapgemm_kernel<BN, KC><<<grid, 256, Cfg::SMEM_BYTES, s>>>(P, mA[0], mA[1], mA[2], mA[3], mB);
+  MPGAN_CHECK_LAUNCH("tapgemm_kernel");
+  return 0;
+}
+
+template <int KC>
+static int launch_tapgemm_kc(int bn, const TapGemmParams& P, const CUtensorMap* mA, const CUtensorMap& mB,
+                             cudaStream_t s) {
+  switch (bn) {
+    case 16: return launch_tapgemm_t<16, KC>(P, mA, mB, s);
+    case 32: return launch_tapgemm_t<32, KC>(P, mA, mB, s);
+    case 64: return launch_tapgemm_t<64, KC>(P, mA, mB, s);
+    case 128: return launch_tapgemm_t<128, KC>(P, mA, mB, s);
+    case 256: return launch_tapgemm_t<256, KC>(P, mA, mB, s);
+  }
+  set_error("bad BN %d", bn);
+  return MPGAN_ERR_UNSUPPORTED;
+}
+
+static int pick_bn(int n) {
+  const int cands[5] = {256, 128, 64, 32, 16};
+  for (int i = 0; i < 5; ++i)
+    if (n % cands[i] == 0) return cands[i];
+  return 0;
+}
+
+// common driver for fprop (dir 0) and bprop (dir 1)
+static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, const void* w, const float* bias, void* out,
+                       int64_t ldo, double* stats, cudaStream_t s) {
+  const int C = dir == 0 ? g.cx : g.cy;  // reduced channels
+  const int N = dir == 0 ? g.cy : g.cx;  // produced channels
+  const int ih = dir == 0 ? g.xh : g.yh, iw = dir == 0 ? g.xw : g.yw;
+  const int oh = dir == 0 ? g.yh : g.xh, ow = dir == 0 ? g.yw : g.xw;
+  const int T = g.kh * g.kw;
+  const int KC = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
+  const int BN = pick_bn(N);
+  MPGAN_REQUIRE(BN > 0, MPGAN_ERR_UNSUPPORTED, "N=%d not tileable", N);
+  MPGAN_REQUIRE(ldi % 8 == 0 && ldo % 8 == 0, MPGAN_ERR_SHAPE, "pixel strides must be multiples of 8 elements");
+  MPGAN_REQUIRE(((uintptr_t)out & 15) == 0, MPGAN_ERR_SHAPE, "output not 16-byte aligned");
+
+  TapGemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.nkc = C / KC;
+  P.nimg = g.n;
+  P.n_total = N;
+  P.n_tiles = N / BN;
+  P.out = (bf16*)out;
+  P.bias = bias;
+  P.stats = stats;
+  MPGAN_REQUIRE(N <= 512, MPGAN_ERR_UNSUPPORTED, "N > 512");
+
+  int ntap = 0;
+  int loh, low;  // logical output grid the tiles cover
+  if (dir == 0) {  // gather X: xpos = ypos*s - pad + r
+    P.ncls = 1;
+    P.cls_tap_begin[0] = 0;
+    for (int rh = 0; rh < g.kh; ++rh)
+      for (int rw = 0; rw < g.kw; ++rw) {
+        int qh = rh - g.ph, qw = rw - g.pw;
+        int ph = g.s == 2 ? ((qh % 2) + 2) % 2 : 0, pw = g.s == 2 ? ((qw % 2) + 2) % 2 : 0;
+        P.tap_map[ntap] = (signed char)(ph * 2 + pw);
+        P.tap_dh[ntap] = (short)(g.s == 2 ? floordiv(qh - ph, 2) : qh);
+        P.tap_dw[ntap] = (short)(g.s == 2 ? floordiv(qw - pw, 2) : qw);
+        P.tap_slab[ntap] = (short)(rh * g.kw + rw);
+        ++ntap;
+      }
+    P.cls_tap_begin[1] = ntap;
+    P.cls_oh[0] = oh; P.cls_ow[0] = ow; P.cls_out_off[0] = 0;
+    P.out_sn = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo; P.out_sw = ldo;
+    loh = oh; low = ow;
+  } else {  // gather Y: ypos = (xpos + pad - r)/s
+    P.ncls = g.s * g.s;
+    for (int cph = 0; cph < g.s; ++cph)
+      for (int cpw = 0; cpw < g.s; ++cpw) {
+        int cls = cph * g.s + cpw;
+        P.cls_tap_begin[cls] = ntap;
+        for (int rh = 0; rh < g.kh; ++rh)
+          for (int rw = 0; rw < g.kw; ++rw) {
+            int ah = cph + g.ph - rh, aw = cpw + g.pw - rw;
+            if (g.s == 2 && ((ah & 1) || (aw & 1))) continue;
+            P.tap_map[ntap] = 0;
+            P.tap_dh[ntap] = (short)(g.s == 2 ? ah / 2 : ah);   // ah even here, exact
+            P.tap_dw[ntap] = (short)(g.s == 2 ? aw / 2 : aw);
+            P.tap_slab[ntap] = (short)(rh * g.kw + rw);
+            ++ntap;
+          }
+        MPGAN_REQUIRE(ntap > P.cls_tap_begin[cls], MPGAN_ERR_UNSUPPORTED, "empty tap class (k < stride)");
+        P.cls_oh[cls] = (oh - cph + g.s - 1) / g.s;
+        P.cls_ow[cls] = (ow - cpw + g.s - 1) / g.s;
+        P.cls_out_off[cls] = ((long long)cph * ow + cpw) * ldo;
+      }
+    P.cls_tap_begin[P.ncls] = ntap;
+    P.out_sn = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo * g.s; P.out_sw = ldo * g.s;
+    loh = (oh + g.s - 1) / g.s; low = (ow + g.s - 1) / g.s;
+  }
+  (void)T;
+  choose_tile(low, loh, g.n, 128, &P.tw_log2, &P.th_log2);
+  const int tw = 1 << P.tw_log2, th = 1 << P.th_log2, tn = 128 / (tw * th);
+  P.tiles_w = (low + tw - 1) / tw; P.tiles_h = (loh + th - 1) / th; P.tiles_n = (g.n + tn - 1) / tn;
+
+  CUtensorMap mA[4], mB;
+  uint32_t boxA[4] = {(uint32_t)KC, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+  int rc = make_act_maps(mA, in, g.n, ih, iw, C, ldi, dir == 0 ? g.s : 1, boxA);
+  if (rc) return rc;
+  {
+    uint64_t dims[3] = {(uint64_t)C, (uint64_t)(g.kh * g.kw), (uint64_t)N};
+    uint64_t str[2] = {(uint64_t)C, (uint64_t)C * g.kh * g.kw};
+    uint32_t box[3] = {(uint32_t)KC, 1u, (uint32_t)BN};
+    rc = encode_map(&mB, w, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  switch (KC) {
+    case 64: return launch_tapgemm_kc<64>(BN, P, mA, mB, s);
+    case 32: return launch_tapgemm_kc<32>(BN, P, mA, mB, s);
+    default: return launch_tapgemm_kc<16>(BN, P, mA, mB, s);
+  }
+}
+
+template <int NX>
+static int launch_wgrad_t(const WgradParams& P, const CUtensorMap& mY, const CUtensorMap* mX, cudaStream_t s) {
+  using Cfg = WgCfg<NX>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    MPGAN_REQUIRE(e == cudaSuccess, MPGAN_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  int grid = P.m_blocks * P.ngroups * P.splits;
+  wgrad_kernel<NX><<<grid, 256, Cfg::SMEM_BYTES, s>>>(P, mY, mX[0], mX[1], mX[2], mX[3]);
+  MPGAN_CHECK_LAUNCH("wgrad_kernel");
+  return 0;
+}
+
+static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, int64_t ldy, float* dw, cudaStream_t s) {
+  MPGAN_REQUIRE(g.cx == 64 || g.cx == 128 || g.cx == 256, MPGAN_ERR_UNSUPPORTED, "tc wgrad needs cx in {64,128,256}");
+  MPGAN_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, MPGAN_ERR_SHAPE, "pixel strides must be multiples of 8 elements");
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  P.cx = g.cx; P.cy = g.cy; P.dw = dw;
+  int ntap = 0;
+  for (int rh = 0; rh < g.kh; ++rh)
+    for (int rw = 0; rw < g.kw; ++rw) {
+      int qh = rh - g.ph, qw = rw - g.pw;
+      int ph = g.s == 2 ? ((qh % 2) + 2) % 2 : 0, pw = g.s == 2 ? ((qw % 2) + 2) % 2 : 0;
+      P.tap_map[ntap] = (signed char)(ph * 2 + pw);
+      P.tap_dh[ntap] = (short)(g.s == 2 ? floordiv(qh - ph, 2) : qh);
+      P.tap_dw[ntap] = (short)(g.s == 2 ? floordiv(qw - pw, 2) : qw);
+      ++ntap;
+    }
+  P.ntaps = ntap;
+  P.taps_per_group = 512 / g.cx;
+  if (P.taps_per_group > ntap) P.taps_per_group = ntap;
+  P.ngroups = (ntap + P.taps_per_group - 1) / P.taps_per_group;
+  P.m_blocks = (g.cy + 127) / 128;
+  choose_tile(g.yw, g.yh, g.n, 64, &P.tw_log2, &P.th_log2);
+  const int tw = 1 << P.tw_log2, th = 1 << P.th_log2, tn = 64 / (tw * th);
+  P.tiles_w = (g.yw + tw - 1) / tw; P.tiles_h = (g.yh + th - 1) / th; P.tiles_n = (g.n + tn - 1) / tn;
+  const int ptiles = P.tiles_w * P.tiles_h * P.tiles_n;
+  const int items = P.m_blocks * P.ngroups;
+  int splits = (num_sms() + items - 1) / items;
+  if (splits > ptiles) splits = ptiles;
+  if (splits < 1) splits = 1;
+  P.splits = splits;
+
+  CUtensorMap mY, mX[4];
+  {
+    uint64_t dims[4] = {(uint64_t)g.cy, (uint64_t)g.yw, (uint64_t)g.yh, (uint64_t)g.n};
+    uint64_t str[3] = {(uint64_t)ldy, (uint64_t)ldy * g.yw, (uint64_t)ldy * g.yw * g.yh};
+    uint32_t box[4] = {64u, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+    int rc = encode_map(&mY, y, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  uint32_t boxX[4] = {64u, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+  int rc = make_act_maps(mX, x, g.n, g.xh, g.xw, g.cx, ldx, g.s, boxX);
+  if (rc) return rc;
+  switch (g.cx) {
+    case 64: return launch_wgrad_t<64>(P, mY, mX, s);
+    case 128: return launch_wgrad_t<128>(P, mY, mX, s);
+    default: return launch_wgrad_t<256>(P, mY, mX, s);
+  }
+}
+
+}  // namespace tc
+}  // namespace mpgan
+
+using namespace mpgan;
+using namespace mpgan::tc;
+
+extern "C" int mpgan_tc_supported(const MpganConvGeom* g, int direction) {
+  Geom2 g2;
+  if (to_geom2(g, &g2) != 0) return 0;
+  if (direction == 2) return (g2.cx == 64 || g2.cx == 128 || g2.cx == 256) ? 1 : 0;
+  const int N = direction == 0 ? g2.cy : g2.cx;
+  if (pick_bn(N) == 0 || N > 512) return 0;
+  if (direction == 1 && g2.s == 2 && (g2.kh < 2 || g2.kw < 2)) return 0;
+  return 1;
+}
+
+extern "C" int mpgan_tc_conv_fprop(const MpganConvGeom* g, const void* x, int64_t ldx, const void* w_f,
+                                   const float* bias, void* y, int64_t ldy, double* stats, void* stream) {
+  Geom2 g2;
+  int rc = to_geom2(g, &g2);
+  if (rc) return rc;
+  return run_tapgemm(g2, 0, x, ldx, w_f, bias, y, ldy, stats, (cudaStream_t)stream);
+}
+
+extern "C" int mpgan_tc_conv_bprop(const MpganConvGeom* g, const void* y, int64_t ldy, const void* w_b,
+                                   const float* bias, void* x, int64_t ldx, double* stats, void* stream) {
+  Geom2 g2;
+  int rc = to_geom2(g, &g2);
+  if (rc) return rc;
+  return run_tapgemm(g2, 1, y, ldy, w_b, bias, x, ldx, stats, (cudaStream_t)stream);
+}
+
+extern "C" size_t mpgan_tc_conv_wgrad_workspace(const MpganConvGeom* g) {
+  (void)g;
+  return 0;  // split partials are reduced with fp32 atomics straight into dw
+}
+
+extern "C" int mpgan_tc_conv_wgrad(const MpganConvGeom* g, const void* x, int64_t ldx, const void* y, int64_t ldy,
+                                   float* dw, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  Geom2 g2;
+  int rc = to_geom2(g, &g2);
+  if (rc) return rc;
+  return run_wgrad(g2, x, ldx, y, ldy, dw, (cudaStream_t)stream);
+}
+

@@ -1,0 +1,343 @@
+// Linear-after-Flatten (split-K GEMV), Sigmoid+BCE, L1, fused Adam, patch gather / scatter-add.
+// Replaces nn.Linear + nn.Sigmoid (/root/reference/code/GAN/GAN_final.py:199-204), F.binary_cross_entropy and
+// F.l1_loss (GAN_final.py:244-248), torch.optim.Adam (GAN_final.py:298-308) and the RandSpatialCropSamplesd
+// slicing + torch.cat of /root/reference/test_runs/GAN.py:313-337.
+#include "common.cuh"
+
+namespace mpgan {
+
+constexpr int kLinK = 4096;  // k-chunk per block
+
+// y[b][j] += sum_k x[b][k] w[j][k]  (+ bias[j] once)
+template <typename T>
+__global__ void __launch_bounds__(256)
+linear_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ y, int64_t K, int J) {
+  __shared__ float part[8];
+  const int b = blockIdx.y;
+  const int64_t k0 = (int64_t)blockIdx.x * kLinK;
+  const int64_t k1 = min(K, k0 + kLinK);
+  const T* xr = x + (int64_t)b * K;
+  float xv[kLinK / 256];
+#pragma unroll
+  for (int i = 0; i < kLinK / 256; ++i) {
+    int64_t k = k0 + threadIdx.x + i * 256;
+    xv[i] = k < k1 ? to_f(xr[k]) : 0.f;
+  }
+  for (int j = 0; j < J; ++j) {
+    const T* wr = w + (int64_t)j * K;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLinK / 256; ++i) {
+      int64_t k = k0 + threadIdx.x + i * 256;
+      if (k < k1) acc = fmaf(xv[i], to_f(wr[k]), acc);
+    }
+    float tot = block_sum(acc, part);
+    if (threadIdx.x == 0) {
+      if (blockIdx.x == 0 && bias) tot += bias[j];
+      atomicAdd(&y[(int64_t)b * J + j], tot);
+    }
+  }
+}
+
+// dx[b][k] = sum_j dy[b][j] w[j][k]
+template <typename T>
+__global__ void linear_dx_kernel(const T* __restrict__ w, const float* __restrict__ dy, T* __restrict__ dx,
+                                 int B, int64_t K, int J) {
+  const int64_t total = (int64_t)B * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = i / K, k = i - b * K;
+    float acc = 0.f;
+    for (int j = 0; j < J; ++j) acc = fmaf(dy[b * J + j], to_f(w[(int64_t)j * K + k]), acc);
+    dx[i] = from_f<T>(acc);
+  }
+}
+
+// dw[j][k] += sum_b dy[b][j] x[b][k]
+template <typename T>
+__global__ void linear_dw_kernel(const T* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                 int B, int64_t K, int J) {
+  const int64_t total = (int64_t)J * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t j = i / K, k = i - j * K;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(dy[(int64_t)b * J + j], to_f(x[(int64_t)b * K + k]), acc);
+    dw[i] += acc;
+  }
+}
+
+__global__ void linear_db_kernel(const float* __restrict__ dy, float* __restrict__ db, int B, int J) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= J) return;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc += dy[(int64_t)b * J + j];
+  db[j] += acc;
+}
+
+// ---- sigmoid, BCE on probabilities ----
+__global__ void sigmoid_fwd_kernel(const float* __restrict__ z, float* __restrict__ p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 1.f / (1.f + expf(-z[i]));
+}
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ p, float* __restrict__ dz,
+                                   int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dz[i] = dp[i] * p[i] * (1.f - p[i]);
+}
+
+__global__ void __launch_bounds__(256)
+bce_fwd_kernel(const float* __restrict__ prob, const float* __restrict__ target, float weight,
+               float* __restrict__ loss, int n) {
+  __shared__ float part[8];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float p = prob[i], t = target[i];
+    float lp = fmaxf(logf(p), -100.f);
+    float lq = fmaxf(log1pf(-p), -100.f);
+    acc += (t - 1.f) * lq - t * lp;
+  }
+  float tot = block_sum(acc, part);
+  if (threadIdx.x == 0) *loss += weight * (tot / (float)n);
+}
+
+__global__ void bce_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ target, float weight,
+                               const float* __restrict__ gscale, float* __restrict__ dprob, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g = (gscale ? *gscale : 1.f) * weight / (float)n;
+  float p = prob[i];
+  dprob[i] = g * (p - target[i]) / fmaxf(p * (1.f - p), 1e-12f);
+}
+
+// ---- L1 ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+l1_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n, float scale, float* __restrict__ loss) {
+  __shared__ float part[8];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += fabsf(to_f(a[i]) - to_f(b[i]));
+  float tot = block_sum(acc, part);
+  if (threadIdx.x == 0) atomicAdd(loss, tot * scale);
+}
+
+template <typename T>
+__global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n, float scale,
+                              const float* __restrict__ gscale, T* __restrict__ da, int accumulate) {
+  const float g = (gscale ? *gscale : 1.f) * scale;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = to_f(a[i]) - to_f(b[i]);
+    float v = d > 0.f ? g : (d < 0.f ? -g : 0.f);
+    if (accumulate) v += to_f(da[i]);
+    da[i] = from_f<T>(v);
+  }
+}
+
+// ---- Adam ----
+// state[0] = step count (as int bits), state[1] = step_size = lr/(1-beta1^t), state[2] = sqrt(1-beta2^t).
+// The step counter lives on the device so a captured CUDA graph advances it on every replay.
+__global__ void adam_prep_kernel(float* __restrict__ state, float lr, float beta1, float beta2) {
+  int step = __float_as_int(state[0]) + 1;
+  state[0] = __int_as_float(step);
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  state[1] = (float)((double)lr / bc1);
+  state[2] = (float)sqrt(bc2);
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float beta1, float beta2, float eps,
+                            const float* __restrict__ state, bf16* __restrict__ shadow) {
+  const float step_size = state[1], bc2_sqrt = state[2];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    float mi = m[i] + (gi - m[i]) * (1.f - beta1);          // exp_avg.lerp_(grad, 1 - beta1)
+    float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    float pi = p[i] - step_size * (mi / denom);
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+// ---- patches ----
+template <typename T>
+__global__ void patch_gather_kernel(const T* __restrict__ vol, int rank, int s0, int s1, int s2, int C,
+                                    const int* __restrict__ origins, int num_samples, int roi, T* __restrict__ out,
+                                    int64_t total) {
+  const int r0 = rank == 3 ? roi : 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); int64_t r = i / C;
+    int w = (int)(r % roi); r /= roi;
+    int h = (int)(r % roi); r /= roi;
+    int d = (int)(r % r0); r /= r0;
+    int64_t patch = r;                 // = b*num_samples + s
+    int64_t b = patch / num_samples;
+    const int* o = origins + patch * rank;
+    int od = rank == 3 ? o[0] : 0, oh = o[rank - 2], ow = o[rank - 1];
+    int64_t src = ((((b * s0) + od + d) * s1 + oh + h) * s2 + ow + w) * C + c;
+    out[i] = vol[src];
+  }
+}
+
+// deterministic backward: every voxel sums the patches covering it in sample order
+template <typename T>
+__global__ void patch_scatter_kernel(const T* __restrict__ dpatch, int rank, int s0, int s1, int s2, int C,
+                                     const int* __restrict__ origins, int num_samples, int roi,
+                                     T* __restrict__ dvol, int64_t total) {
+  const int r0 = rank == 3 ? roi : 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); int64_t r = i / C;
+    int w = (int)(r % s2); r /= s2;
+    int h = (int)(r % s1); r /= s1;
+    int d = (int)(r % s0); r /= s0;
+    int64_t b = r;
+    float acc = to_f(dvol[i]);
+    for (int s = 0; s < num_samples; ++s) {
+      int64_t patch = b * num_samples + s;
+      const int* o = origins + patch * rank;
+      int od = rank == 3 ? o[0] : 0, oh = o[rank - 2], ow = o[rank - 1];
+      int pd = d - od, ph = h - oh, pw = w - ow;
+      if (pd >= 0 && pd < r0 && ph >= 0 && ph < roi && pw >= 0 && pw < roi)
+        acc += to_f(dpatch[((((patch * r0) + pd) * roi + ph) * roi + pw) * C + c]);
+    }
+    dvol[i] = from_f<T>(acc);
+  }
+}
+
+static inline int ew_grid(int64_t total) {
+  int64_t b = ceil_div(total, 256);
+  int64_t cap = (int64_t)num_sms() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace mpgan
+
+using namespace mpgan;
+
+extern "C" int mpgan_linear_fwd(int dtype, const void* x, const void* w, const float* bias, float* y,
+                                int32_t batch, int64_t k, int32_t j, void* stream) {
+  MPGAN_REQUIRE(batch > 0 && k > 0 && j > 0 && batch <= 65535, MPGAN_ERR_SHAPE, "linear_fwd: bad shape");
+  dim3 grid((unsigned)ceil_div(k, kLinK), (unsigned)batch);
+  MPGAN_DISPATCH_DTYPE(dtype, T, {
+    linear_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)w, bias, y, k, j);
+    MPGAN_CHECK_LAUNCH("linear_fwd");
+    return 0;
+  });
+}
+
+extern "C" int mpgan_linear_bwd(int dtype, const void* x, const void* w, const float* dy, void* dx, float* dw,
+                                float* db, int32_t batch, int64_t k, int32_t j, void* stream) {
+  MPGAN_REQUIRE(batch > 0 && k > 0 && j > 0 && dy, MPGAN_ERR_SHAPE, "linear_bwd: bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  MPGAN_DISPATCH_DTYPE(dtype, T, {
+    if (dx) {
+      linear_dx_kernel<T><<<ew_grid((int64_t)batch * k), 256, 0, s>>>((const T*)w, dy, (T*)dx, batch, k, j);
+      MPGAN_CHECK_LAUNCH("linear_dx");
+    }
+    if (dw) {
+      linear_dw_kernel<T><<<ew_grid((int64_t)j * k), 256, 0, s>>>((const T*)x, dy, dw, batch, k, j);
+      MPGAN_CHECK_LAUNCH("linear_dw");
+    }
+    if (db) {
+      linear_db_kernel<<<(j + 63) / 64, 64, 0, s>>>(dy, db, batch, j);
+      MPGAN_CHECK_LAUNCH("linear_db");
+    }
+    return 0;
+  });
+}
+
+extern "C" int mpgan_sigmoid_fwd(const float* z, float* prob, int32_t n, void* stream) {
+  MPGAN_REQUIRE(n > 0 && z && prob, MPGAN_ERR_SHAPE, "sigmoid_fwd: bad arguments");
+  sigmoid_fwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(z, prob, n);
+  MPGAN_CHECK_LAUNCH("sigmoid_fwd");
+  return 0;
+}
+
+extern "C" int mpgan_sigmoid_bwd(const float* dprob, const float* prob, float* dz, int32_t n, void* stream) {
+  MPGAN_REQUIRE(n > 0 && dprob && prob && dz, MPGAN_ERR_SHAPE, "sigmoid_bwd: bad arguments");
+  sigmoid_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dprob, prob, dz, n);
+  MPGAN_CHECK_LAUNCH("sigmoid_bwd");
+  return 0;
+}
+
+extern "C" int mpgan_bce_fwd(const float* prob, const float* target, float weight, float* loss, int32_t n,
+                             void* stream) {
+  MPGAN_REQUIRE(n > 0 && prob && target && loss, MPGAN_ERR_SHAPE, "bce_fwd: bad arguments");
+  bce_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(prob, target, weight, loss, n);
+  MPGAN_CHECK_LAUNCH("bce_fwd");
+  return 0;
+}
+
+extern "C" int mpgan_bce_bwd(const float* prob, const float* target, float weight, const float* gscale,
+                             float* dprob, int32_t n, void* stream) {
+  MPGAN_REQUIRE(n > 0 && prob && target && dprob, MPGAN_ERR_SHAPE, "bce_bwd: bad arguments");
+  bce_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prob, target, weight, gscale, dprob, n);
+  MPGAN_CHECK_LAUNCH("bce_bwd");
+  return 0;
+}
+
+extern "C" int mpgan_l1_fwd(int dtype, const void* a, const void* b, int64_t n, float weight, float* loss,
+                            void* stream) {
+  MPGAN_REQUIRE(n > 0 && a && b && loss, MPGAN_ERR_SHAPE, "l1_fwd: bad arguments");
+  int grid = ew_grid(n);
+  if (grid > num_sms() * 4) grid = num_sms() * 4;
+  MPGAN_DISPATCH_DTYPE(dtype, T, {
+    l1_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, n, weight / (float)n, loss);
+    MPGAN_CHECK_LAUNCH("l1_fwd");
+    return 0;
+  });
+}
+
+extern "C" int mpgan_l1_bwd(int dtype, const void* a, const void* b, int64_t n, float weight, const float* gscale,
+                            void* da, int accumulate, void* stream) {
+  MPGAN_REQUIRE(n > 0 && a && b && da, MPGAN_ERR_SHAPE, "l1_bwd: bad arguments");
+  MPGAN_DISPATCH_DTYPE(dtype, T, {
+    l1_bwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, n, weight / (float)n,
+                                                                 gscale, (T*)da, accumulate);
+    MPGAN_CHECK_LAUNCH("l1_bwd");
+    return 0;
+  });
+}
+
+extern "C" int mpgan_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                               float lr, float beta1, float beta2, float eps, float* state, void* bf16_shadow,
+                               void* stream) {
+  MPGAN_REQUIRE(n > 0 && state && param && grad && exp_avg && exp_avg_sq, MPGAN_ERR_SHAPE, "adam: bad arguments");
+  adam_prep_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2);
+  MPGAN_CHECK_LAUNCH("adam_prep");
+  adam_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
+                                                           state, (bf16*)bf16_shadow);
+  MPGAN_CHECK_LAUNCH("adam");
+  return 0;
+}
+
+extern "C" int mpgan_patch_gather(int dtype, const void* vol, int32_t batch, int32_t rank, const int32_t* spatial,
+                                  int32_t c, const int32_t* origins, int32_t num_samples, int32_t roi, void* out,
+                                  void* stream) {
+  MPGAN_REQUIRE((rank == 2 || rank == 3) && batch > 0 && c > 0 && num_samples > 0 && roi > 0 && spatial && origins,
+                MPGAN_ERR_SHAPE, "patch_gather: bad arguments");
+  int s0 = rank == 3 ? spatial[0] : 1, s1 = spatial[rank - 2], s2 = spatial[rank - 1];
+  int64_t total = (int64_t)batch * num_samples * (rank == 3 ? roi : 1) * roi * roi * c;
+  MPGAN_DISPATCH_DTYPE(dtype, T, {
+    patch_gather_kernel<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)vol, rank, s0, s1, s2, c,
+                                                                           origins, num_samples, roi, (T*)out, total);
+    MPGAN_CHECK_LAUNCH("patch_gather");
+    return 0;
+  });
+}
+
+extern "C" int mpgan_patch_scatter_add(int dtype, const void* dpatch, int32_t batch, int32_t rank,
+                                       const int32_t* spatial, int32_t c, const int32_t* origins,
+                                       int32_t num_samples, int32_t roi, void* dvol, void* stream) {
+  MPGAN_REQUIRE((rank == 2 || rank == 3) && batch > 0 && c > 0 && num_samples > 0 && roi > 0 && spatial && origins,
+                MPGAN_ERR_SHAPE, "patch_scatter_add: bad arguments");
+  int s0 = rank == 3 ? spatial[0] : 1, s1 = spatial[rank - 2], s2 = spatial[rank - 1];
+  int64_t total = (int64_t)batch * s0 * s1 * s2 * c;
+  MPGAN_DISPATCH_DTYPE(dtype, T, {
+    patch_scatter_kernel<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)dpatch, rank, s0, s1, s2, c,
+                                                                            origins, num_samples, roi, (T*)dvol, total);
+    MPGAN_CHECK_LAUNCH("patch_scatter_add");
+    return 0;
+  });
+}

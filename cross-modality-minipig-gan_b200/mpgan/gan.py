@@ -1,0 +1,335 @@
+"""``GAN``: the reference's LightningModule surface on top of the B200 kernel plans.
+
+Mirrors /root/reference/code/GAN/GAN_final.py:212-308 (variant="final": BCE + L1, full-image discriminator) and
+/root/reference/test_runs/GAN.py:236-447 (variant="perceptual": patch discriminator, discriminator-feature
+"perceptual" loss, L1 on patches).  Two ways to drive it:
+
+* the reference's own protocol -- ``training_step(batch, batch_idx, optimizer_idx)`` returns a loss tensor, the
+  caller runs ``loss.backward()`` / ``optimizer.step()`` / ``zero_grad()`` (``fit_batch`` below is the
+  pytorch-lightning 1.2.1 two-optimizer loop, with ``toggle_optimizer`` semantics);
+* ``fused_step(batch)`` -- the same arithmetic as one static sequence of kernels with no autograd and no host
+  synchronisation, which ``capture()`` records into a CUDA graph.  ``bench.py`` times this path.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .nets import CasNetGenerator, Discriminator, PatchDiscriminator, DEFAULT_PRECISION
+from .runtime import FlatAdam
+
+
+class _Hparams(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+class _BCE(torch.autograd.Function):
+    """F.binary_cross_entropy(y_hat, y) (mean) with torch's log clamp (GAN_final.py:244-245)."""
+
+    @staticmethod
+    def forward(ctx, prob, target):
+        p = prob.detach().float().contiguous()
+        t = target.detach().float().contiguous().expand_as(p).contiguous()
+        loss = torch.zeros((), dtype=torch.float32, device=p.device)
+        ops.bce_fwd(p, t, 1.0, loss)
+        ctx.save_for_backward(p, t)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        p, t = ctx.saved_tensors
+        d = ops.bce_bwd(p, t, 1.0, g.contiguous(), torch.empty_like(p))
+        return d, None
+
+
+class _L1(torch.autograd.Function):
+    """F.l1_loss(y_hat, y) (mean) (GAN_final.py:247-248)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ac, bc = a.detach().float().contiguous(), b.detach().float().contiguous()
+        loss = torch.zeros((), dtype=torch.float32, device=ac.device)
+        ops.l1_fwd(ac, bc, 1.0, loss)
+        ctx.save_for_backward(ac, bc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous()
+        da = ops.l1_bwd(a, b, 1.0, g, torch.empty_like(a), False) if ctx.needs_input_grad[0] else None
+        db = ops.l1_bwd(b, a, 1.0, g, torch.empty_like(b), False) if ctx.needs_input_grad[1] else None
+        return da, db
+
+
+class GAN(nn.Module):
+    def __init__(self, channels, width, height, depth=None, latent_dim: int = 100, d_lr: float = 0.0005,
+                 g_lr: float = 0.0005, b1: float = 0.5, b2: float = 0.999, batch_size: int = 64,
+                 example_data=None, one_sided_label_value=0.9, variant="final", lr=None, precision=None,
+                 n_unet_blocks=None, num_samples=128, roi=16, **kwargs):
+        super().__init__()
+        assert variant in ("final", "perceptual")
+        self.variant = variant
+        if variant == "perceptual":  # test_runs/GAN.py:238-250: a single lr (2e-4) for both optimisers
+            g_lr = d_lr = 0.0002 if lr is None else lr
+        self.hparams = _Hparams(latent_dim=latent_dim, g_lr=g_lr, d_lr=d_lr, b1=b1, b2=b2, batch_size=batch_size,
+                                one_sided_label_value=one_sided_label_value)
+        data_shape = (channels, width, height) if depth is None else (channels, width, height, depth)
+        self.dims = len(data_shape) - 1
+        self.precision = precision or DEFAULT_PRECISION
+        self.num_samples, self.roi = num_samples, roi
+        if variant == "final":
+            self.generator = CasNetGenerator(img_shape=data_shape, n_unet_blocks=n_unet_blocks or 6,
+                                             precision=self.precision)
+            # the reference hard-codes the Linear fan-in for 128^3 inputs (GAN_final.py:201); it is derived from
+            # `width` here so that other (and 2-D) sizes work -- identical at the reference's own 128^3
+            self.discriminator = Discriminator(img_shape=data_shape, precision=self.precision, spatial=width)
+        else:
+            self.generator = CasNetGenerator(img_shape=data_shape, n_unet_blocks=n_unet_blocks or 4,
+                                             channels=(32, 64, 128, 256), strides=(2, 2, 2, 2),
+                                             precision=self.precision)
+            self.discriminator = PatchDiscriminator(img_shape=data_shape, spatial=roi, precision=self.precision)
+        if example_data is not None and variant == "final":
+            self.example_input_array_test = example_data[0]["t1w"]
+            self.example_input_array_train = example_data[1]["t1w"]
+        self.logged = {}
+        self._rng = np.random.RandomState()  # RandSpatialCropSamplesd's unseeded RandomState
+        self._opt = None
+        self._graph = None
+        self.comm = None  # set by mpgan.ddp.attach()
+
+    # ---------------------------------------------------------------- reference surface
+    def forward(self, x):
+        return self.generator(x)
+
+    def adversarial_loss(self, y_hat, y):
+        return _BCE.apply(y_hat, y)
+
+    def reconstruction_loss(self, y_hat, y):
+        return _L1.apply(y_hat, y)
+
+    def perceptual_loss(self, y_hat_activations, y_activations):
+        assert set(y_activations.keys()) == set(y_hat_activations.keys())
+        running_sum = torch.zeros(1, dtype=torch.float32, device=y_hat_activations[0].device)
+        for key in y_activations.keys():
+            running_sum = running_sum + _L1.apply(y_activations[key], y_hat_activations[key]) / y_activations[key].numel()
+        return running_sum
+
+    def log(self, name, value, **kw):
+        self.logged[name] = value.detach()
+
+    def sample_patch_origins(self, batch, spatial):
+        o = np.empty((batch, self.num_samples, len(spatial)), dtype=np.int64)
+        for b in range(batch):
+            for s in range(self.num_samples):
+                for d, size in enumerate(spatial):
+                    o[b, s, d] = self._rng.randint(0, size - self.roi + 1)
+        return o
+
+    def _patches(self, vol, origins_dev):
+        """(B,1,*S) -> (B*num_samples,1,roi..) via the gather kernel (C == 1: NCHW and channels-last coincide)."""
+        b, sp = vol.shape[0], tuple(vol.shape[2:])
+        v = vol.contiguous().reshape((b,) + sp + (1,))
+        return _PatchGather.apply(v, origins_dev, self.num_samples, self.roi).reshape(
+            (b * self.num_samples, 1) + (self.roi,) * len(sp))
+
+    def training_step(self, batch, batch_idx, optimizer_idx, patch_origins=None):
+        t1, t2 = batch["t1w"], batch["t2w"]
+        n = t1.shape[0]
+        dev = t1.device
+        if self.variant == "final":
+            if optimizer_idx == 0:
+                gen = self(t1)
+                self.generated_imgs = gen
+                valid = torch.ones(n, 1, device=dev)
+                g_adv = self.adversarial_loss(self.discriminator(gen), valid)
+                self.log("g_adv_loss", g_adv)
+                g_rec = self.reconstruction_loss(gen, t2)
+                self.log("g_recon_loss", g_rec)
+                g_loss = g_adv + g_rec
+                self.log("g_loss", g_loss)
+                return g_loss
+            valid = torch.ones(n, 1, device=dev) * self.hparams.one_sided_label_value
+            real_loss = self.adversarial_loss(self.discriminator(t2), valid)
+            fake = torch.zeros(n, 1, device=dev)
+            fake_loss = self.adversarial_loss(self.discriminator(self(t1).detach()), fake)
+            d_loss = (real_loss + fake_loss) / 2
+            self.log("d_loss", d_loss)
+            return d_loss
+        # ---- perceptual variant (test_runs/GAN.py:300-438): the prologue runs for both optimizer indices
+        gen = self(t1)
+        self.generated_imgs = gen
+        if patch_origins is None:
+            patch_origins = self.sample_patch_origins(n, tuple(t1.shape[2:]))
+        o_dev = torch.as_tensor(np.asarray(patch_origins).reshape(-1, self.dims), dtype=torch.int32, device=dev)
+        fake_p, real_p = self._patches(gen, o_dev), self._patches(t2, o_dev)
+        m = fake_p.shape[0]
+        if optimizer_idx == 0:
+            out_f, acts_f = self.discriminator(fake_p)
+            _, acts_r = self.discriminator(real_p)
+            g_perc = self.perceptual_loss(acts_f, acts_r)
+            self.log("g_perceptual_loss", g_perc)
+            g_adv = self.adversarial_loss(out_f, torch.ones(m, 1, device=dev))
+            self.log("g_adv_loss", g_adv)
+            g_rec = self.reconstruction_loss(fake_p, real_p)
+            self.log("g_recon_loss", g_rec)
+            g_loss = g_adv + g_rec + g_perc
+            self.log("g_loss", g_loss)
+            return g_loss
+        valid = torch.ones(m, 1, device=dev) * self.hparams.one_sided_label_value
+        real_loss = self.adversarial_loss(self.discriminator(real_p)[0], valid)
+        fake_loss = self.adversarial_loss(self.discriminator(fake_p)[0], torch.zeros(m, 1, device=dev))
+        d_loss = (real_loss + fake_loss) / 2
+        self.log("d_loss", d_loss)
+        return d_loss
+
+    def configure_optimizers(self):
+        hp = self.hparams
+        opt_g = FlatAdam(self.generator, lr=hp.g_lr, betas=(hp.b1, hp.b2))
+        opt_d = FlatAdam(self.discriminator, lr=hp.d_lr, betas=(hp.b1, hp.b2))
+        return [opt_g, opt_d], []
+
+    def on_epoch_end(self):
+        """GAN_final.py:310-317: two extra train-mode generator forwards (they update the BN running stats);
+        returns the images instead of writing them to TensorBoard."""
+        outs = []
+        for name in ("example_input_array_test", "example_input_array_train"):
+            x = getattr(self, name, None)
+            if x is not None:
+                outs.append(self(x.to(self.discriminator.model_conv[0].weight.device).float()))
+        return outs
+
+    # ---------------------------------------------------------------- Lightning 1.2.1 loop
+    def fit_batch(self, batch, batch_idx=0, optimizers=None, patch_origins=None):
+        """toggle_optimizer -> training_step -> backward -> step -> zero_grad -> untoggle, for opt_idx 0 then 1."""
+        if optimizers is None:
+            if self._opt is None:
+                self._opt = self.configure_optimizers()[0]
+            optimizers = self._opt
+        nets = (self.generator, self.discriminator)
+        losses = []
+        for opt_idx, opt in enumerate(optimizers):
+            for i, net in enumerate(nets):
+                for p in net.parameters():
+                    p.requires_grad_(i == opt_idx)
+            kw = {"patch_origins": patch_origins} if self.variant != "final" else {}
+            loss = self.training_step(batch, batch_idx, opt_idx, **kw)
+            loss.backward()
+            if self.comm is not None:
+                self.comm.allreduce(nets[opt_idx].runtime.grad)
+            opt.step()
+            opt.zero_grad()
+            for net in nets:
+                for p in net.parameters():
+                    p.requires_grad_(True)
+            losses.append(loss.detach())
+        return losses
+
+    # ---------------------------------------------------------------- fused static step
+    def _consts(self, n, dev):
+        key = (n, str(dev))
+        c = getattr(self, "_const_cache", None)
+        if c is None or c[0] != key:
+            ones = torch.ones(n, 1, device=dev)
+            c = (key, ones, ones * self.hparams.one_sided_label_value, torch.zeros(n, 1, device=dev))
+            self._const_cache = c
+        return c[1], c[2], c[3]
+
+    def fused_step(self, batch, logs=None):
+        """One full two-optimizer training step (variant "final").  Returns ``logs`` (device fp32):
+        [g_adv, g_recon, d_real/2, d_fake/2];  g_loss = logs[0]+logs[1], d_loss = logs[2]+logs[3]."""
+        assert self.variant == "final", "fused_step covers the GAN_final.py step"
+        t1, t2 = batch["t1w"], batch["t2w"]
+        G, D, hp = self.generator, self.discriminator, self.hparams
+        n, dev = t1.shape[0], t1.device
+        ones, soft, zeros = self._consts(n, dev)
+        if logs is None:
+            logs = torch.zeros(4, dtype=torch.float32, device=dev)
+        else:
+            logs.zero_()
+        t2c = t2.contiguous()
+        # ---- optimizer 0: generator (discriminator frozen: data gradient only)
+        gen, gplan = G.run_forward(t1, save=True, need_wgrad=True)
+        p, dplan = D.run_forward(gen, save=True, need_wgrad=False)
+        ops.bce_fwd(p, ones, 1.0, logs[0:1])
+        ops.l1_fwd(gen, t2c, 1.0, logs[1:2])
+        dprob = ops.bce_bwd(p, ones, 1.0, None, torch.empty_like(p))
+        dgen = D.run_backward(dplan, dprob, need_dx=True)
+        ops.l1_bwd(gen, t2c, 1.0, None, dgen, True)
+        G.run_backward(gplan, dgen, need_dx=False)
+        if self.comm is not None:
+            self.comm.allreduce(G.runtime.grad)
+        G.runtime.adam_step(hp.g_lr, hp.b1, hp.b2)
+        G.runtime.zero_grad()
+        # ---- optimizer 1: discriminator (generator frozen: forward only, train-mode BN)
+        p_real, plan_r = D.run_forward(t2, save=True, need_wgrad=True)
+        ops.bce_fwd(p_real, soft, 0.5, logs[2:3])
+        gen2, _ = G.run_forward(t1, save=False, need_wgrad=False)
+        p_fake, plan_f = D.run_forward(gen2, save=True, need_wgrad=True)
+        ops.bce_fwd(p_fake, zeros, 0.5, logs[3:4])
+        D.run_backward(plan_f, ops.bce_bwd(p_fake, zeros, 0.5, None, torch.empty_like(p_fake)), need_dx=False)
+        D.run_backward(plan_r, ops.bce_bwd(p_real, soft, 0.5, None, torch.empty_like(p_real)), need_dx=False)
+        if self.comm is not None:
+            self.comm.allreduce(D.runtime.grad)
+        D.runtime.adam_step(hp.d_lr, hp.b1, hp.b2)
+        D.runtime.zero_grad()
+        return logs
+
+    def capture(self, batch):
+        """Record ``fused_step`` on static input buffers into a CUDA graph.  Returns (graph, static_batch, logs)."""
+        dev = batch["t1w"].device
+        static = {k: batch[k].clone() for k in ("t1w", "t2w")}
+        logs = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.generator.runtime.ensure(dev)
+        self.discriminator.runtime.ensure(dev)
+        self._consts(static["t1w"].shape[0], dev)
+        snap = self._snapshot()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):  # warm-up (lazy module loading, cudaFuncSetAttribute) outside capture
+            self.fused_step(static, logs)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._restore(snap)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.fused_step(static, logs)
+        self._restore(snap)  # capture does not execute, but keep state exactly as before either way
+        self._graph = (graph, static, logs)
+        return self._graph
+
+    def _snapshot(self):
+        st = []
+        for net in (self.generator, self.discriminator):
+            rt = net.runtime
+            st.append((rt.flat.clone(), rt.exp_avg.clone(), rt.exp_avg_sq.clone(), rt.adam_state.clone(),
+                       [b.clone() for b in net.buffers()]))
+        return st
+
+    def _restore(self, snap):
+        for net, (flat, m, v, a, bufs) in zip((self.generator, self.discriminator), snap):
+            rt = net.runtime
+            rt.flat.copy_(flat), rt.exp_avg.copy_(m), rt.exp_avg_sq.copy_(v), rt.adam_state.copy_(a)
+            rt.grad.zero_()
+            for b, s in zip(net.buffers(), bufs):
+                b.copy_(s)
+            rt.refresh_shadows(force=True)
+
+
+class _PatchGather(torch.autograd.Function):
+    """RandSpatialCropSamplesd + torch.cat (test_runs/GAN.py:313-337): bit-exact gather, deterministic scatter-add."""
+
+    @staticmethod
+    def forward(ctx, vol, origins, num_samples, roi):
+        ctx.save_for_backward(origins)
+        ctx.meta = (tuple(vol.shape), num_samples, roi)
+        return ops.patch_gather(vol.detach().contiguous(), origins, num_samples, roi)
+
+    @staticmethod
+    def backward(ctx, g):
+        (origins,) = ctx.saved_tensors
+        shape, num_samples, roi = ctx.meta
+        dvol = torch.zeros(shape, dtype=g.dtype, device=g.device)
+        ops.patch_scatter_add(g.contiguous(), origins, num_samples, roi, dvol)
+        return dvol, None, None, None

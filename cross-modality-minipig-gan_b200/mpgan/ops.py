@@ -1,0 +1,344 @@
+"""Tensor-level wrappers over the C ABI (include/mpgan.h).  torch is used for device memory and streams only.
+
+Activation tensors are channels-last ``(N, *spatial, C)`` with unit channel stride and pixel-linear leading
+strides (a channel slice of a wider concat buffer is fine).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_PRELU, ACT_TANH, BF16, F32, ConvGeom, check
+
+_NULL = None
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def ld(t):
+    return t.stride(-2) if t.dim() >= 2 else t.shape[-1]
+
+
+def pixels(t):
+    return t.numel() // t.shape[-1]
+
+
+def check_act(t, what="activation"):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: the mpgan kernels have no CPU path")
+    if t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise RuntimeError(f"{what}: channel stride must be 1, got strides {t.stride()}")
+    l = ld(t)
+    exp = l
+    for i in range(t.dim() - 2, -1, -1):
+        if t.shape[i] != 1 and t.stride(i) != exp:
+            raise RuntimeError(f"{what}: not pixel-linear, shape {tuple(t.shape)} strides {t.stride()}")
+        exp *= t.shape[i]
+    return t
+
+
+class ConvSpec:
+    """Geometry of one Conv / ConvTranspose layer in terms of its underlying convolution X -> Y."""
+
+    def __init__(self, rank, cx, cy, k, stride, pad, transposed=False, output_padding=0):
+        self.rank, self.cx, self.cy = rank, cx, cy
+        self.k, self.stride, self.pad = (k,) * rank, (stride,) * rank, (pad,) * rank
+        self.transposed, self.output_padding = transposed, output_padding
+        self.taps = k ** rank
+
+    @classmethod
+    def from_module(cls, m):
+        import torch.nn as nn
+        transposed = isinstance(m, (nn.ConvTranspose2d, nn.ConvTranspose3d))
+        rank = len(m.kernel_size)
+        k, s, p = m.kernel_size[0], m.stride[0], m.padding[0]
+        assert all(v == k for v in m.kernel_size) and all(v == s for v in m.stride) and all(v == p for v in m.padding)
+        if transposed:  # ConvT(in, out): in lives on the Y grid, out on the X grid
+            return cls(rank, m.out_channels, m.in_channels, k, s, p, True, m.output_padding[0])
+        return cls(rank, m.in_channels, m.out_channels, k, s, p, False)
+
+    def y_of_x(self, xs):
+        return tuple((v + 2 * p - k) // s + 1 for v, k, s, p in zip(xs, self.k, self.stride, self.pad))
+
+    def x_of_y(self, ys):
+        return tuple((v - 1) * s - 2 * p + k + self.output_padding
+                     for v, k, s, p in zip(ys, self.k, self.stride, self.pad))
+
+    def geom(self, n, xs, ys):
+        g = ConvGeom()
+        g.rank, g.n, g.cx, g.cy = self.rank, n, self.cx, self.cy
+        pad3 = 3 - self.rank
+        for i in range(3):
+            j = i - pad3
+            g.xs[i] = xs[j] if j >= 0 else 1
+            g.ys[i] = ys[j] if j >= 0 else 1
+            g.k[i] = self.k[j] if j >= 0 else 1
+            g.stride[i] = self.stride[j] if j >= 0 else 1
+            g.pad[i] = self.pad[j] if j >= 0 else 0
+        return g
+
+
+def tc_supported(geom, direction):
+    return bool(_lib.load().mpgan_tc_supported(ctypes.byref(geom), direction))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# convolution.  w: OTI [cy][taps][cx] in the activation dtype; wt: transposed bf16 shadow (tcgen05 bprop)
+# ---------------------------------------------------------------------------------------------------------
+def conv_fprop(spec, x, w, bias, out=None, stats=None, use_tc=True):
+    """X-grid tensor -> Y-grid tensor (Conv forward; ConvTranspose data gradient)."""
+    lib = _lib.require_device()
+    check_act(x, "conv input")
+    n, xs = x.shape[0], tuple(x.shape[1:-1])
+    ys = spec.y_of_x(xs)
+    if out is None:
+        out = torch.empty((n,) + ys + (spec.cy,), dtype=x.dtype, device=x.device)
+    check_act(out, "conv output")
+    g = spec.geom(n, xs, ys)
+    if use_tc and x.dtype == torch.bfloat16 and tc_supported(g, 0):
+        check(lib.mpgan_tc_conv_fprop(ctypes.byref(g), ptr(x), ld(x), ptr(w), ptr(bias), ptr(out), ld(out), ptr(stats),
+                                      _stream()), "tc_conv_fprop")
+        return out, stats is not None
+    check(lib.mpgan_conv_fprop(ctypes.byref(g), dt(x), ptr(x), ld(x), ptr(w), ptr(bias), ptr(out), ld(out), _stream()),
+          "conv_fprop")
+    return out, False
+
+
+def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True):
+    """Y-grid tensor -> X-grid tensor (ConvTranspose forward; Conv data gradient)."""
+    lib = _lib.require_device()
+    check_act(y, "conv input")
+    n, ys = y.shape[0], tuple(y.shape[1:-1])
+    if xs is None:
+        xs = spec.x_of_y(ys)
+    if out is None:
+        out = torch.empty((n,) + tuple(xs) + (spec.cx,), dtype=y.dtype, device=y.device)
+    check_act(out, "conv output")
+    g = spec.geom(n, xs, ys)
+    if use_tc and wt is not None and y.dtype == torch.bfloat16 and tc_supported(g, 1):
+        check(lib.mpgan_tc_conv_bprop(ctypes.byref(g), ptr(y), ld(y), ptr(wt), ptr(bias), ptr(out), ld(out), ptr(stats),
+                                      _stream()), "tc_conv_bprop")
+        return out, stats is not None
+    check(lib.mpgan_conv_bprop(ctypes.byref(g), dt(y), ptr(y), ld(y), ptr(w), ptr(bias), ptr(out), ld(out), _stream()),
+          "conv_bprop")
+    return out, False
+
+
+def conv_wgrad(spec, x, y, dw, use_tc=True):
+    """dw[cy][taps][cx] (fp32, accumulates) from the X-grid tensor and the Y-grid tensor."""
+    lib = _lib.require_device()
+    check_act(x), check_act(y)
+    n, xs, ys = x.shape[0], tuple(x.shape[1:-1]), tuple(y.shape[1:-1])
+    g = spec.geom(n, xs, ys)
+    assert dw.dtype == torch.float32
+    if use_tc and x.dtype == torch.bfloat16 and tc_supported(g, 2):
+        check(lib.mpgan_tc_conv_wgrad(ctypes.byref(g), ptr(x), ld(x), ptr(y), ld(y), ptr(dw), None, 0, _stream()),
+              "tc_conv_wgrad")
+    else:
+        check(lib.mpgan_conv_wgrad(ctypes.byref(g), dt(x), ptr(x), ld(x), ptr(y), ld(y), ptr(dw), _stream()),
+              "conv_wgrad")
+
+
+def colsum(x, out):
+    lib = _lib.require_device()
+    check(lib.mpgan_colsum(dt(x), ptr(x), ld(x), pixels(x), x.shape[-1], ptr(out), _stream()), "colsum")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batch norm + activation
+# ---------------------------------------------------------------------------------------------------------
+def bn_stats(x, stats):
+    lib = _lib.require_device()
+    check(lib.mpgan_bn_stats(dt(x), ptr(x), ld(x), pixels(x), x.shape[-1], ptr(stats), _stream()), "bn_stats")
+
+
+def bn_finalize(stats, npix, bn, training, mean, invstd, scale, shift):
+    lib = _lib.require_device()
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    check(lib.mpgan_bn_finalize(ptr(stats), npix, bn.num_features, ptr(bn.weight), ptr(bn.bias), bn.eps, mom,
+                                1 if training else 0, ptr(bn.running_mean), ptr(bn.running_var),
+                                ptr(bn.num_batches_tracked), ptr(mean), ptr(invstd), ptr(scale), ptr(shift),
+                                _stream()), "bn_finalize")
+
+
+def bn_act_apply(x, scale, shift, act, alpha, leaky, res, out):
+    lib = _lib.require_device()
+    check_act(x), check_act(out)
+    check(lib.mpgan_bn_act_apply(dt(x), ptr(x), ld(x), pixels(x), x.shape[-1], ptr(scale), ptr(shift), act,
+                                 ptr(alpha), leaky, ptr(res), ld(res) if res is not None else 0, ptr(out), ld(out),
+                                 _stream()), "bn_act_apply")
+    return out
+
+
+def bn_act_bwd(dy, x, mean, invstd, scale, shift, act, alpha, leaky, sums, dgamma, dbeta, dalpha, dx):
+    lib = _lib.require_device()
+    check_act(dy), check_act(x), check_act(dx)
+    c = x.shape[-1]
+    check(lib.mpgan_bn_act_bwd_reduce(dt(x), ptr(dy), ld(dy), ptr(x), ld(x), pixels(x), c, ptr(mean), ptr(invstd),
+                                      ptr(scale), ptr(shift), act, ptr(alpha), leaky, ptr(sums), _stream()),
+          "bn_act_bwd_reduce")
+    check(lib.mpgan_bn_act_bwd_apply(dt(x), ptr(dy), ld(dy), ptr(x), ld(x), pixels(x), c, ptr(mean), ptr(invstd),
+                                     ptr(scale), ptr(shift), act, ptr(alpha), leaky, ptr(sums), ptr(dgamma),
+                                     ptr(dbeta), ptr(dalpha), ptr(dx), ld(dx), _stream()), "bn_act_bwd_apply")
+    return dx
+
+
+def act_bwd(dy, z, act, leaky, dx):
+    """dx = dy * act'(z) for a parameter-free activation (LeakyReLU backward on a saved pre-activation)."""
+    lib = _lib.require_device()
+    check_act(dy), check_act(z), check_act(dx)
+    dummy = torch.zeros(1, dtype=torch.float64, device=z.device)
+    check(lib.mpgan_bn_act_bwd_apply(dt(z), ptr(dy), ld(dy), ptr(z), ld(z), pixels(z), z.shape[-1], None, None, None,
+                                     None, act, None, leaky, ptr(dummy), None, None, None, ptr(dx), ld(dx), _stream()),
+          "act_bwd")
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------------------
+# elementwise
+# ---------------------------------------------------------------------------------------------------------
+def add_copy(a, b, out):
+    """out = a (+ b) over channels-last tensors with independent pixel strides / dtypes (a, b same dtype)."""
+    lib = _lib.require_device()
+    check_act(a), check_act(out)
+    if b is not None:
+        check_act(b)
+        assert b.dtype == a.dtype
+    check(lib.mpgan_add_copy(dt(a), ptr(a), ld(a), ptr(b), ld(b) if b is not None else 0, dt(out), ptr(out), ld(out),
+                             pixels(a), a.shape[-1], _stream()), "add_copy")
+    return out
+
+
+def tanh_fwd(x, out):
+    lib = _lib.require_device()
+    assert x.is_contiguous() and out.is_contiguous()
+    check(lib.mpgan_tanh_fwd(dt(x), ptr(x), dt(out), ptr(out), x.numel(), _stream()), "tanh_fwd")
+    return out
+
+
+def tanh_bwd(dy, y, dx):
+    lib = _lib.require_device()
+    assert dy.is_contiguous() and y.is_contiguous() and dx.is_contiguous() and dy.dtype == y.dtype == dx.dtype
+    check(lib.mpgan_tanh_bwd(dt(dy), ptr(dy), ptr(y), ptr(dx), dy.numel(), _stream()), "tanh_bwd")
+    return dx
+
+
+def cast(src, dst):
+    lib = _lib.require_device()
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    check(lib.mpgan_cast(dt(src), ptr(src), dt(dst), ptr(dst), src.numel(), _stream()), "cast")
+    return dst
+
+
+def weight_transpose(src, dst, cy, taps, cx):
+    lib = _lib.require_device()
+    check(lib.mpgan_weight_transpose(dt(src), ptr(src), dt(dst), ptr(dst), cy, taps, cx, _stream()), "weight_transpose")
+    return dst
+
+
+def permute_flatten(src, dst, rows, c, spatial, to_cl, accumulate=False):
+    lib = _lib.require_device()
+    check(lib.mpgan_permute_flatten(dt(src), ptr(src), dt(dst), ptr(dst), rows, c, spatial, 1 if to_cl else 0,
+                                    1 if accumulate else 0, _stream()), "permute_flatten")
+    return dst
+
+
+# ---------------------------------------------------------------------------------------------------------
+# linear, losses, optimiser, patches
+# ---------------------------------------------------------------------------------------------------------
+def linear_fwd(x, w, bias, y):
+    """x (B,K) and w (J,K) share dtype and flatten order; y (B,J) fp32 must be zeroed by the caller."""
+    lib = _lib.require_device()
+    b, k = x.shape
+    check(lib.mpgan_linear_fwd(dt(x), ptr(x), ptr(w), ptr(bias), ptr(y), b, k, w.shape[0], _stream()), "linear_fwd")
+    return y
+
+
+def linear_bwd(x, w, dy, dx, dw, db):
+    lib = _lib.require_device()
+    b, k = x.shape
+    check(lib.mpgan_linear_bwd(dt(x), ptr(x), ptr(w), ptr(dy), ptr(dx), ptr(dw), ptr(db), b, k, w.shape[0],
+                               _stream()), "linear_bwd")
+
+
+def sigmoid_fwd(z, p):
+    lib = _lib.require_device()
+    check(lib.mpgan_sigmoid_fwd(ptr(z), ptr(p), z.numel(), _stream()), "sigmoid_fwd")
+    return p
+
+
+def sigmoid_bwd(dp, p, dz):
+    lib = _lib.require_device()
+    check(lib.mpgan_sigmoid_bwd(ptr(dp), ptr(p), ptr(dz), p.numel(), _stream()), "sigmoid_bwd")
+    return dz
+
+
+def bce_fwd(prob, target, weight, loss):
+    lib = _lib.require_device()
+    check(lib.mpgan_bce_fwd(ptr(prob), ptr(target), weight, ptr(loss), prob.numel(), _stream()), "bce_fwd")
+
+
+def bce_bwd(prob, target, weight, gscale, dprob):
+    lib = _lib.require_device()
+    check(lib.mpgan_bce_bwd(ptr(prob), ptr(target), weight, ptr(gscale), ptr(dprob), prob.numel(), _stream()),
+          "bce_bwd")
+    return dprob
+
+
+def l1_fwd(a, b, weight, loss):
+    lib = _lib.require_device()
+    assert a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype
+    check(lib.mpgan_l1_fwd(dt(a), ptr(a), ptr(b), a.numel(), weight, ptr(loss), _stream()), "l1_fwd")
+
+
+def l1_bwd(a, b, weight, gscale, da, accumulate):
+    lib = _lib.require_device()
+    assert a.is_contiguous() and b.is_contiguous() and da.is_contiguous() and a.dtype == b.dtype == da.dtype
+    check(lib.mpgan_l1_bwd(dt(a), ptr(a), ptr(b), a.numel(), weight, ptr(gscale), ptr(da), 1 if accumulate else 0,
+                           _stream()), "l1_bwd")
+    return da
+
+
+def adam_step(param, grad, m, v, lr, b1, b2, eps, state, shadow=None):
+    lib = _lib.require_device()
+    check(lib.mpgan_adam_step(ptr(param), ptr(grad), ptr(m), ptr(v), param.numel(), lr, b1, b2, eps, ptr(state),
+                              ptr(shadow), _stream()), "adam_step")
+
+
+def patch_gather(vol, origins, num_samples, roi, out=None):
+    """vol (B,*S,C) channels-last contiguous; origins int32 device (B*num_samples, rank)."""
+    lib = _lib.require_device()
+    assert vol.is_contiguous() and origins.dtype == torch.int32 and origins.is_contiguous()
+    b, sp, c = vol.shape[0], tuple(vol.shape[1:-1]), vol.shape[-1]
+    rank = len(sp)
+    if out is None:
+        out = torch.empty((b * num_samples,) + (roi,) * rank + (c,), dtype=vol.dtype, device=vol.device)
+    spatial = (ctypes.c_int32 * rank)(*sp)
+    check(lib.mpgan_patch_gather(dt(vol), ptr(vol), b, rank, spatial, c, ptr(origins), num_samples, roi, ptr(out),
+                                 _stream()), "patch_gather")
+    return out
+
+
+def patch_scatter_add(dpatch, origins, num_samples, roi, dvol):
+    lib = _lib.require_device()
+    assert dvol.is_contiguous() and dpatch.is_contiguous() and origins.dtype == torch.int32
+    b, sp, c = dvol.shape[0], tuple(dvol.shape[1:-1]), dvol.shape[-1]
+    rank = len(sp)
+    spatial = (ctypes.c_int32 * rank)(*sp)
+    check(lib.mpgan_patch_scatter_add(dt(dvol), ptr(dpatch), b, rank, spatial, c, ptr(origins), num_samples, roi,
+                                      ptr(dvol), _stream()), "patch_scatter_add")
+    return dvol

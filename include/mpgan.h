@@ -1,0 +1,167 @@
+/*
+ * mpgan.h -- C ABI of libmpgan_sm100.so: the B200 (sm_100a) kernels behind the GAN hot path of
+ * mbrzus/Cross-Modality-Minipig-Gan.
+ *
+ * The reference has no FFI seam for this path: its arithmetic is PyTorch ops called from plain Python
+ * classes.  Each entry point below replaces the torch op(s) named in its comment
+ * (file:line into /root/reference).  Conventions:
+ *   - extern "C", plain pointers and sizes only; the caller owns every buffer (device memory unless noted).
+ *   - activations are channels-last: (N, [D,] H, W, C) with a pixel stride `ld*` in elements (>= C), so a
+ *     tensor may be a channel slice of a wider concat buffer.
+ *   - conv weights are "OTI": [Cy][tap][Cx] (taps in (kd,kh,kw) order) for the underlying convolution
+ *     X-grid -> Y-grid; a ConvTranspose is the same weight used in the Y -> X direction.
+ *   - dtype: MPGAN_F32 or MPGAN_BF16 for activations/weights; statistics, losses, master weights and
+ *     gradients of parameters are always fp32 (batch-norm sums fp64).
+ *   - every call is asynchronous on `stream` (a cudaStream_t), never synchronises or allocates, and is
+ *     CUDA-graph-capture safe.  Return 0 on success; <0 on error, text via mpgan_last_error().
+ *   - no CPU fallback exists: on a machine without a B200 the compute entry points fail with MPGAN_ERR_CUDA.
+ */
+#ifndef MPGAN_H_
+#define MPGAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPGAN_VERSION 100
+
+enum { MPGAN_OK = 0, MPGAN_ERR_SHAPE = -1, MPGAN_ERR_UNSUPPORTED = -2, MPGAN_ERR_CUDA = -3 };
+enum { MPGAN_F32 = 0, MPGAN_BF16 = 1 };
+enum { MPGAN_ACT_NONE = 0, MPGAN_ACT_PRELU = 1, MPGAN_ACT_LEAKY = 2, MPGAN_ACT_TANH = 3 };
+
+/* Geometry of the underlying convolution X-grid -> Y-grid (y = x*stride - pad + r). rank 2 uses index 1,2 of
+ * the 3-vectors (index 0: size 1, k 1, stride 1, pad 0). */
+typedef struct {
+  int32_t rank;       /* 2 or 3 spatial dims */
+  int32_t n;          /* batch */
+  int32_t xs[3];      /* X-grid spatial extent (D,H,W) */
+  int32_t ys[3];      /* Y-grid spatial extent */
+  int32_t cx, cy;     /* channels on the X / Y side */
+  int32_t k[3], stride[3], pad[3];
+} MpganConvGeom;
+
+int mpgan_version(void);
+const char* mpgan_last_error(void);
+/* 1 if a CUDA device of compute capability 10.x is usable by this process, else 0 (never raises). */
+int mpgan_device_ok(void);
+
+/* ---- convolution, generic CUDA-core path (any channel count, rank 2/3, f32 or bf16 storage, fp32 accumulate) ----
+ * nn.Conv3d/Conv2d forward  (GAN_final.py:167-189, MONAI Convolution via GAN_final.py:106-114)  = fprop
+ * nn.ConvTranspose forward  (MONAI up path)                                                       = bprop
+ * and their data gradients (torch autograd's convolution_backward) the other way round.
+ * `w` is OTI [cy][taps][cx] in `dtype`; bias fp32 [channels of the output side] or NULL. */
+int mpgan_conv_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* w,
+                     const float* bias, void* y, int64_t ldy, void* stream);
+int mpgan_conv_bprop(const MpganConvGeom* g, int dtype, const void* y, int64_t ldy, const void* w,
+                     const float* bias, void* x, int64_t ldx, void* stream);
+/* dw[cy][taps][cx] += sum_pixels y (x) x   (fp32, accumulates: the caller zeroes);  weight gradient of both
+ * Conv and ConvTranspose. */
+int mpgan_conv_wgrad(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* y, int64_t ldy,
+                     float* dw, void* stream);
+
+/* ---- convolution, tcgen05 path (bf16 operands, fp32 TMEM accumulators, TMA-staged NHWC tiles; rank 2) ----
+ * Same contracts as above with dtype == BF16.  Requirements: cx, cy multiples of 16 (>= 16).
+ * w_f is OTI [cy][taps][cx] bf16 (used by fprop); w_b is its transpose [cx][taps][cy] bf16 (used by bprop).
+ * Optional fused epilogue: bias add and per-channel batch-norm partial sums (sum, sum of squares of the
+ * stored bf16 values) accumulated into stats[2*C] (fp64, caller zeroes) when stats != NULL. */
+int mpgan_tc_supported(const MpganConvGeom* g, int direction /*0 fprop,1 bprop,2 wgrad*/);
+int mpgan_tc_conv_fprop(const MpganConvGeom* g, const void* x, int64_t ldx, const void* w_f, const float* bias,
+                        void* y, int64_t ldy, double* stats, void* stream);
+int mpgan_tc_conv_bprop(const MpganConvGeom* g, const void* y, int64_t ldy, const void* w_b, const float* bias,
+                        void* x, int64_t ldx, double* stats, void* stream);
+/* workspace_bytes from mpgan_tc_conv_wgrad_workspace(); dw accumulates (fp32 [cy][taps][cx]). */
+size_t mpgan_tc_conv_wgrad_workspace(const MpganConvGeom* g);
+int mpgan_tc_conv_wgrad(const MpganConvGeom* g, const void* x, int64_t ldx, const void* y, int64_t ldy, float* dw,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* ---- batch norm (nn.BatchNorm3d, GAN_final.py:170-188; MONAI norm=BATCH) + activation, fused ----
+ * stats: per-channel sum / sum-of-squares in fp64 (accumulates; caller zeroes). */
+int mpgan_bn_stats(int dtype, const void* x, int64_t ldx, int64_t pixels, int32_t c, double* stats, void* stream);
+/* training: batch mean / biased var -> scale=gamma*invstd, shift=beta-mean*scale; saves mean, invstd;
+ * running_mean/var updated with `momentum` (unbiased var), num_batches_tracked (int64) += 1.
+ * eval (training==0): scale/shift from the running statistics; stats may be NULL. */
+int mpgan_bn_finalize(const double* stats, int64_t pixels, int32_t c, const float* gamma, const float* beta,
+                      float eps, float momentum, int training, float* running_mean, float* running_var,
+                      int64_t* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
+                      void* stream);
+/* y = act(x*scale[c] + shift[c]) (+ res).  act: NONE, PRELU (slope read from *alpha), LEAKY (slope = *alpha
+ * when alpha != NULL else 0.2), TANH.  scale/shift may be NULL (identity).  res may be NULL. */
+int mpgan_bn_act_apply(int dtype, const void* x, int64_t ldx, int64_t pixels, int32_t c, const float* scale,
+                       const float* shift, int act, const float* alpha, float leaky_slope, const void* res,
+                       int64_t ldres, void* y, int64_t ldy, void* stream);
+/* backward of y = act(bn(x)): pass 1 reduces  sums[0:C]=sum g, sums[C:2C]=sum g*xhat, sums[2C]=sum dy*min(z,0)
+ * (PReLU slope grad), all fp64 accumulating;  pass 2 writes dx and accumulates dgamma/dbeta/dalpha (fp32). */
+int mpgan_bn_act_bwd_reduce(int dtype, const void* dy, int64_t lddy, const void* x, int64_t ldx, int64_t pixels,
+                            int32_t c, const float* mean, const float* invstd, const float* scale,
+                            const float* shift, int act, const float* alpha, float leaky_slope, double* sums,
+                            void* stream);
+int mpgan_bn_act_bwd_apply(int dtype, const void* dy, int64_t lddy, const void* x, int64_t ldx, int64_t pixels,
+                           int32_t c, const float* mean, const float* invstd, const float* scale,
+                           const float* shift, int act, const float* alpha, float leaky_slope, const double* sums,
+                           float* dgamma, float* dbeta, float* dalpha, void* dx, int64_t lddx, void* stream);
+
+/* ---- elementwise helpers on channels-last tensors ---- */
+/* y[p, 0:c] = a[p, 0:c] (+ b[p, 0:c]) with independent pixel strides (residual add, concat copy, casts). */
+int mpgan_add_copy(int dtype_in, const void* a, int64_t lda, const void* b, int64_t ldb, int dtype_out, void* y,
+                   int64_t ldy, int64_t pixels, int32_t c, void* stream);
+/* nn.Tanh (GAN_final.py:117) forward and backward on a flat tensor: y = tanh(x);  dx = dy*(1-y^2). */
+int mpgan_tanh_fwd(int dtype_in, const void* x, int dtype_out, void* y, int64_t n, void* stream);
+int mpgan_tanh_bwd(int dtype, const void* dy, const void* y, void* dx, int64_t n, void* stream);
+/* per-channel column sum: out[c] += sum_p x[p,c]  (conv bias gradient). fp32 accumulate into out. */
+int mpgan_colsum(int dtype, const void* x, int64_t ldx, int64_t pixels, int32_t c, float* out, void* stream);
+
+/* ---- nn.Linear after Flatten (GAN_final.py:200-201; test_runs/GAN.py:176-181) ----
+ * x: (batch, k) in `dtype` (channels-last flatten order), w: (j, k) in `dtype` pre-permuted to the same order,
+ * bias fp32 (j) or NULL, y fp32 (batch, j).  fwd accumulates into y (caller zeroes y). */
+int mpgan_linear_fwd(int dtype, const void* x, const void* w, const float* bias, float* y, int32_t batch,
+                     int64_t k, int32_t j, void* stream);
+/* dx (batch,k) `dtype` = dy (batch,j) fp32 * w;   dw (j,k) fp32 += dy^T x;  db (j) += sum dy.  NULL skips. */
+int mpgan_linear_bwd(int dtype, const void* x, const void* w, const float* dy, void* dx, float* dw, float* db,
+                     int32_t batch, int64_t k, int32_t j, void* stream);
+/* (c, spatial) <-> (spatial, c) permutation of each row of a (rows, c*spatial) matrix, with dtype conversion:
+ * to_cl=1: dst[r][s][c] = src[r][c][s];  to_cl=0: dst[r][c][s] (+)= src[r][s][c]. */
+int mpgan_permute_flatten(int dtype_src, const void* src, int dtype_dst, void* dst, int32_t rows, int32_t c,
+                          int64_t spatial, int to_cl, int accumulate, void* stream);
+
+/* ---- losses ----
+ * nn.Sigmoid (GAN_final.py:203) on the (n) fp32 logits and its backward dz = dprob * p * (1-p). */
+int mpgan_sigmoid_fwd(const float* z, float* prob, int32_t n, void* stream);
+int mpgan_sigmoid_bwd(const float* dprob, const float* prob, float* dz, int32_t n, void* stream);
+/* F.binary_cross_entropy (GAN_final.py:244-245) on probabilities, torch's clamp semantics:
+ * loss += weight * mean(-(t*max(log p,-100) + (1-t)*max(log1p(-p),-100)));  loss (1) fp32 accumulates.
+ * backward: dprob = gscale * weight/n * (p - t)/max(p(1-p), 1e-12)   (gscale: device scalar or NULL = 1). */
+int mpgan_bce_fwd(const float* prob, const float* target, float weight, float* loss, int32_t n, void* stream);
+int mpgan_bce_bwd(const float* prob, const float* target, float weight, const float* gscale, float* dprob,
+                  int32_t n, void* stream);
+/* F.l1_loss (GAN_final.py:247-248): loss += weight * mean|a-b| ;  da = gscale*weight/n * sign(a-b) */
+int mpgan_l1_fwd(int dtype, const void* a, const void* b, int64_t n, float weight, float* loss, void* stream);
+int mpgan_l1_bwd(int dtype, const void* a, const void* b, int64_t n, float weight, const float* gscale, void* da,
+                 int accumulate, void* stream);
+
+/* ---- torch.optim.Adam (GAN_final.py:298-308), one launch over a flat fp32 buffer ----
+ * state: 3 device floats {step count (int bits), step_size, sqrt(1-beta2^t)}; zero-initialised by the caller.
+ * The call increments the device-side step count first (so a captured CUDA graph advances it on replay), then
+ * applies exp_avg/exp_avg_sq/param updates with torch's formula.  Optionally writes a bf16 shadow copy. */
+int mpgan_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float* state, void* bf16_shadow, void* stream);
+/* dst = cast(src) for flat buffers (f32 <-> bf16). */
+int mpgan_cast(int dtype_src, const void* src, int dtype_dst, void* dst, int64_t n, void* stream);
+/* OTI [cy][taps][cx] -> transposed shadow [cx][taps][cy] with dtype conversion. */
+int mpgan_weight_transpose(int dtype_src, const void* src, int dtype_dst, void* dst, int32_t cy, int32_t taps,
+                           int32_t cx, void* stream);
+
+/* ---- RandSpatialCropSamplesd gather (test_runs/GAN.py:263-272,313-337), bit-exact copy ----
+ * vol: (batch, *S, c) channels-last; origins: device int32 (batch*num_samples, rank) in (D,H,W) order;
+ * out: (batch*num_samples, roi.., c).  scatter_add is its deterministic backward (dvol += patches). */
+int mpgan_patch_gather(int dtype, const void* vol, int32_t batch, int32_t rank, const int32_t* spatial, int32_t c,
+                       const int32_t* origins, int32_t num_samples, int32_t roi, void* out, void* stream);
+int mpgan_patch_scatter_add(int dtype, const void* dpatch, int32_t batch, int32_t rank, const int32_t* spatial,
+                            int32_t c, const int32_t* origins, int32_t num_samples, int32_t roi, void* dvol,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPGAN_H_ */

@@ -1,0 +1,360 @@
+"""Per-kernel parity on the GPU, through the C ABI, against plain torch fp32 references of the same op."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+from mpgan import ops  # noqa: E402
+from mpgan._lib import ACT_LEAKY, ACT_NONE, ACT_PRELU  # noqa: E402
+
+DEV = "cuda"
+
+
+def cl(x, dtype=torch.float32):
+    """NC[D]HW -> channels-last contiguous in `dtype`."""
+    nd = x.dim() - 2
+    return x.permute((0,) + tuple(range(2, nd + 2)) + (1,)).contiguous().to(dtype)
+
+
+def uncl(x):
+    nd = x.dim() - 2
+    return x.float().permute((0, nd + 1) + tuple(range(1, nd + 1))).contiguous()
+
+
+def oti(w, dtype=torch.float32):
+    nd = w.dim() - 2
+    return w.permute((0,) + tuple(range(2, nd + 2)) + (1,)).contiguous().to(dtype)
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.rand(shape, generator=g) * 2 - 1).to(DEV)
+
+
+CONV_CASES = [
+    # rank, n, cin, cout, size, k, s, p
+    (2, 2, 1, 16, 20, 3, 2, 1),
+    (2, 2, 1, 64, 19, 3, 1, 0),
+    (2, 3, 16, 16, 17, 3, 1, 1),
+    (2, 2, 32, 1, 16, 3, 1, 1),
+    (2, 2, 24, 40, 13, 4, 2, 0),
+    (2, 2, 64, 128, 8, 1, 1, 0),
+    (3, 2, 1, 8, 9, 3, 2, 1),
+    (3, 1, 6, 10, 8, 3, 1, 0),
+    (3, 2, 8, 8, 7, 4, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_generic_fwd_dgrad_wgrad(case, dtype):
+    rank, n, cin, cout, size, k, s, p = case
+    conv = F.conv2d if rank == 2 else F.conv3d
+    x = rnd(n, cin, *([size] * rank), seed=1)
+    w = rnd(cout, cin, *([k] * rank), seed=2) * 0.2
+    b = rnd(cout, seed=3)
+    if dtype == torch.bfloat16:
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    x.requires_grad_(True), w.requires_grad_(True)
+    y = conv(x, w, b, stride=s, padding=p)
+    dy = rnd(*y.shape, seed=4)
+    if dtype == torch.bfloat16:
+        dy = dy.bfloat16().float()
+    y.backward(dy)
+    spec = ops.ConvSpec(rank, cin, cout, k, s, p)
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    yk, _ = ops.conv_fprop(spec, cl(x.detach(), dtype), oti(w.detach(), dtype), b, use_tc=False)
+    assert rel_l2(uncl(yk), y) <= tol
+    dxk, _ = ops.conv_bprop(spec, cl(dy, dtype), oti(w.detach(), dtype), None, None, xs=(size,) * rank, use_tc=False)
+    assert rel_l2(uncl(dxk), x.grad) <= tol
+    dw = torch.zeros(cout, k ** rank, cin, device=DEV)
+    ops.conv_wgrad(spec, cl(x.detach(), dtype), cl(dy, dtype), dw, use_tc=False)
+    assert rel_l2(dw, oti(w.grad)) <= (1e-4 if dtype == torch.float32 else 6e-3)
+    db = torch.zeros(cout, device=DEV)
+    ops.colsum(cl(dy, dtype), db)
+    assert rel_l2(db, dy.sum(dim=[0] + list(range(2, rank + 2)))) <= 1e-4
+
+
+def test_conv_transpose_is_bprop():
+    """ConvTranspose2d(k3,s2,p1,op1) forward == bprop of the underlying conv with the same OTI weight."""
+    ct = torch.nn.ConvTranspose2d(24, 8, 3, stride=2, padding=1, output_padding=1).to(DEV)
+    x = rnd(2, 24, 9, 9, seed=5)
+    y = ct(x)
+    spec = ops.ConvSpec.from_module(ct)
+    assert spec.transposed and spec.cx == 8 and spec.cy == 24
+    yk, _ = ops.conv_bprop(spec, cl(x), oti(ct.weight.detach()), None, ct.bias.detach(), use_tc=False)
+    assert yk.shape == (2, 18, 18, 8)
+    assert rel_l2(uncl(yk), y) <= 1e-5
+
+
+def test_conv_channel_slices_of_concat_buffer():
+    x = rnd(2, 16, 12, 12, seed=6)
+    w = rnd(8, 16, 3, 3, seed=7) * 0.2
+    y = F.conv2d(x, w, None, padding=1)
+    big_in = torch.zeros(2, 12, 12, 40, device=DEV)
+    big_in[..., 8:24] = cl(x)
+    big_out = torch.full((2, 12, 12, 24), 7.0, device=DEV)
+    spec = ops.ConvSpec(2, 16, 8, 3, 1, 1)
+    ops.conv_fprop(spec, big_in[..., 8:24], oti(w), None, out=big_out[..., 16:24], use_tc=False)
+    assert rel_l2(uncl(big_out[..., 16:24]), y) <= 1e-5
+    assert torch.all(big_out[..., :16] == 7.0)
+
+
+# ------------------------------------------------------------------ tcgen05 path
+TC_CASES = [
+    # n, cin, cout, h, w, k, s, p
+    (2, 64, 128, 30, 30, 3, 1, 0),      # D layer 2 family (valid padding, odd extents)
+    (2, 128, 256, 30, 30, 4, 2, 0),     # D layer 3 family (k4 s2: parity maps)
+    (3, 256, 256, 29, 29, 4, 2, 0),     # D layer 4 family (odd input)
+    (2, 16, 16, 32, 32, 3, 1, 1),       # G: 32-byte swizzle, padding via OOB fill
+    (2, 16, 32, 32, 32, 3, 2, 1),       # G down, stride 2 with padding
+    (2, 32, 64, 16, 16, 3, 2, 1),
+    (2, 64, 128, 8, 8, 1, 1, 0),        # 1x1 residual conv == plain GEMM
+    (2, 128, 128, 8, 8, 3, 1, 1),
+    (5, 256, 512, 10, 10, 3, 1, 0),     # patch-D layer 4: two N tiles, tiny images
+    (1, 192, 32, 6, 6, 3, 1, 1),        # three 64-channel chunks
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tc_conv_fprop(case):
+    n, cin, cout, h, w_, k, s, p = case
+    x = rnd(n, cin, h, w_, seed=11).bfloat16()
+    w = (rnd(cout, cin, k, k, seed=12) * 0.1).bfloat16()
+    b = rnd(cout, seed=13)
+    ref = F.conv2d(x.float(), w.float(), b, stride=s, padding=p)
+    spec = ops.ConvSpec(2, cin, cout, k, s, p)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    y, fused = ops.conv_fprop(spec, cl(x, torch.bfloat16), oti(w, torch.bfloat16), b, stats=stats)
+    assert fused, "tcgen05 path was not taken"
+    torch.cuda.synchronize()
+    assert rel_l2(uncl(y), ref) <= 6e-3
+    yr = uncl(y).double()
+    assert rel_l2(stats[:cout], yr.sum(dim=(0, 2, 3))) <= 1e-4
+    assert rel_l2(stats[cout:], (yr * yr).sum(dim=(0, 2, 3))) <= 1e-4
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tc_conv_bprop(case):
+    n, cin, cout, h, w_, k, s, p = case
+    oh, ow = (h + 2 * p - k) // s + 1, (w_ + 2 * p - k) // s + 1
+    dy = rnd(n, cout, oh, ow, seed=14).bfloat16()
+    w = (rnd(cout, cin, k, k, seed=15) * 0.1).bfloat16()
+    ref = torch.nn.grad.conv2d_input((n, cin, h, w_), w.float(), dy.float(), stride=s, padding=p)
+    spec = ops.ConvSpec(2, cin, cout, k, s, p)
+    wt = torch.empty(w.numel(), dtype=torch.bfloat16, device=DEV)
+    ops.weight_transpose(oti(w, torch.bfloat16), wt, cout, k * k, cin)
+    dx, _ = ops.conv_bprop(spec, cl(dy, torch.bfloat16), oti(w, torch.bfloat16), wt, None, xs=(h, w_))
+    torch.cuda.synchronize()
+    assert rel_l2(uncl(dx), ref) <= 6e-3
+
+
+@pytest.mark.parametrize("case", [c for c in TC_CASES if c[1] in (64, 128, 256)])
+def test_tc_conv_wgrad(case):
+    n, cin, cout, h, w_, k, s, p = case
+    oh, ow = (h + 2 * p - k) // s + 1, (w_ + 2 * p - k) // s + 1
+    x = rnd(n, cin, h, w_, seed=16).bfloat16()
+    dy = rnd(n, cout, oh, ow, seed=17).bfloat16()
+    ref = torch.nn.grad.conv2d_weight(x.float(), (cout, cin, k, k), dy.float(), stride=s, padding=p)
+    spec = ops.ConvSpec(2, cin, cout, k, s, p)
+    dw = torch.zeros(cout, k * k, cin, device=DEV)
+    ops.conv_wgrad(spec, cl(x, torch.bfloat16), cl(dy, torch.bfloat16), dw)
+    torch.cuda.synchronize()
+    assert rel_l2(dw, oti(ref)) <= 2e-3
+    ops.conv_wgrad(spec, cl(x, torch.bfloat16), cl(dy, torch.bfloat16), dw)  # accumulates
+    assert rel_l2(dw, 2 * oti(ref)) <= 2e-3
+
+
+def test_tc_conv_full_size_linearity():
+    """BASELINE-size D layer 3 (32 x 252^2 x 128 -> 125^2 x 256): checked through linearity and a sampled window."""
+    n, cin, cout, h = 8, 128, 256, 252
+    x1, x2 = rnd(n, h, h, cin, seed=21).bfloat16(), rnd(n, h, h, cin, seed=22).bfloat16()
+    w = (rnd(cout, 16, cin, seed=23) * 0.05).bfloat16()
+    spec = ops.ConvSpec(2, cin, cout, 4, 2, 0)
+    y1, _ = ops.conv_fprop(spec, x1, w, None)
+    y2, _ = ops.conv_fprop(spec, x2, w, None)
+    y12, _ = ops.conv_fprop(spec, (x1.float() + x2.float()).bfloat16(), w, None)
+    assert y1.shape == (n, 125, 125, cout)
+    assert rel_l2(y12.float(), y1.float() + y2.float()) <= 2e-2
+    ref = F.conv2d(uncl(x1)[:1, :, :40, :40], w.view(cout, 4, 4, cin).permute(0, 3, 1, 2).float(), stride=2)
+    assert rel_l2(uncl(y1)[:1, :, :19, :19], ref) <= 6e-3
+
+
+# ------------------------------------------------------------------ batch norm / activations
+@pytest.mark.parametrize("c,act", [(1, ACT_PRELU), (16, ACT_PRELU), (64, ACT_LEAKY), (24, ACT_NONE), (512, ACT_LEAKY)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bn_act_forward_backward(c, act, dtype):
+    n, h, w_ = 3, 9, 11
+    x = (rnd(n, c, h, w_, seed=31) * 2 + 0.3)
+    res = rnd(n, c, h, w_, seed=32)
+    if dtype == torch.bfloat16:
+        x, res = x.bfloat16().float(), res.bfloat16().float()
+    x.requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(c).to(DEV)
+    with torch.no_grad():
+        bn.weight.copy_(rnd(c, seed=33) + 1.5), bn.bias.copy_(rnd(c, seed=34))
+    bn_k = torch.nn.BatchNorm2d(c).to(DEV)
+    bn_k.load_state_dict(bn.state_dict())
+    alpha = torch.nn.Parameter(torch.tensor([0.25], device=DEV))
+    z = bn(x)
+    yr = F.prelu(z, alpha) if act == ACT_PRELU else (F.leaky_relu(z, 0.2) if act == ACT_LEAKY else z)
+    yr = yr + res
+    dy = rnd(n, c, h, w_, seed=35)
+    if dtype == torch.bfloat16:
+        dy = dy.bfloat16().float()
+    yr.backward(dy)
+    # kernels
+    xc = cl(x.detach(), dtype)
+    stats = torch.zeros(2 * c, dtype=torch.float64, device=DEV)
+    ops.bn_stats(xc, stats)
+    buf = torch.empty(4, c, device=DEV)
+    ops.bn_finalize(stats, n * h * w_, bn_k, True, buf[0], buf[1], buf[2], buf[3])
+    a = alpha.detach() if act == ACT_PRELU else None
+    y = ops.bn_act_apply(xc, buf[2], buf[3], act, a, 0.2, cl(res, dtype), torch.empty_like(xc))
+    tol = 2e-5 if dtype == torch.float32 else 8e-3
+    assert rel_l2(uncl(y), yr) <= tol
+    assert rel_l2(bn_k.running_mean, bn.running_mean) <= 1e-5 and rel_l2(bn_k.running_var, bn.running_var) <= 1e-5
+    assert int(bn_k.num_batches_tracked) == 1
+    sums = torch.zeros(2 * c + 1, dtype=torch.float64, device=DEV)
+    dg, db, da = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV), torch.zeros(1, device=DEV)
+    dx = ops.bn_act_bwd(cl(dy, dtype), xc, buf[0], buf[1], buf[2], buf[3], act, a, 0.2, sums, dg, db, da,
+                        torch.empty_like(xc))
+    btol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert rel_l2(uncl(dx), x.grad) <= btol
+    assert rel_l2(dg, bn.weight.grad) <= 1e-4 and rel_l2(db, bn.bias.grad) <= 1e-4
+    if act == ACT_PRELU:
+        assert rel_l2(da, alpha.grad) <= 1e-4
+
+
+def test_bn_eval_mode():
+    c = 16
+    bn = torch.nn.BatchNorm2d(c).to(DEV).eval()
+    with torch.no_grad():
+        bn.running_mean.copy_(rnd(c, seed=41)), bn.running_var.copy_(rnd(c, seed=42).abs() + 0.5)
+    x = rnd(2, c, 6, 6, seed=43)
+    buf = torch.empty(4, c, device=DEV)
+    ops.bn_finalize(None, 72, bn, False, buf[0], buf[1], buf[2], buf[3])
+    y = ops.bn_act_apply(cl(x), buf[2], buf[3], ACT_NONE, None, 0.0, None, torch.empty_like(cl(x)))
+    assert rel_l2(uncl(y), bn(x)) <= 1e-5
+    assert int(bn.num_batches_tracked) == 0
+
+
+# ------------------------------------------------------------------ linear / losses / adam / patches
+@pytest.mark.parametrize("b,c,s,j", [(4, 8, 100, 1), (3, 16, 9, 64), (2, 256, 61 * 61, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_after_flatten(b, c, s, j, dtype):
+    k = c * s
+    lin = torch.nn.Linear(k, j).to(DEV)
+    h = rnd(b, c, s, seed=51)           # NCHW-flatten order (c, spatial)
+    if dtype == torch.bfloat16:
+        h = h.bfloat16().float()
+        with torch.no_grad():
+            lin.weight.copy_(lin.weight.bfloat16().float())
+    h.requires_grad_(True)
+    z = lin(h.reshape(b, -1))
+    dz = rnd(b, j, seed=52)
+    z.backward(dz)
+    hcl = h.detach().permute(0, 2, 1).contiguous().reshape(b, -1).to(dtype)   # (spatial, c) order
+    wcl = ops.permute_flatten(lin.weight.detach(), torch.empty(j, k, dtype=dtype, device=DEV), j, c, s, True)
+    zk = ops.linear_fwd(hcl, wcl, lin.bias.detach(), torch.zeros(b, j, device=DEV))
+    tol = 2e-5 if dtype == torch.float32 else 2e-3
+    assert rel_l2(zk, z) <= tol
+    dx, dwcl, dbias = torch.empty_like(hcl), torch.zeros(j, k, device=DEV), torch.zeros(j, device=DEV)
+    ops.linear_bwd(hcl, wcl, dz, dx, dwcl, dbias)
+    dw = ops.permute_flatten(dwcl, torch.zeros(j, k, device=DEV), j, c, s, False, True)
+    assert rel_l2(dw, lin.weight.grad) <= tol and rel_l2(dbias, lin.bias.grad) <= 1e-5
+    assert rel_l2(dx.float().reshape(b, s, c).permute(0, 2, 1), h.grad) <= (tol if dtype == torch.float32 else 8e-3)
+
+
+def test_sigmoid_bce_matches_torch_including_clamp():
+    z = torch.tensor([[-200.0], [-20.0], [-1.0], [0.0], [0.3], [30.0], [200.0]], device=DEV, requires_grad=True)
+    for target in (1.0, 0.9, 0.0):
+        t = torch.full_like(z, target)
+        p = torch.sigmoid(z)
+        ref = F.binary_cross_entropy(p, t)
+        (gz,) = torch.autograd.grad(ref, z)
+        pk = ops.sigmoid_fwd(z.detach().contiguous(), torch.empty_like(z))
+        loss = torch.zeros(1, device=DEV)
+        ops.bce_fwd(pk, t, 1.0, loss)
+        assert torch.equal(pk, p.detach())
+        assert abs(float(loss) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+        dz = ops.sigmoid_bwd(ops.bce_bwd(pk, t, 1.0, None, torch.empty_like(pk)), pk, torch.empty_like(pk))
+        assert torch.allclose(dz, gz, rtol=1e-5, atol=1e-7)
+    # saturated discriminator: clamped loss is exactly 100 and the gradient vanishes
+    zs = torch.full((4, 1), -500.0, device=DEV)
+    ps = ops.sigmoid_fwd(zs, torch.empty_like(zs))
+    loss = torch.zeros(1, device=DEV)
+    ops.bce_fwd(ps, torch.ones_like(ps), 1.0, loss)
+    assert float(loss) == 100.0
+    dz = ops.sigmoid_bwd(ops.bce_bwd(ps, torch.ones_like(ps), 1.0, None, torch.empty_like(ps)), ps, torch.empty_like(ps))
+    assert float(dz.abs().max()) == 0.0
+
+
+def test_l1_and_tanh():
+    a, b = rnd(3, 1, 17, 19, seed=61).requires_grad_(True), rnd(3, 1, 17, 19, seed=62)
+    ref = F.l1_loss(a, b)
+    (ga,) = torch.autograd.grad(ref, a)
+    loss = torch.zeros(1, device=DEV)
+    ops.l1_fwd(a.detach(), b, 1.0, loss)
+    assert abs(float(loss) - float(ref)) <= 1e-6
+    da = ops.l1_bwd(a.detach(), b, 1.0, None, torch.zeros_like(b), False)
+    assert torch.allclose(da, ga)
+    x = rnd(1000, seed=63) * 3
+    y = ops.tanh_fwd(x, torch.empty_like(x))
+    assert torch.allclose(y, torch.tanh(x), atol=1e-6)
+    dy = rnd(1000, seed=64)
+    assert torch.allclose(ops.tanh_bwd(dy, y, torch.empty_like(x)), dy * (1 - torch.tanh(x) ** 2), atol=1e-6)
+
+
+def test_adam_matches_torch_over_steps():
+    n = 10007
+    p = torch.nn.Parameter(rnd(n, seed=71))
+    opt = torch.optim.Adam([p], lr=5e-4, betas=(0.5, 0.999))
+    pk, m, v = p.detach().clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    state = torch.zeros(4, device=DEV)
+    shadow = torch.zeros(n, dtype=torch.bfloat16, device=DEV)
+    for step in range(5):
+        g = rnd(n, seed=80 + step) * (10.0 ** (step - 2))
+        p.grad = g.clone()
+        opt.step()
+        ops.adam_step(pk, g, m, v, 5e-4, 0.5, 0.999, 1e-8, state, shadow)
+        assert rel_l2(pk, p.detach()) <= 1e-6
+    assert torch.equal(shadow, pk.bfloat16())
+    assert int(state[0].view(torch.int32)) == 5
+
+
+@pytest.mark.parametrize("rank", [2, 3])
+def test_patch_gather_bit_exact_and_scatter_add(rank):
+    b, ns, roi = 3, 7, 16
+    sp = (40, 37) if rank == 2 else (20, 18, 21)
+    vol = rnd(b, *sp, 1, seed=91)
+    rng = np.random.RandomState(2)
+    o = np.stack([rng.randint(0, s - roi + 1, size=(b, ns)) for s in sp], axis=-1)
+    o_dev = torch.as_tensor(o.reshape(-1, rank), dtype=torch.int32, device=DEV)
+    out = ops.patch_gather(vol, o_dev, ns, roi)
+    for bi in range(b):
+        for si in range(ns):
+            sl = tuple(slice(int(v), int(v) + roi) for v in o[bi, si])
+            assert torch.equal(out[bi * ns + si], vol[bi][sl])   # bit exact
+    g = rnd(*out.shape, seed=92)
+    dvol = ops.patch_scatter_add(g, o_dev, ns, roi, torch.zeros_like(vol))
+    ref = torch.zeros_like(vol)
+    for bi in range(b):
+        for si in range(ns):
+            sl = tuple(slice(int(v), int(v) + roi) for v in o[bi, si])
+            ref[bi][sl] += g[bi * ns + si]
+    assert torch.allclose(dvol, ref, atol=1e-5)
+    again = ops.patch_scatter_add(g, o_dev, ns, roi, torch.zeros_like(vol))
+    assert torch.equal(dvol, again)   # deterministic
+
+
+def test_empty_and_bad_inputs_raise():
+    with pytest.raises(RuntimeError):
+        ops.cast(torch.empty(0, device=DEV), torch.empty(0, dtype=torch.bfloat16, device=DEV))
+    spec = ops.ConvSpec(2, 4, 4, 3, 1, 0)
+    with pytest.raises(RuntimeError):
+        ops.conv_fprop(spec, torch.zeros(1, 5, 5, 4), torch.zeros(4, 9, 4, device=DEV), None)  # CPU tensor
