@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py -- GAN train image-pairs/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- the GAN_final.py two-optimizer training step
+(G = 6 x UNet(16,32,64,128) + tanh, D = 4 x conv/BN/LeakyReLU + Linear + sigmoid, BCE + L1, Adam x 2) on a batch
+of 32 synthetic 256x256 T1/T2 slices per GPU, bf16 operands / fp32 accumulation, weights random-init (seed 0).
+N > 1 (torchrun) = configs[3]: weak scaling, 32 pairs per rank, flat-bucket NCCL gradient all-reduce per network.
+
+value  : device-resident inputs, the fused step replayed from a CUDA graph, CUDA-event timed, max over ranks.
+e2e    : the same step driven from pinned HOST buffers (H2D of both image batches and D2H of the loss scalars
+         inside the timed region every step).
+roofline: the tcgen05 implicit-GEMM conv kernel on D's 128->256 k4 s2 layer (the FLOP-dominant launch), timed
+         alone with CUDA events; FLOPs are algorithmic (2 * pixels * Cout * taps * Cin).
+cpu_baseline / --impl reference: the reference path (oracle = the reference's classes restated, pinned against
+         them in tests/golden) on the host cores, batch 1 per step (BASELINE.json configs[0]).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "cross-modality-minipig-gan_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+SIZE, BATCH = 256, 32
+G_FWD_MAC, D_FWD_MAC = 3_621_126_144, 16_813_888_000          # SURVEY.md section 8d (per 256^2 sample)
+FLOP_PER_PAIR = 2 * (4 * G_FWD_MAC + 8 * D_FWD_MAC)            # 2.980e11
+METRIC, UNIT = "gan_train_image_pairs_per_sec", "image-pairs/s"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_run(steps, warmup):
+    """The reference path on the host cores: oracle two-optimizer step, batch 1, 256x256, fp32."""
+    from oracle.gan import GANOracle, lightning_step, synthetic_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = GANOracle("final", dims=2, spatial=SIZE)
+    opts, _ = model.configure_optimizers()
+    batch = synthetic_batch(1, 2, SIZE, seed=1)
+    for i in range(warmup):
+        lightning_step(model, opts, batch, i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        lightning_step(model, opts, batch, warmup + i)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms, cores = cpu_reference_run(args.steps, args.warmup)
+    sample = f"{args.steps} two-optimizer steps of batch 1 at {SIZE}x{SIZE} (fp32, torch CPU, {cores} threads)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "GAN_final.py train step (G 6xUNet + D, BCE+L1, Adam x2), CPU, batch 1, 256x256"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def time_dominant_kernel(device, reps=20):
+    """D layer 3 (128 -> 256, k4 s2, 252^2 -> 125^2) forward through the tcgen05 kernel, alone."""
+    from mpgan import ops
+    n, cin, cout, h = BATCH, 128, 256, 252
+    x = torch.randn(n, h, h, cin, device=device).bfloat16()          # 520 MB > L2
+    w = (torch.randn(cout, 16, cin, device=device) * 0.05).bfloat16()
+    spec = ops.ConvSpec(2, cin, cout, 4, 2, 0)
+    y, _ = ops.conv_fprop(spec, x, w, None)
+    for _ in range(3):
+        ops.conv_fprop(spec, x, w, None, out=y)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.conv_fprop(spec, x, w, None, out=y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * n * 125 * 125 * cout * 16 * cin
+    del x, y
+    return flops / (ms * 1e-3) / 1e12, ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import mpgan
+    from mpgan import _lib, ddp
+    from oracle.gan import synthetic_batch  # synthetic-input generator only (SURVEY.md section 8d seeds)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, local = 0, 0
+    if world > 1:
+        rank, world, local = ddp.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.require_device()
+
+    torch.manual_seed(0)
+    model = mpgan.GAN(1, SIZE, SIZE, precision=args.precision)
+    host = synthetic_batch(BATCH, 2, SIZE, seed=1 + rank)
+    batch = {k: v.to(dev) for k, v in host.items()}
+    if world > 1:
+        comm = ddp.attach(model)
+        model.generator.runtime.ensure(dev), model.discriminator.runtime.ensure(dev)
+        comm.broadcast_parameters(model)
+
+    calls0 = _lib.ABI_CALLS
+    use_graph = not args.no_graph
+    if use_graph:
+        try:
+            graph, static, logs = model.capture(batch)
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"# CUDA graph capture failed ({e!r}); timing the eager fused step", file=sys.stderr)
+            use_graph = False
+    if not use_graph:
+        static, logs = batch, torch.zeros(4, device=dev)
+        model.fused_step(static, logs)
+    launches_per_step = model.abi_calls_per_step if use_graph else (_lib.ABI_CALLS - calls0)
+
+    def step():
+        if use_graph:
+            graph.replay()
+        else:
+            model.fused_step(static, logs)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    # ---- end to end: pinned host buffers -> device, step, loss scalars back, every step
+    pin = {k: v.pin_memory() for k, v in host.items()}
+    logs_host = torch.zeros(4).pin_memory()
+    for _ in range(2):
+        for k in pin:
+            static[k].copy_(pin[k], non_blocking=True)
+        step()
+        logs_host.copy_(logs, non_blocking=True)
+    sync_all()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        for k in pin:
+            static[k].copy_(pin[k], non_blocking=True)
+        step()
+        logs_host.copy_(logs, non_blocking=True)
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+    final_logs = logs_host.tolist()
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        value = world * BATCH * args.steps / (ms_total * 1e-3)
+        e2e = world * BATCH * args.steps / (ms_e2e * 1e-3)
+        tf, kms = time_dominant_kernel(dev)
+        peak_tf = float(pk["bf16_tflops"])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"GAN_final.py train step (G 6xUNet(16,32,64,128)+tanh, D 4xconv+Linear, BCE+L1, "
+                                   f"Adam x2), batch {BATCH}/GPU of {SIZE}x{SIZE} slices, {args.precision}",
+                       "global_batch": world * BATCH, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (>= 2 GB of activations) far exceeds the 126 MB L2; no flush needed",
+                       "cuda_graph": use_graph, "flop_per_pair": FLOP_PER_PAIR,
+                       "step_tflops": value * FLOP_PER_PAIR / 1e12},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * SIZE * SIZE * 4,
+                    "d2h_bytes_per_step": 16},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel<256,64> (D conv 128->256 k4 s2, batch 32)",
+                         "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                         "peak_kind": f"{pk_kind} burst bf16", "kernel_ms": kms, "traffic": None},
+            "losses": {"g_adv": final_logs[0], "g_recon": final_logs[1], "d_loss": final_logs[2] + final_logs[3]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores = cpu_reference_run(5, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"5 two-optimizer steps of batch 1 at {SIZE}x{SIZE}, fp32 torch CPU "
+                                              f"({ms:.0f} ms/step)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -92,7 +92,12 @@ def last_error():
     return load().mpgan_last_error().decode()
 
 
+ABI_CALLS = 0  # compute entry points invoked by this process (each launches >= 1 kernel of ours)
+
+
 def check(rc, what):
+    global ABI_CALLS
+    ABI_CALLS += 1
     if rc != 0:
         raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}")
 

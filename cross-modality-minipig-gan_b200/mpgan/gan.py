@@ -292,9 +292,12 @@ class GAN(nn.Module):
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._restore(snap)
+        from . import _lib
         graph = torch.cuda.CUDAGraph()
+        calls0 = _lib.ABI_CALLS
         with torch.cuda.graph(graph):
             self.fused_step(static, logs)
+        self.abi_calls_per_step = _lib.ABI_CALLS - calls0
         self._restore(snap)  # capture does not execute, but keep state exactly as before either way
         self._graph = (graph, static, logs)
         return self._graph

@@ -11,6 +11,19 @@ for p in (ROOT, os.path.join(ROOT, "cross-modality-minipig-gan_b200")):
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def _no_tf32():
+    # the torch references must be true fp32 (cuDNN/cuBLAS default to TF32 for convs on Ampere+)
+    try:
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:  # noqa: BLE001
+        pass
+
+
+_no_tf32()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
     config.addinivalue_line("markers", "slow: long CPU test (set MPGAN_SLOW=1 to run)")
