@@ -4,8 +4,8 @@
 //
 // Layout: channels-last (pixels, C) with pixel stride ld.  Vector path: 8 channels per thread (16 B bf16 /
 // 32 B f32) when C, ld are multiples of 8 and the pointers are 16/32-byte aligned; scalar path otherwise (C = 1).
-// Per-channel sums are accumulated per thread in fp32 over a bounded pixel run, reduced in shared memory and
-// added to fp64 global accumulators (one atomic per channel per block).
+// Per-channel sums are accumulated in fp64 end to end (per thread, shared-memory reduce, one global atomic per
+// channel per block): E[x^2]-mean^2 must survive |mean| >> std.
 #include "common.cuh"
 
 namespace mpgan {
@@ -60,7 +60,9 @@ constexpr int kPixPerBlock = 2048;  // pixel run per block for the reductions
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 bn_stats_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, double* __restrict__ stats) {
-  __shared__ float s1[kThreads * V], s2[kThreads * V];
+  // fp64 partial sums: var = E[x^2] - mean^2 cancels catastrophically in fp32 when |mean| >> std (the un-normalised
+  // hand-over between cascaded UNets produces exactly that)
+  __shared__ double s1[kThreads * V], s2[kThreads * V];
   const int cv = C / V;
   const int CL = cv < kThreads ? cv : kThreads;   // channel lanes
   const int PL = kThreads / CL;                   // pixel lanes
@@ -69,15 +71,15 @@ bn_stats_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, double* 
   const int64_t p1 = min(P, p0 + kPixPerBlock);
   for (int cb = 0; cb < cv; cb += CL) {
     const int vc = cb + cl;
-    float a1[V], a2[V];
+    double a1[V], a2[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) a1[i] = a2[i] = 0.f;
+    for (int i = 0; i < V; ++i) a1[i] = a2[i] = 0.0;
     if (pl < PL && vc < cv) {
       for (int64_t p = p0 + pl; p < p1; p += PL) {
         float v[V];
         Vec<T, V>::load(x + p * ldx + (int64_t)vc * V, v);
 #pragma unroll
-        for (int i = 0; i < V; ++i) { a1[i] += v[i]; a2[i] = fmaf(v[i], v[i], a2[i]); }
+        for (int i = 0; i < V; ++i) { a1[i] += (double)v[i]; a2[i] = fma((double)v[i], (double)v[i], a2[i]); }
       }
     }
 #pragma unroll
@@ -87,11 +89,11 @@ bn_stats_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, double* 
     for (int j = threadIdx.x; j < CL * V; j += kThreads) {
       int lane = j / V, e = j % V;
       if (cb + lane < cv) {
-        float t1 = 0.f, t2 = 0.f;
+        double t1 = 0.0, t2 = 0.0;
         for (int q = 0; q < PL; ++q) { t1 += s1[(q * CL + lane) * V + e]; t2 += s2[(q * CL + lane) * V + e]; }
         int ch = (cb + lane) * V + e;
-        atomicAdd(&stats[ch], (double)t1);
-        atomicAdd(&stats[C + ch], (double)t2);
+        atomicAdd(&stats[ch], t1);
+        atomicAdd(&stats[C + ch], t2);
       }
     }
     __syncthreads();
@@ -163,7 +165,7 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
                          int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ scale, const float* __restrict__ shift, int act,
                          const float* __restrict__ alpha, float leaky, double* __restrict__ sums) {
-  __shared__ float s1[kThreads * V], s2[kThreads * V];
+  __shared__ double s1[kThreads * V], s2[kThreads * V];
   __shared__ float red[32];
   const int cv = C / V;
   const int CL = cv < kThreads ? cv : kThreads;
@@ -175,9 +177,9 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
   float aslope = 0.f;
   for (int cb = 0; cb < cv; cb += CL) {
     const int vc = cb + cl;
-    float a1[V], a2[V];
+    double a1[V], a2[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) a1[i] = a2[i] = 0.f;
+    for (int i = 0; i < V; ++i) a1[i] = a2[i] = 0.0;
     if (pl < PL && vc < cv) {
       const int c0 = vc * V;
       float sc[V], sh[V], mu[V], is[V];
@@ -195,8 +197,8 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
           float z = fmaf(xv[e], sc[e], sh[e]);
           if (act == MPGAN_ACT_PRELU && z <= 0.f) aslope = fmaf(g[e], z, aslope);
           float gz = g[e] * act_grad(z, act, slope);
-          a1[e] += gz;
-          a2[e] = fmaf(gz, (xv[e] - mu[e]) * is[e], a2[e]);
+          a1[e] += (double)gz;
+          a2[e] = fma((double)gz, (double)((xv[e] - mu[e]) * is[e]), a2[e]);
         }
       }
     }
@@ -206,11 +208,11 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
     for (int j = threadIdx.x; j < CL * V; j += kThreads) {
       int lane = j / V, e = j % V;
       if (cb + lane < cv) {
-        float t1 = 0.f, t2 = 0.f;
+        double t1 = 0.0, t2 = 0.0;
         for (int q = 0; q < PL; ++q) { t1 += s1[(q * CL + lane) * V + e]; t2 += s2[(q * CL + lane) * V + e]; }
         int ch = (cb + lane) * V + e;
-        atomicAdd(&sums[ch], (double)t1);
-        atomicAdd(&sums[C + ch], (double)t2);
+        atomicAdd(&sums[ch], t1);
+        atomicAdd(&sums[C + ch], t2);
       }
     }
     __syncthreads();

@@ -236,7 +236,7 @@ class GAN(nn.Module):
             self._const_cache = c
         return c[1], c[2], c[3]
 
-    def fused_step(self, batch, logs=None):
+    def fused_step(self, batch, logs=None, grad_probe=None):
         """One full two-optimizer training step (variant "final").  Returns ``logs`` (device fp32):
         [g_adv, g_recon, d_real/2, d_fake/2];  g_loss = logs[0]+logs[1], d_loss = logs[2]+logs[3]."""
         assert self.variant == "final", "fused_step covers the GAN_final.py step"
@@ -258,6 +258,8 @@ class GAN(nn.Module):
         dgen = D.run_backward(dplan, dprob, need_dx=True)
         ops.l1_bwd(gen, t2c, 1.0, None, dgen, True)
         G.run_backward(gplan, dgen, need_dx=False)
+        if grad_probe is not None:  # test hook: look at the gradients before the optimiser consumes them
+            grad_probe("generator", G)
         if self.comm is not None:
             self.comm.allreduce(G.runtime.grad)
         G.runtime.adam_step(hp.g_lr, hp.b1, hp.b2)
@@ -270,6 +272,8 @@ class GAN(nn.Module):
         ops.bce_fwd(p_fake, zeros, 0.5, logs[3:4])
         D.run_backward(plan_f, ops.bce_bwd(p_fake, zeros, 0.5, None, torch.empty_like(p_fake)), need_dx=False)
         D.run_backward(plan_r, ops.bce_bwd(p_real, soft, 0.5, None, torch.empty_like(p_real)), need_dx=False)
+        if grad_probe is not None:
+            grad_probe("discriminator", D)
         if self.comm is not None:
             self.comm.allreduce(D.runtime.grad)
         D.runtime.adam_step(hp.d_lr, hp.b1, hp.b2)

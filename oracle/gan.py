@@ -85,13 +85,13 @@ class GANOracle(nn.Module):
             if optimizer_idx == 0:
                 gen = self(t1)
                 self.generated_imgs = gen
-                g_adv = self.adversarial_loss(self.discriminator(gen), torch.ones(n, 1))
+                g_adv = self.adversarial_loss(self.discriminator(gen), torch.ones(n, 1).type_as(t1))
                 g_rec = self.reconstruction_loss(gen, t2)
                 g_loss = g_adv + g_rec
                 self.log("g_adv_loss", g_adv), self.log("g_recon_loss", g_rec), self.log("g_loss", g_loss)
                 return g_loss
-            real = self.adversarial_loss(self.discriminator(t2), torch.ones(n, 1) * self.one_sided)
-            fake = self.adversarial_loss(self.discriminator(self(t1).detach()), torch.zeros(n, 1))
+            real = self.adversarial_loss(self.discriminator(t2), (torch.ones(n, 1) * self.one_sided).type_as(t1))
+            fake = self.adversarial_loss(self.discriminator(self(t1).detach()), torch.zeros(n, 1).type_as(t1))
             d_loss = (real + fake) / 2
             self.log("d_loss", d_loss)
             return d_loss
@@ -105,14 +105,14 @@ class GANOracle(nn.Module):
             out_f, acts_f = self.discriminator(fake_p)
             _, acts_r = self.discriminator(real_p)
             g_perc = self.perceptual_loss(acts_f, acts_r)
-            g_adv = self.adversarial_loss(out_f, torch.ones(m, 1))
+            g_adv = self.adversarial_loss(out_f, torch.ones(m, 1).type_as(t1))
             g_rec = self.reconstruction_loss(fake_p, real_p)
             g_loss = g_adv + g_rec + g_perc
             self.log("g_perceptual_loss", g_perc), self.log("g_adv_loss", g_adv)
             self.log("g_recon_loss", g_rec), self.log("g_loss", g_loss)
             return g_loss
-        real = self.adversarial_loss(self.discriminator(real_p)[0], torch.ones(m, 1) * self.one_sided)
-        fake = self.adversarial_loss(self.discriminator(fake_p)[0], torch.zeros(m, 1))
+        real = self.adversarial_loss(self.discriminator(real_p)[0], (torch.ones(m, 1) * self.one_sided).type_as(t1))
+        fake = self.adversarial_loss(self.discriminator(fake_p)[0], torch.zeros(m, 1).type_as(t1))
         d_loss = (real + fake) / 2
         self.log("d_loss", d_loss)
         return d_loss
