@@ -166,7 +166,6 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
                          const float* __restrict__ scale, const float* __restrict__ shift, int act,
                          const float* __restrict__ alpha, float leaky, double* __restrict__ sums) {
   __shared__ double s1[kThreads * V], s2[kThreads * V];
-  __shared__ float red[32];
   const int cv = C / V;
   const int CL = cv < kThreads ? cv : kThreads;
   const int PL = kThreads / CL;
@@ -174,7 +173,7 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
   const int64_t p0 = (int64_t)blockIdx.x * kPixPerBlock;
   const int64_t p1 = min(P, p0 + kPixPerBlock);
   const float slope = (act == MPGAN_ACT_PRELU || (act == MPGAN_ACT_LEAKY && alpha)) ? *alpha : leaky;
-  float aslope = 0.f;
+  double aslope = 0.0;
   for (int cb = 0; cb < cv; cb += CL) {
     const int vc = cb + cl;
     double a1[V], a2[V];
@@ -195,7 +194,7 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
 #pragma unroll
         for (int e = 0; e < V; ++e) {
           float z = fmaf(xv[e], sc[e], sh[e]);
-          if (act == MPGAN_ACT_PRELU && z <= 0.f) aslope = fmaf(g[e], z, aslope);
+          if (act == MPGAN_ACT_PRELU && z <= 0.f) aslope = fma((double)g[e], (double)z, aslope);
           float gz = g[e] * act_grad(z, act, slope);
           a1[e] += (double)gz;
           a2[e] = fma((double)gz, (double)((xv[e] - mu[e]) * is[e]), a2[e]);
@@ -217,9 +216,16 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
     }
     __syncthreads();
   }
-  if (act == MPGAN_ACT_PRELU) {
-    float tot = block_sum(aslope, red);
-    if (threadIdx.x == 0) atomicAdd(&sums[2 * C], (double)tot);
+  if (act == MPGAN_ACT_PRELU) {  // block-wide fp64 sum of the slope-gradient partials
+    double w = warp_sum(aslope);
+    __shared__ double dred[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) dred[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < kThreads / 32; ++i) tot += dred[i];
+      atomicAdd(&sums[2 * C], tot);
+    }
   }
 }
 
