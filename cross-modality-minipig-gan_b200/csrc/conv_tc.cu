@@ -281,15 +281,25 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
 
 // ---------------------------------------------------------------------------------------------------------
 // weight gradient:  D_tap[cy(128-block), cx] += sum over 64-pixel tiles  dY^T(tile) * X_tap(tile)
+// One pipeline stage = the dY tile (loaded once) + the X tiles of up to TPS taps; the accumulators of a whole
+// tap group (<= 512 TMEM columns) stay resident while the CTA walks its share of the pixel tiles.
 // ---------------------------------------------------------------------------------------------------------
+template <int NX> struct WgB;   // B operand (X tile of one tap): MN-major, swizzle chosen by the row width
+template <> struct WgB<16>  { static constexpr int BYTES = 64 * 32,  BOXES = 1, BOXC = 16, LAYOUT = 6, SBO = 256,  KSTEP = 512,  LBO = 256,  TPS = 9; };
+template <> struct WgB<32>  { static constexpr int BYTES = 64 * 64,  BOXES = 1, BOXC = 32, LAYOUT = 4, SBO = 512,  KSTEP = 1024, LBO = 512,  TPS = 9; };
+template <> struct WgB<64>  { static constexpr int BYTES = 64 * 128, BOXES = 1, BOXC = 64, LAYOUT = 2, SBO = 1024, KSTEP = 2048, LBO = 8192, TPS = 4; };
+template <> struct WgB<128> { static constexpr int BYTES = 2 * 8192, BOXES = 2, BOXC = 64, LAYOUT = 2, SBO = 1024, KSTEP = 2048, LBO = 8192, TPS = 2; };
+template <> struct WgB<256> { static constexpr int BYTES = 4 * 8192, BOXES = 4, BOXC = 64, LAYOUT = 2, SBO = 1024, KSTEP = 2048, LBO = 8192, TPS = 1; };
+
 template <int NX> struct WgCfg {
+  using B = WgB<NX>;
   static constexpr int A_BYTES = 2 * 64 * 128;         // two 64-channel column groups x 64 pixels x 128 B
-  static constexpr int B_BYTES = (NX / 64) * 64 * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B::TPS * B::BYTES;
   static constexpr int AUX_BYTES = 256;
   static constexpr int MAX_STAGES = (kSmemLimit - 1024 - AUX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + AUX_BYTES;
+  static constexpr int MAX_TPG = 512 / NX;              // taps whose accumulators fit in TMEM
 };
 
 template <int NX>
@@ -298,6 +308,7 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
              const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
              const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmX3) {
   using Cfg = WgCfg<NX>;
+  using B = WgB<NX>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -344,18 +355,22 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
         const int thi = t % P.tiles_h; t /= P.tiles_h;
         const int tni = t;
         const int w0 = twi << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
-        for (int tl = 0; tl < ntap; ++tl) {
-          const int tap = tap0 + tl;
+        for (int tl0 = 0; tl0 < ntap; tl0 += B::TPS) {
+          const int nt = min(B::TPS, ntap - tl0);
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
-          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          mbar_expect_tx(&full[stage], Cfg::A_BYTES + nt * B::BYTES);
           tma_load_4d(sA, &tmY, &full[stage], mb * 128, w0, h0, n0);
           tma_load_4d(sA + 8192, &tmY, &full[stage], mb * 128 + 64, w0, h0, n0);
-          const CUtensorMap* mX = mapsX[P.tap_map[tap]];
+          for (int q = 0; q < nt; ++q) {
+            const int tap = tap0 + tl0 + q;
+            const CUtensorMap* mX = mapsX[P.tap_map[tap]];
 #pragma unroll
-          for (int i = 0; i < NX / 64; ++i)
-            tma_load_4d(sB + i * 8192, mX, &full[stage], i * 64, w0 + P.tap_dw[tap], h0 + P.tap_dh[tap], n0);
+            for (int i = 0; i < B::BOXES; ++i)
+              tma_load_4d(sB + q * B::BYTES + i * 8192, mX, &full[stage], i * 64, w0 + P.tap_dw[tap],
+                          h0 + P.tap_dh[tap], n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -366,17 +381,20 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        for (int tl = 0; tl < ntap; ++tl) {
+        for (int tl0 = 0; tl0 < ntap; tl0 += B::TPS) {
+          const int nt = min(B::TPS, ntap - tl0);
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(tl * NX);
+          for (int q = 0; q < nt; ++q) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((tl0 + q) * NX);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 64 pixels = 4 x K16; 16 rows of 128 B per step
-            const uint64_t adesc = make_smem_desc(a_addr + k * 2048, 8192, 1024, 2);
-            const uint64_t bdesc = make_smem_desc(b_addr + k * 2048, 8192, 1024, 2);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {  // 64 pixels = 4 x K16
+              const uint64_t adesc = make_smem_desc(a_addr + k * 2048, 8192, 1024, 2);
+              const uint64_t bdesc = make_smem_desc(b_addr + q * B::BYTES + k * B::KSTEP, B::LBO, B::SBO, B::LAYOUT);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -392,15 +410,17 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
     for (int tl = 0; tl < ntap; ++tl) {
       const int tap = tap0 + tl;
       float* drow = P.dw + ((long long)m * P.ntaps + tap) * P.cx;
+      constexpr int CH = NX >= 32 ? 32 : 16;
 #pragma unroll 1
-      for (int c0 = 0; c0 < NX; c0 += 32) {
+      for (int c0 = 0; c0 < NX; c0 += CH) {
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * NX + c0), r);
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * NX + c0);
+        if (CH == 32) tmem_ld_32x32(ta, r);
+        else tmem_ld_32x16(ta, r);
         tmem_ld_wait();
         if (m < P.cy) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < P.cx) atomicAdd(drow + c0 + j, __uint_as_float(r[j]));
+          for (int j = 0; j < CH; ++j) atomicAdd(drow + c0 + j, __uint_as_float(r[j]));
         }
       }
     }
@@ -663,7 +683,8 @@ static int launch_wgrad_t(const WgradParams& P, const CUtensorMap& mY, const CUt
 }
 
 static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, int64_t ldy, float* dw, cudaStream_t s) {
-  MPGAN_REQUIRE(g.cx == 64 || g.cx == 128 || g.cx == 256, MPGAN_ERR_UNSUPPORTED, "tc wgrad needs cx in {64,128,256}");
+  MPGAN_REQUIRE(g.cx == 16 || g.cx == 32 || g.cx == 64 || g.cx == 128 || g.cx == 256, MPGAN_ERR_UNSUPPORTED,
+                "tc wgrad needs cx in {16,32,64,128,256}");
   MPGAN_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, MPGAN_ERR_SHAPE, "pixel strides must be multiples of 8 elements");
   WgradParams P;
   memset(&P, 0, sizeof(P));
@@ -679,9 +700,9 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
       ++ntap;
     }
   P.ntaps = ntap;
-  P.taps_per_group = 512 / g.cx;
-  if (P.taps_per_group > ntap) P.taps_per_group = ntap;
-  P.ngroups = (ntap + P.taps_per_group - 1) / P.taps_per_group;
+  const int max_tpg = 512 / g.cx;
+  P.ngroups = (ntap + max_tpg - 1) / max_tpg;
+  P.taps_per_group = (ntap + P.ngroups - 1) / P.ngroups;   // balanced groups
   P.m_blocks = (g.cy + 127) / 128;
   choose_tile(g.yw, g.yh, g.n, 64, &P.tw_log2, &P.th_log2);
   const int tw = 1 << P.tw_log2, th = 1 << P.th_log2, tn = 64 / (tw * th);
@@ -701,10 +722,12 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
     int rc = encode_map(&mY, y, 4, dims, str, box);
     if (rc) return rc;
   }
-  uint32_t boxX[4] = {64u, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+  uint32_t boxX[4] = {(uint32_t)(g.cx < 64 ? g.cx : 64), (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
   int rc = make_act_maps(mX, x, g.n, g.xh, g.xw, g.cx, ldx, g.s, boxX);
   if (rc) return rc;
   switch (g.cx) {
+    case 16: return launch_wgrad_t<16>(P, mY, mX, s);
+    case 32: return launch_wgrad_t<32>(P, mY, mX, s);
     case 64: return launch_wgrad_t<64>(P, mY, mX, s);
     case 128: return launch_wgrad_t<128>(P, mY, mX, s);
     default: return launch_wgrad_t<256>(P, mY, mX, s);
@@ -720,7 +743,7 @@ using namespace mpgan::tc;
 extern "C" int mpgan_tc_supported(const MpganConvGeom* g, int direction) {
   Geom2 g2;
   if (to_geom2(g, &g2) != 0) return 0;
-  if (direction == 2) return (g2.cx == 64 || g2.cx == 128 || g2.cx == 256) ? 1 : 0;
+  if (direction == 2) return (g2.cx == 16 || g2.cx == 32 || g2.cx == 64 || g2.cx == 128 || g2.cx == 256) ? 1 : 0;
   const int N = direction == 0 ? g2.cy : g2.cx;
   if (pick_bn(N) == 0 || N > 512) return 0;
   if (direction == 1 && g2.s == 2 && (g2.kh < 2 || g2.kw < 2)) return 0;

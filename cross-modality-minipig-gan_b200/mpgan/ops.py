@@ -99,7 +99,7 @@ def tc_supported(geom, direction):
 # ---------------------------------------------------------------------------------------------------------
 # convolution.  w: OTI [cy][taps][cx] in the activation dtype; wt: transposed bf16 shadow (tcgen05 bprop)
 # ---------------------------------------------------------------------------------------------------------
-def conv_fprop(spec, x, w, bias, out=None, stats=None, use_tc=True):
+def conv_fprop(spec, x, w, bias, out=None, stats=None, use_tc=True, use_c1=True):
     """X-grid tensor -> Y-grid tensor (Conv forward; ConvTranspose data gradient)."""
     lib = _lib.require_device()
     check_act(x, "conv input")
@@ -113,12 +113,16 @@ def conv_fprop(spec, x, w, bias, out=None, stats=None, use_tc=True):
         check(lib.mpgan_tc_conv_fprop(ctypes.byref(g), ptr(x), ld(x), ptr(w), ptr(bias), ptr(out), ld(out), ptr(stats),
                                       _stream()), "tc_conv_fprop")
         return out, stats is not None
+    if use_c1 and lib.mpgan_c1_supported(ctypes.byref(g), 0):
+        check(lib.mpgan_c1_conv_fprop(ctypes.byref(g), dt(x), ptr(x), ld(x), ptr(w), ptr(bias), ptr(out), ld(out),
+                                      _stream()), "c1_conv_fprop")
+        return out, False
     check(lib.mpgan_conv_fprop(ctypes.byref(g), dt(x), ptr(x), ld(x), ptr(w), ptr(bias), ptr(out), ld(out), _stream()),
           "conv_fprop")
     return out, False
 
 
-def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True):
+def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True, use_c1=True):
     """Y-grid tensor -> X-grid tensor (ConvTranspose forward; Conv data gradient)."""
     lib = _lib.require_device()
     check_act(y, "conv input")
@@ -133,12 +137,16 @@ def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True)
         check(lib.mpgan_tc_conv_bprop(ctypes.byref(g), ptr(y), ld(y), ptr(wt), ptr(bias), ptr(out), ld(out), ptr(stats),
                                       _stream()), "tc_conv_bprop")
         return out, stats is not None
+    if use_c1 and lib.mpgan_c1_supported(ctypes.byref(g), 1):
+        check(lib.mpgan_c1_conv_bprop(ctypes.byref(g), dt(y), ptr(y), ld(y), ptr(w), ptr(bias), ptr(out), ld(out),
+                                      _stream()), "c1_conv_bprop")
+        return out, False
     check(lib.mpgan_conv_bprop(ctypes.byref(g), dt(y), ptr(y), ld(y), ptr(w), ptr(bias), ptr(out), ld(out), _stream()),
           "conv_bprop")
     return out, False
 
 
-def conv_wgrad(spec, x, y, dw, use_tc=True):
+def conv_wgrad(spec, x, y, dw, use_tc=True, use_c1=True):
     """dw[cy][taps][cx] (fp32, accumulates) from the X-grid tensor and the Y-grid tensor."""
     lib = _lib.require_device()
     check_act(x), check_act(y)
@@ -148,6 +156,9 @@ def conv_wgrad(spec, x, y, dw, use_tc=True):
     if use_tc and x.dtype == torch.bfloat16 and tc_supported(g, 2):
         check(lib.mpgan_tc_conv_wgrad(ctypes.byref(g), ptr(x), ld(x), ptr(y), ld(y), ptr(dw), None, 0, _stream()),
               "tc_conv_wgrad")
+    elif use_c1 and lib.mpgan_c1_supported(ctypes.byref(g), 2):
+        check(lib.mpgan_c1_conv_wgrad(ctypes.byref(g), dt(x), ptr(x), ld(x), ptr(y), ld(y), ptr(dw), _stream()),
+              "c1_conv_wgrad")
     else:
         check(lib.mpgan_conv_wgrad(ctypes.byref(g), dt(x), ptr(x), ld(x), ptr(y), ld(y), ptr(dw), _stream()),
               "conv_wgrad")

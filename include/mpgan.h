@@ -76,6 +76,18 @@ int mpgan_tc_conv_bprop(const MpganConvGeom* g, const void* y, int64_t ldy, cons
 size_t mpgan_tc_conv_wgrad_workspace(const MpganConvGeom* g);
 int mpgan_tc_conv_wgrad(const MpganConvGeom* g, const void* x, int64_t ldx, const void* y, int64_t ldy, float* dw,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* ---- convolution, one-channel edge layers: bandwidth-bound direct kernels, rank 2/3, f32 or bf16 ----
+ * fprop with cy == 1 (e.g. ConvTranspose 32->1 data gradient / 1->1 conv), bprop with cx == 1 (ConvTranspose 32->1
+ * forward, data gradient of the 1->16 / 1->64 first convolutions), wgrad with cx == 1.  Same contracts as the generic
+ * entry points; mpgan_c1_supported() says whether a (geometry, direction) is covered. */
+int mpgan_c1_supported(const MpganConvGeom* g, int direction /*0 fprop,1 bprop,2 wgrad*/);
+int mpgan_c1_conv_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* w,
+                        const float* bias, void* y, int64_t ldy, void* stream);
+int mpgan_c1_conv_bprop(const MpganConvGeom* g, int dtype, const void* y, int64_t ldy, const void* w,
+                        const float* bias, void* x, int64_t ldx, void* stream);
+int mpgan_c1_conv_wgrad(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* y, int64_t ldy,
+                        float* dw, void* stream);
+
 /* ---- batch norm (nn.BatchNorm3d, GAN_final.py:170-188; MONAI norm=BATCH) + activation, fused ----
  * stats: per-channel sum / sum-of-squares in fp64 (accumulates; caller zeroes). */
 int mpgan_bn_stats(int dtype, const void* x, int64_t ldx, int64_t pixels, int32_t c, double* stats, void* stream);

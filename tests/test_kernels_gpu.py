@@ -37,6 +37,9 @@ def rnd(*shape, seed=0):
 
 CONV_CASES = [
     # rank, n, cin, cout, size, k, s, p
+    (2, 3, 1, 1, 33, 3, 1, 1),
+    (2, 2, 1, 64, 41, 3, 1, 0),
+    (2, 2, 1, 32, 30, 3, 2, 1),
     (2, 2, 1, 16, 20, 3, 2, 1),
     (2, 2, 1, 64, 19, 3, 1, 0),
     (2, 3, 16, 16, 17, 3, 1, 1),
@@ -51,7 +54,9 @@ CONV_CASES = [
 
 @pytest.mark.parametrize("case", CONV_CASES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_conv_generic_fwd_dgrad_wgrad(case, dtype):
+@pytest.mark.parametrize("use_c1", [False, True])
+def test_conv_generic_fwd_dgrad_wgrad(case, dtype, use_c1):
+    """use_c1=False: the generic implicit-GEMM kernels only; True: the one-channel direct kernels where they apply."""
     rank, n, cin, cout, size, k, s, p = case
     conv = F.conv2d if rank == 2 else F.conv3d
     x = rnd(n, cin, *([size] * rank), seed=1)
@@ -67,12 +72,13 @@ def test_conv_generic_fwd_dgrad_wgrad(case, dtype):
     y.backward(dy)
     spec = ops.ConvSpec(rank, cin, cout, k, s, p)
     tol = 1e-5 if dtype == torch.float32 else 6e-3
-    yk, _ = ops.conv_fprop(spec, cl(x.detach(), dtype), oti(w.detach(), dtype), b, use_tc=False)
+    yk, _ = ops.conv_fprop(spec, cl(x.detach(), dtype), oti(w.detach(), dtype), b, use_tc=False, use_c1=use_c1)
     assert rel_l2(uncl(yk), y) <= tol
-    dxk, _ = ops.conv_bprop(spec, cl(dy, dtype), oti(w.detach(), dtype), None, None, xs=(size,) * rank, use_tc=False)
+    dxk, _ = ops.conv_bprop(spec, cl(dy, dtype), oti(w.detach(), dtype), None, None, xs=(size,) * rank, use_tc=False,
+                            use_c1=use_c1)
     assert rel_l2(uncl(dxk), x.grad) <= tol
     dw = torch.zeros(cout, k ** rank, cin, device=DEV)
-    ops.conv_wgrad(spec, cl(x.detach(), dtype), cl(dy, dtype), dw, use_tc=False)
+    ops.conv_wgrad(spec, cl(x.detach(), dtype), cl(dy, dtype), dw, use_tc=False, use_c1=use_c1)
     assert rel_l2(dw, oti(w.grad)) <= (1e-4 if dtype == torch.float32 else 6e-3)
     db = torch.zeros(cout, device=DEV)
     ops.colsum(cl(dy, dtype), db)
@@ -153,7 +159,7 @@ def test_tc_conv_bprop(case):
     assert rel_l2(uncl(dx), ref) <= 6e-3
 
 
-@pytest.mark.parametrize("case", [c for c in TC_CASES if c[1] in (64, 128, 256)])
+@pytest.mark.parametrize("case", [c for c in TC_CASES if c[1] in (16, 32, 64, 128, 256)])
 def test_tc_conv_wgrad(case):
     n, cin, cout, h, w_, k, s, p = case
     oh, ow = (h + 2 * p - k) // s + 1, (w_ + 2 * p - k) // s + 1
