@@ -131,6 +131,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t P, 
   shift[c] = b - mean * sc;
 }
 
+// The three hot kernels below share one mapping: the grid is sized so that (gridDim*blockDim) is a multiple of the
+// number of channel vectors per pixel (cv), hence every thread keeps ONE channel group for its whole pixel walk and
+// the per-channel constants live in registers; pixels are walked with a 2x unroll for memory-level parallelism.
+
 // ---------------- apply: y = act(x*scale + shift) (+ res) ----------------
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
@@ -138,107 +142,124 @@ bn_act_apply_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, cons
                     const float* __restrict__ shift, int act, const float* __restrict__ alpha, float leaky,
                     const T* __restrict__ res, int64_t ldres, T* __restrict__ y, int64_t ldy) {
   const int cv = C / V;
-  const int64_t total = P * cv;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+  const int c0 = (int)(tid % cv) * V;
+  const int64_t pstep = nthr / cv;
   const float slope = (act == MPGAN_ACT_PRELU || (act == MPGAN_ACT_LEAKY && alpha)) ? *alpha : leaky;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / cv;
-    const int c0 = (int)(i - p * cv) * V;
-    float v[V], r[V];
-    Vec<T, V>::load(x + p * ldx + c0, v);
-    if (res) Vec<T, V>::load(res + p * ldres + c0, r);
+  float sc[V], sh[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) { sc[e] = scale ? scale[c0 + e] : 1.f; sh[e] = shift ? shift[c0 + e] : 0.f; }
+  int64_t p = tid / cv;
+  for (; p + pstep < P; p += 2 * pstep) {
+    float v0[V], v1[V], r0[V], r1[V];
+    Vec<T, V>::load(x + p * ldx + c0, v0);
+    Vec<T, V>::load(x + (p + pstep) * ldx + c0, v1);
+    if (res) { Vec<T, V>::load(res + p * ldres + c0, r0); Vec<T, V>::load(res + (p + pstep) * ldres + c0, r1); }
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      float z = v[e];
-      if (scale) z = fmaf(z, scale[c0 + e], shift[c0 + e]);
-      z = act_fwd(z, act, slope);
-      if (res) z += r[e];
-      v[e] = z;
+      float z0 = act_fwd(fmaf(v0[e], sc[e], sh[e]), act, slope), z1 = act_fwd(fmaf(v1[e], sc[e], sh[e]), act, slope);
+      if (res) { z0 += r0[e]; z1 += r1[e]; }
+      v0[e] = z0; v1[e] = z1;
     }
-    Vec<T, V>::store(y + p * ldy + c0, v);
+    Vec<T, V>::store(y + p * ldy + c0, v0);
+    Vec<T, V>::store(y + (p + pstep) * ldy + c0, v1);
+  }
+  if (p < P) {
+    float v0[V], r0[V];
+    Vec<T, V>::load(x + p * ldx + c0, v0);
+    if (res) Vec<T, V>::load(res + p * ldres + c0, r0);
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      float z0 = act_fwd(fmaf(v0[e], sc[e], sh[e]), act, slope);
+      if (res) z0 += r0[e];
+      v0[e] = z0;
+    }
+    Vec<T, V>::store(y + p * ldy + c0, v0);
   }
 }
 
 // ---------------- backward pass 1: reductions ----------------
+// per thread: fp32 over pairs of pixels, pairs summed in fp64; per block: shared-memory fp64 atomics per channel.
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ x, int64_t ldx, int64_t P,
                          int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ scale, const float* __restrict__ shift, int act,
                          const float* __restrict__ alpha, float leaky, double* __restrict__ sums) {
-  __shared__ double s1[kThreads * V], s2[kThreads * V];
+  extern __shared__ double sred[];   // [2*C + 1]
+  for (int i = threadIdx.x; i < 2 * C + 1; i += blockDim.x) sred[i] = 0.0;
+  __syncthreads();
   const int cv = C / V;
-  const int CL = cv < kThreads ? cv : kThreads;
-  const int PL = kThreads / CL;
-  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
-  const int64_t p0 = (int64_t)blockIdx.x * kPixPerBlock;
-  const int64_t p1 = min(P, p0 + kPixPerBlock);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+  const int c0 = (int)(tid % cv) * V;
+  const int64_t pstep = nthr / cv;
   const float slope = (act == MPGAN_ACT_PRELU || (act == MPGAN_ACT_LEAKY && alpha)) ? *alpha : leaky;
-  double aslope = 0.0;
-  for (int cb = 0; cb < cv; cb += CL) {
-    const int vc = cb + cl;
-    double a1[V], a2[V];
+  float sc[V], sh[V], mu[V], is[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) a1[i] = a2[i] = 0.0;
-    if (pl < PL && vc < cv) {
-      const int c0 = vc * V;
-      float sc[V], sh[V], mu[V], is[V];
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        sc[e] = scale ? scale[c0 + e] : 1.f; sh[e] = shift ? shift[c0 + e] : 0.f;
-        mu[e] = mean ? mean[c0 + e] : 0.f; is[e] = invstd ? invstd[c0 + e] : 1.f;
-      }
-      for (int64_t p = p0 + pl; p < p1; p += PL) {
-        float g[V], xv[V];
-        Vec<T, V>::load(dy + p * lddy + c0, g);
-        Vec<T, V>::load(x + p * ldx + c0, xv);
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          float z = fmaf(xv[e], sc[e], sh[e]);
-          if (act == MPGAN_ACT_PRELU && z <= 0.f) aslope = fma((double)g[e], (double)z, aslope);
-          float gz = g[e] * act_grad(z, act, slope);
-          a1[e] += (double)gz;
-          a2[e] = fma((double)gz, (double)((xv[e] - mu[e]) * is[e]), a2[e]);
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < V; ++i) { s1[threadIdx.x * V + i] = a1[i]; s2[threadIdx.x * V + i] = a2[i]; }
-    __syncthreads();
-    for (int j = threadIdx.x; j < CL * V; j += kThreads) {
-      int lane = j / V, e = j % V;
-      if (cb + lane < cv) {
-        double t1 = 0.0, t2 = 0.0;
-        for (int q = 0; q < PL; ++q) { t1 += s1[(q * CL + lane) * V + e]; t2 += s2[(q * CL + lane) * V + e]; }
-        int ch = (cb + lane) * V + e;
-        atomicAdd(&sums[ch], t1);
-        atomicAdd(&sums[C + ch], t2);
-      }
-    }
-    __syncthreads();
+  for (int e = 0; e < V; ++e) {
+    sc[e] = scale ? scale[c0 + e] : 1.f; sh[e] = shift ? shift[c0 + e] : 0.f;
+    mu[e] = mean ? mean[c0 + e] : 0.f; is[e] = invstd ? invstd[c0 + e] : 1.f;
   }
-  if (act == MPGAN_ACT_PRELU) {  // block-wide fp64 sum of the slope-gradient partials
+  double a1[V], a2[V], aslope = 0.0;
+#pragma unroll
+  for (int e = 0; e < V; ++e) a1[e] = a2[e] = 0.0;
+  int64_t p = tid / cv;
+  for (; p < P; p += 2 * pstep) {
+    const bool two = p + pstep < P;
+    float g0[V], x0[V], g1[V], x1[V];
+    Vec<T, V>::load(dy + p * lddy + c0, g0);
+    Vec<T, V>::load(x + p * ldx + c0, x0);
+    if (two) { Vec<T, V>::load(dy + (p + pstep) * lddy + c0, g1); Vec<T, V>::load(x + (p + pstep) * ldx + c0, x1); }
+    float fs = 0.f;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      float z = fmaf(x0[e], sc[e], sh[e]);
+      if (act == MPGAN_ACT_PRELU && z <= 0.f) fs = fmaf(g0[e], z, fs);
+      float gz = g0[e] * act_grad(z, act, slope);
+      float s1 = gz, s2 = gz * ((x0[e] - mu[e]) * is[e]);
+      if (two) {
+        float z1 = fmaf(x1[e], sc[e], sh[e]);
+        if (act == MPGAN_ACT_PRELU && z1 <= 0.f) fs = fmaf(g1[e], z1, fs);
+        float gz1 = g1[e] * act_grad(z1, act, slope);
+        s1 += gz1;
+        s2 = fmaf(gz1, (x1[e] - mu[e]) * is[e], s2);
+      }
+      a1[e] += (double)s1;
+      a2[e] += (double)s2;
+    }
+    aslope += (double)fs;
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e) { atomicAdd(&sred[c0 + e], a1[e]); atomicAdd(&sred[C + c0 + e], a2[e]); }
+  if (act == MPGAN_ACT_PRELU) {
     double w = warp_sum(aslope);
-    __shared__ double dred[kThreads / 32];
-    if ((threadIdx.x & 31) == 0) dred[threadIdx.x >> 5] = w;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot = 0.0;
-      for (int i = 0; i < kThreads / 32; ++i) tot += dred[i];
-      atomicAdd(&sums[2 * C], tot);
-    }
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sred[2 * C], w);
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C + 1; i += blockDim.x)
+    if (sred[i] != 0.0) atomicAdd(&sums[i], sred[i]);
 }
 
-// ---------------- backward pass 2: dx, and parameter grads ----------------
+// ---------------- backward pass 2: dx, parameter grads, and (optionally) the conv bias grad = sum_p dx ----------------
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 bn_act_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ x, int64_t ldx, int64_t P,
                         int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ scale, const float* __restrict__ shift, int act,
                         const float* __restrict__ alpha, float leaky, const double* __restrict__ sums,
-                        float* dgamma, float* dbeta, float* dalpha, T* __restrict__ dx, int64_t lddx) {
+                        float* dgamma, float* dbeta, float* dalpha, float* dbias, T* __restrict__ dx, int64_t lddx) {
+  extern __shared__ float sbias[];   // [C] when dbias
+  if (dbias) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sbias[i] = 0.f;
+    __syncthreads();
+  }
   const int cv = C / V;
-  const int64_t total = P * cv;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+  const int c0 = (int)(tid % cv) * V;
+  const int64_t pstep = nthr / cv;
   const float slope = (act == MPGAN_ACT_PRELU || (act == MPGAN_ACT_LEAKY && alpha)) ? *alpha : leaky;
   const float invP = 1.f / (float)P;
   if (blockIdx.x == 0) {  // parameter gradients (accumulate), once
@@ -248,28 +269,52 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restr
     }
     if (threadIdx.x == 0 && dalpha && act == MPGAN_ACT_PRELU) *dalpha += (float)sums[2 * C];
   }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / cv;
-    const int c0 = (int)(i - p * cv) * V;
-    float g[V], xv[V];
-    Vec<T, V>::load(dy + p * lddy + c0, g);
-    Vec<T, V>::load(x + p * ldx + c0, xv);
+  const bool train = mean != nullptr;
+  float sc[V], sh[V], mu[V], is[V], mg[V], mgx[V], bsum[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    sc[e] = scale ? scale[c0 + e] : 1.f; sh[e] = shift ? shift[c0 + e] : 0.f;
+    mu[e] = train ? mean[c0 + e] : 0.f; is[e] = train ? invstd[c0 + e] : 1.f;
+    mg[e] = train ? (float)sums[c0 + e] * invP : 0.f;
+    mgx[e] = train ? (float)sums[C + c0 + e] * invP : 0.f;
+    bsum[e] = 0.f;
+  }
+  int64_t p = tid / cv;
+  for (; p < P; p += 2 * pstep) {
+    const bool two = p + pstep < P;
+    float g0[V], x0[V], g1[V], x1[V];
+    Vec<T, V>::load(dy + p * lddy + c0, g0);
+    Vec<T, V>::load(x + p * ldx + c0, x0);
+    if (two) { Vec<T, V>::load(dy + (p + pstep) * lddy + c0, g1); Vec<T, V>::load(x + (p + pstep) * ldx + c0, x1); }
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      const int c = c0 + e;
-      float sc = scale ? scale[c] : 1.f, sh = shift ? shift[c] : 0.f;
-      float z = fmaf(xv[e], sc, sh);
-      float gz = g[e] * act_grad(z, act, slope);
-      if (mean) {
-        float xh = (xv[e] - mean[c]) * invstd[c];
-        float mg = (float)sums[c] * invP, mgx = (float)sums[C + c] * invP;
-        gz = sc * (gz - mg - xh * mgx);
-      } else {
-        gz *= sc;  // eval-mode / affine-only
+      float z = fmaf(x0[e], sc[e], sh[e]);
+      float gz = g0[e] * act_grad(z, act, slope);
+      gz = train ? sc[e] * (gz - mg[e] - ((x0[e] - mu[e]) * is[e]) * mgx[e]) : gz * sc[e];
+      g0[e] = gz;
+      if (two) {
+        float z1 = fmaf(x1[e], sc[e], sh[e]);
+        float gz1 = g1[e] * act_grad(z1, act, slope);
+        gz1 = train ? sc[e] * (gz1 - mg[e] - ((x1[e] - mu[e]) * is[e]) * mgx[e]) : gz1 * sc[e];
+        g1[e] = gz1;
       }
-      g[e] = gz;
     }
-    Vec<T, V>::store(dx + p * lddx + c0, g);
+    Vec<T, V>::store(dx + p * lddx + c0, g0);
+    if (two) Vec<T, V>::store(dx + (p + pstep) * lddx + c0, g1);
+    if (dbias) {  // bias gradient of the producing conv: column sum of dx as stored (rounded to T)
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        bsum[e] += to_f(from_f<T>(g0[e]));
+        if (two) bsum[e] += to_f(from_f<T>(g1[e]));
+      }
+    }
+  }
+  if (dbias) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) atomicAdd(&sbias[c0 + e], bsum[e]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x)
+      if (sbias[i] != 0.f) atomicAdd(&dbias[i], sbias[i]);
   }
 }
 
@@ -278,10 +323,17 @@ static inline bool vec_ok(const void* p, int64_t ld, int dtype) {
   return p == nullptr || (((uintptr_t)p % align) == 0 && (ld % 8) == 0);
 }
 
-static inline int ew_grid(int64_t total) {
-  int64_t b = ceil_div(total, kThreads);
-  int64_t cap = (int64_t)num_sms() * 16;
-  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+static inline int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
+
+// grid for the fixed-channel-group mapping: gridDim*kThreads must be a multiple of cv
+static inline int ew_grid(int64_t pixels, int cv, int blocks_per_sm = 8) {
+  int64_t total = pixels * cv;
+  int64_t b = ceil_div(total, (int64_t)kThreads * 2);   // two pixels per thread-iteration
+  int64_t cap = (int64_t)num_sms() * blocks_per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  int64_t mult = cv / gcd64(cv, kThreads);
+  return (int)(ceil_div(b, mult) * mult);
 }
 
 }  // namespace mpgan
@@ -325,10 +377,10 @@ extern "C" int mpgan_bn_act_apply(int dtype, const void* x, int64_t ldx, int64_t
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(y, ldy, dtype) && vec_ok(res, res ? ldres : 8, dtype);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     if (vec)
-      bn_act_apply_kernel<T, 8><<<ew_grid(pixels * (c / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+      bn_act_apply_kernel<T, 8><<<ew_grid(pixels, c / 8), kThreads, 0, (cudaStream_t)stream>>>(
           (const T*)x, ldx, pixels, c, scale, shift, act, alpha, leaky_slope, (const T*)res, ldres, (T*)y, ldy);
     else
-      bn_act_apply_kernel<T, 1><<<ew_grid(pixels * c), kThreads, 0, (cudaStream_t)stream>>>(
+      bn_act_apply_kernel<T, 1><<<ew_grid(pixels, c), kThreads, 0, (cudaStream_t)stream>>>(
           (const T*)x, ldx, pixels, c, scale, shift, act, alpha, leaky_slope, (const T*)res, ldres, (T*)y, ldy);
     MPGAN_CHECK_LAUNCH("bn_act_apply");
     return 0;
@@ -341,13 +393,14 @@ extern "C" int mpgan_bn_act_bwd_reduce(int dtype, const void* dy, int64_t lddy, 
                                        float leaky_slope, double* sums, void* stream) {
   MPGAN_REQUIRE(pixels > 0 && c > 0 && ldx >= c && lddy >= c && sums, MPGAN_ERR_SHAPE, "bn_act_bwd_reduce: bad shape");
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(dy, lddy, dtype);
-  const int grid = (int)ceil_div(pixels, kPixPerBlock);
+  const size_t smem = (size_t)(2 * c + 1) * sizeof(double);
+  MPGAN_REQUIRE(smem <= 48 * 1024, MPGAN_ERR_UNSUPPORTED, "bn_act_bwd_reduce: too many channels (%d)", c);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     if (vec)
-      bn_act_bwd_reduce_kernel<T, 8><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+      bn_act_bwd_reduce_kernel<T, 8><<<ew_grid(pixels, c / 8, 4), kThreads, smem, (cudaStream_t)stream>>>(
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums);
     else
-      bn_act_bwd_reduce_kernel<T, 1><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+      bn_act_bwd_reduce_kernel<T, 1><<<ew_grid(pixels, c, 4), kThreads, smem, (cudaStream_t)stream>>>(
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums);
     MPGAN_CHECK_LAUNCH("bn_act_bwd_reduce");
     return 0;
@@ -358,20 +411,21 @@ extern "C" int mpgan_bn_act_bwd_apply(int dtype, const void* dy, int64_t lddy, c
                                       int64_t pixels, int32_t c, const float* mean, const float* invstd,
                                       const float* scale, const float* shift, int act, const float* alpha,
                                       float leaky_slope, const double* sums, float* dgamma, float* dbeta,
-                                      float* dalpha, void* dx, int64_t lddx, void* stream) {
+                                      float* dalpha, float* dbias, void* dx, int64_t lddx, void* stream) {
   MPGAN_REQUIRE(pixels > 0 && c > 0 && ldx >= c && lddy >= c && lddx >= c && sums, MPGAN_ERR_SHAPE,
                 "bn_act_bwd_apply: bad shape");
   MPGAN_REQUIRE((mean == nullptr) == (invstd == nullptr), MPGAN_ERR_SHAPE, "mean/invstd must both be given");
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(dy, lddy, dtype) && vec_ok(dx, lddx, dtype);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
+    const size_t smem = dbias ? (size_t)c * sizeof(float) : 0;
     if (vec)
-      bn_act_bwd_apply_kernel<T, 8><<<ew_grid(pixels * (c / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+      bn_act_bwd_apply_kernel<T, 8><<<ew_grid(pixels, c / 8), kThreads, smem, (cudaStream_t)stream>>>(
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums,
-          dgamma, dbeta, dalpha, (T*)dx, lddx);
+          dgamma, dbeta, dalpha, dbias, (T*)dx, lddx);
     else
-      bn_act_bwd_apply_kernel<T, 1><<<ew_grid(pixels * c), kThreads, 0, (cudaStream_t)stream>>>(
+      bn_act_bwd_apply_kernel<T, 1><<<ew_grid(pixels, c), kThreads, smem, (cudaStream_t)stream>>>(
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums,
-          dgamma, dbeta, dalpha, (T*)dx, lddx);
+          dgamma, dbeta, dalpha, dbias, (T*)dx, lddx);
     MPGAN_CHECK_LAUNCH("bn_act_bwd_apply");
     return 0;
   });

@@ -45,7 +45,7 @@ _SIGS = {
     "mpgan_bn_act_bwd_reduce": (c_int, [c_int, _P, c_int64, _P, c_int64, c_int64, c_int32, _P, _P, _P, _P, c_int, _P,
                                         c_float, _P, _P]),
     "mpgan_bn_act_bwd_apply": (c_int, [c_int, _P, c_int64, _P, c_int64, c_int64, c_int32, _P, _P, _P, _P, c_int, _P,
-                                       c_float, _P, _P, _P, _P, _P, c_int64, _P]),
+                                       c_float, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "mpgan_add_copy": (c_int, [c_int, _P, c_int64, _P, c_int64, c_int, _P, c_int64, c_int64, c_int32, _P]),
     "mpgan_tanh_fwd": (c_int, [c_int, _P, c_int, _P, c_int64, _P]),
     "mpgan_tanh_bwd": (c_int, [c_int, _P, _P, _P, c_int64, _P]),

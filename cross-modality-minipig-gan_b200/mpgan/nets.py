@@ -52,15 +52,16 @@ def conv_apply(rec, x, out=None, stats=None):
     return ops.conv_fprop(rec.spec, x, rec.w, rec.bias, out=out, stats=stats)
 
 
-def conv_backward(rec, x, dy, plan, need_dx):
-    """x: the layer's input, dy: gradient of its output (contiguous or sliced).  Returns dx or None."""
+def conv_backward(rec, x, dy, plan, need_dx, bias_done=False):
+    """x: the layer's input, dy: gradient of its output (contiguous or sliced).  Returns dx or None.
+    bias_done: the bias gradient was already accumulated by the fused BatchNorm backward."""
     spec = rec.spec
     if plan.need_wgrad:
         if spec.transposed:
             ops.conv_wgrad(spec, dy, x, rec.dw)
         else:
             ops.conv_wgrad(spec, x, dy, rec.dw)
-        if rec.db is not None:
+        if rec.db is not None and not bias_done:
             ops.colsum(dy, rec.db)
     if not need_dx:
         return None
@@ -84,7 +85,8 @@ def bn_act_forward(c, bn, act, alpha, leaky, res, out, plan, stats, fused_stats)
     return out, (mean, invstd, scale, shift)
 
 
-def bn_act_backward(dy, c, saved, bn, act, alpha_param, leaky, plan, trained):
+def bn_act_backward(dy, c, saved, bn, act, alpha_param, leaky, plan, trained, conv_db=None):
+    """conv_db: bias-gradient buffer of the convolution that produced c (accumulated in the same pass)."""
     mean, invstd, scale, shift = saved
     ch = c.shape[-1]
     sums = torch.zeros(2 * ch + 1, dtype=torch.float64, device=c.device)
@@ -92,7 +94,8 @@ def bn_act_backward(dy, c, saved, bn, act, alpha_param, leaky, plan, trained):
     wg = plan.need_wgrad
     ops.bn_act_bwd(dy, c, mean if trained else None, invstd if trained else None, scale, shift, act, alpha_param,
                    leaky, sums, bn.weight.grad if wg else None, bn.bias.grad if wg else None,
-                   alpha_param.grad if (wg and alpha_param is not None) else None, dc)
+                   alpha_param.grad if (wg and alpha_param is not None) else None, dc,
+                   dbias=conv_db if wg else None)
     return dc
 
 
@@ -150,8 +153,8 @@ class Convolution(nn.Sequential):
             (x,) = plan.tape.pop()
             return conv_backward(rec, x, dy, plan, need_dx)
         x, c, saved, trained = plan.tape.pop()
-        dc = bn_act_backward(dy, c, saved, self.norm, ACT_PRELU, self.act.weight, 0.0, plan, trained)
-        return conv_backward(rec, x, dc, plan, need_dx)
+        dc = bn_act_backward(dy, c, saved, self.norm, ACT_PRELU, self.act.weight, 0.0, plan, trained, conv_db=rec.db)
+        return conv_backward(rec, x, dc, plan, need_dx, bias_done=True)
 
 
 class ResidualUnit(nn.Module):
@@ -561,11 +564,14 @@ class _ConvBnLeakyStack(_PlanNet):
                 if (3 * i + 1) in ag:
                     dbn = dbn + ag[3 * i + 1].permute(to_cl).to(dbn.dtype)
                 dc = bn_act_backward(dbn, c, saved, bns[i], ACT_NONE, None, 0.0, plan, trained)
+                fused_bias = False
             else:
-                dc = bn_act_backward(dh, c, saved, bns[i], ACT_LEAKY, None, 0.2, plan, trained)
+                fused_bias = (3 * i) not in ag
+                dc = bn_act_backward(dh, c, saved, bns[i], ACT_LEAKY, None, 0.2, plan, trained,
+                                     conv_db=rt.rec[convs[i]].db if fused_bias else None)
             if (3 * i) in ag:
                 dc = dc + ag[3 * i].permute(to_cl).to(dc.dtype)
-            dh = conv_backward(rt.rec[convs[i]], h_in, dc, plan, need_dx=(need_dx or i > 0))
+            dh = conv_backward(rt.rec[convs[i]], h_in, dc, plan, need_dx=(need_dx or i > 0), bias_done=fused_bias)
         if not need_dx:
             return None
         d_in = dh if dh.dtype == torch.float32 else ops.add_copy(dh, None, _new(dh, dh.shape, torch.float32))

@@ -195,7 +195,7 @@ def bn_act_apply(x, scale, shift, act, alpha, leaky, res, out):
     return out
 
 
-def bn_act_bwd(dy, x, mean, invstd, scale, shift, act, alpha, leaky, sums, dgamma, dbeta, dalpha, dx):
+def bn_act_bwd(dy, x, mean, invstd, scale, shift, act, alpha, leaky, sums, dgamma, dbeta, dalpha, dx, dbias=None):
     lib = _lib.require_device()
     check_act(dy), check_act(x), check_act(dx)
     c = x.shape[-1]
@@ -204,7 +204,7 @@ def bn_act_bwd(dy, x, mean, invstd, scale, shift, act, alpha, leaky, sums, dgamm
           "bn_act_bwd_reduce")
     check(lib.mpgan_bn_act_bwd_apply(dt(x), ptr(dy), ld(dy), ptr(x), ld(x), pixels(x), c, ptr(mean), ptr(invstd),
                                      ptr(scale), ptr(shift), act, ptr(alpha), leaky, ptr(sums), ptr(dgamma),
-                                     ptr(dbeta), ptr(dalpha), ptr(dx), ld(dx), _stream()), "bn_act_bwd_apply")
+                                     ptr(dbeta), ptr(dalpha), ptr(dbias), ptr(dx), ld(dx), _stream()), "bn_act_bwd_apply")
     return dx
 
 
@@ -214,8 +214,8 @@ def act_bwd(dy, z, act, leaky, dx):
     check_act(dy), check_act(z), check_act(dx)
     dummy = torch.zeros(1, dtype=torch.float64, device=z.device)
     check(lib.mpgan_bn_act_bwd_apply(dt(z), ptr(dy), ld(dy), ptr(z), ld(z), pixels(z), z.shape[-1], None, None, None,
-                                     None, act, None, leaky, ptr(dummy), None, None, None, ptr(dx), ld(dx), _stream()),
-          "act_bwd")
+                                     None, act, None, leaky, ptr(dummy), None, None, None, None, ptr(dx), ld(dx),
+                                     _stream()), "act_bwd")
     return dx
 
 

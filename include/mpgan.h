@@ -104,7 +104,8 @@ int mpgan_bn_act_apply(int dtype, const void* x, int64_t ldx, int64_t pixels, in
                        const float* shift, int act, const float* alpha, float leaky_slope, const void* res,
                        int64_t ldres, void* y, int64_t ldy, void* stream);
 /* backward of y = act(bn(x)): pass 1 reduces  sums[0:C]=sum g, sums[C:2C]=sum g*xhat, sums[2C]=sum dy*min(z,0)
- * (PReLU slope grad), all fp64 accumulating;  pass 2 writes dx and accumulates dgamma/dbeta/dalpha (fp32). */
+ * (PReLU slope grad), all fp64 accumulating;  pass 2 writes dx and accumulates dgamma/dbeta/dalpha (fp32) and, when
+ * dbias != NULL, the bias gradient of the convolution that produced x: dbias[c] += sum_p dx[p,c]. */
 int mpgan_bn_act_bwd_reduce(int dtype, const void* dy, int64_t lddy, const void* x, int64_t ldx, int64_t pixels,
                             int32_t c, const float* mean, const float* invstd, const float* scale,
                             const float* shift, int act, const float* alpha, float leaky_slope, double* sums,
@@ -112,7 +113,8 @@ int mpgan_bn_act_bwd_reduce(int dtype, const void* dy, int64_t lddy, const void*
 int mpgan_bn_act_bwd_apply(int dtype, const void* dy, int64_t lddy, const void* x, int64_t ldx, int64_t pixels,
                            int32_t c, const float* mean, const float* invstd, const float* scale,
                            const float* shift, int act, const float* alpha, float leaky_slope, const double* sums,
-                           float* dgamma, float* dbeta, float* dalpha, void* dx, int64_t lddx, void* stream);
+                           float* dgamma, float* dbeta, float* dalpha, float* dbias, void* dx, int64_t lddx,
+                           void* stream);
 
 /* ---- elementwise helpers on channels-last tensors ---- */
 /* y[p, 0:c] = a[p, 0:c] (+ b[p, 0:c]) with independent pixel strides (residual add, concat copy, casts). */

@@ -227,8 +227,10 @@ def test_bn_act_forward_backward(c, act, dtype):
     assert int(bn_k.num_batches_tracked) == 1
     sums = torch.zeros(2 * c + 1, dtype=torch.float64, device=DEV)
     dg, db, da = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV), torch.zeros(1, device=DEV)
+    dbias = torch.zeros(c, device=DEV)
     dx = ops.bn_act_bwd(cl(dy, dtype), xc, buf[0], buf[1], buf[2], buf[3], act, a, 0.2, sums, dg, db, da,
-                        torch.empty_like(xc))
+                        torch.empty_like(xc), dbias=dbias)
+    assert torch.allclose(dbias, dx.float().sum(dim=(0, 1, 2)), rtol=1e-3, atol=1e-3 * float(dx.float().abs().max()))
     btol = 1e-4 if dtype == torch.float32 else 1e-2
     assert rel_l2(uncl(dx), x.grad) <= btol
     assert rel_l2(dg, bn.weight.grad) <= 1e-4 and rel_l2(db, bn.bias.grad) <= 1e-4
