@@ -6,6 +6,8 @@
 // 32 B f32) when C, ld are multiples of 8 and the pointers are 16/32-byte aligned; scalar path otherwise (C = 1).
 // Per-channel sums are accumulated in fp64 end to end (per thread, shared-memory reduce, one global atomic per
 // channel per block): E[x^2]-mean^2 must survive |mean| >> std.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace mpgan {
@@ -131,16 +133,56 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t P, 
   shift[c] = b - mean * sc;
 }
 
-// The three hot kernels below share one mapping: the grid is sized so that (gridDim*blockDim) is a multiple of the
+// The hot kernels below share one mapping: the grid is sized so that (gridDim*blockDim) is a multiple of the
 // number of channel vectors per pixel (cv), hence every thread keeps ONE channel group for its whole pixel walk and
-// the per-channel constants live in registers; pixels are walked with a 2x unroll for memory-level parallelism.
+// the per-channel constants live in registers; pixels are walked with a 4x (apply: 2x) unroll for memory-level
+// parallelism.  Per-channel reductions: per-thread fp64 partials -> warp shuffles across the lanes that share a
+// channel group -> one shared-memory slot per (warp, channel) -> one global fp64 atomic per channel per block.
+
+// scale/shift (and the saved mean/invstd) straight from the fp64 statistics: the arithmetic of bn_finalize_kernel
+struct BnTrain {
+  const double* stats;       // [2C] sum, sum of squares; nullptr = scale/shift given
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  int64_t* nbt;
+  float* mean_out;           // [C] each; written by the first block
+  float* invstd_out;
+  float* scale_out;
+  float* shift_out;
+};
+
+__device__ __forceinline__ void bn_train_coeffs(const BnTrain& f, int c, int C, int64_t P, bool writer, float& sc,
+                                                float& sh) {
+  const double m = f.stats[c] / (double)P;
+  double var = f.stats[C + c] / (double)P - m * m;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)m;
+  const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+  const float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
+  sc = g * invstd;
+  sh = b - mean * sc;
+  if (writer) {
+    if (f.running_mean) f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+    if (f.running_var) {
+      double unb = P > 1 ? var * ((double)P / (double)(P - 1)) : var;
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unb;
+    }
+    if (f.mean_out) f.mean_out[c] = mean;
+    if (f.invstd_out) f.invstd_out[c] = invstd;
+    f.scale_out[c] = sc;
+    f.shift_out[c] = sh;
+  }
+}
 
 // ---------------- apply: y = act(x*scale + shift) (+ res) ----------------
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 bn_act_apply_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, const float* __restrict__ scale,
-                    const float* __restrict__ shift, int act, const float* __restrict__ alpha, float leaky,
-                    const T* __restrict__ res, int64_t ldres, T* __restrict__ y, int64_t ldy) {
+                    const float* __restrict__ shift, const BnTrain f, int act, const float* __restrict__ alpha,
+                    float leaky, const T* __restrict__ res, int64_t ldres, T* __restrict__ y, int64_t ldy) {
   const int cv = C / V;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
@@ -148,8 +190,23 @@ bn_act_apply_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, cons
   const int64_t pstep = nthr / cv;
   const float slope = (act == MPGAN_ACT_PRELU || (act == MPGAN_ACT_LEAKY && alpha)) ? *alpha : leaky;
   float sc[V], sh[V];
+  if (f.stats) {
+    // one channel per thread -> shared memory (the fp64 divide / sqrt chain runs once per channel per block)
+    extern __shared__ float s_coef[];   // [2*C]
+    if (tid == 0 && f.nbt) *f.nbt += 1;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a, b;
+      bn_train_coeffs(f, c, C, P, blockIdx.x == 0, a, b);
+      s_coef[c] = a;
+      s_coef[C + c] = b;
+    }
+    __syncthreads();
 #pragma unroll
-  for (int e = 0; e < V; ++e) { sc[e] = scale ? scale[c0 + e] : 1.f; sh[e] = shift ? shift[c0 + e] : 0.f; }
+    for (int e = 0; e < V; ++e) { sc[e] = s_coef[c0 + e]; sh[e] = s_coef[C + c0 + e]; }
+  } else {
+#pragma unroll
+    for (int e = 0; e < V; ++e) { sc[e] = scale ? scale[c0 + e] : 1.f; sh[e] = shift ? shift[c0 + e] : 0.f; }
+  }
   int64_t p = tid / cv;
   for (; p + pstep < P; p += 2 * pstep) {
     float v0[V], v1[V], r0[V], r1[V];
@@ -179,17 +236,57 @@ bn_act_apply_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, cons
   }
 }
 
+// Block-level reduction of NV per-thread fp64 partials that belong to channel group (tid % cv); the totals of
+// value i of group g are added to out[i_hi * C + g*V + i_lo] (i = i_hi*V + i_lo) with one global atomic each.
+// sm: kThreads*NV doubles.
+template <int V, int NV, typename OutT>
+__device__ __forceinline__ void group_reduce_to_global(double (&a)[NV], int cv, int C, int64_t tid, double* sm,
+                                                       OutT* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (cv <= 32 && (32 % cv) == 0) {
+    for (int off = 16; off >= cv; off >>= 1) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], off);
+    }
+    if (lane < cv) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sm[(warp * cv + lane) * NV + i] = a[i];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cv * NV; j += kThreads) {
+      const int g = j / NV, i = j - g * NV;
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) t += sm[(w * cv + g) * NV + i];
+      atomicAdd(&out[(i / V) * C + g * V + (i % V)], (OutT)t);
+    }
+  } else if ((kThreads % cv) == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sm[threadIdx.x * NV + i] = a[i];
+    __syncthreads();
+    const int reps = kThreads / cv;
+    for (int j = threadIdx.x; j < cv * NV; j += kThreads) {
+      const int g = j / NV, i = j - g * NV;
+      double t = 0.0;
+      for (int k = 0; k < reps; ++k) t += sm[(g + k * cv) * NV + i];
+      atomicAdd(&out[(i / V) * C + g * V + (i % V)], (OutT)t);
+    }
+  } else {  // channel group varies with the block: straight to global (odd channel counts; tests only)
+    const int g = (int)(tid % cv);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) atomicAdd(&out[(i / V) * C + g * V + (i % V)], (OutT)a[i]);
+  }
+}
+
 // ---------------- backward pass 1: reductions ----------------
-// per thread: fp32 over pairs of pixels, pairs summed in fp64; per block: shared-memory fp64 atomics per channel.
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ x, int64_t ldx, int64_t P,
                          int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ scale, const float* __restrict__ shift, int act,
                          const float* __restrict__ alpha, float leaky, double* __restrict__ sums) {
-  extern __shared__ double sred[];   // [2*C + 1]
-  for (int i = threadIdx.x; i < 2 * C + 1; i += blockDim.x) sred[i] = 0.0;
-  __syncthreads();
+  __shared__ double sm[kThreads * 2 * V];
+  __shared__ double sslope[kThreads / 32];
   const int cv = C / V;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
@@ -202,47 +299,55 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
     sc[e] = scale ? scale[c0 + e] : 1.f; sh[e] = shift ? shift[c0 + e] : 0.f;
     mu[e] = mean ? mean[c0 + e] : 0.f; is[e] = invstd ? invstd[c0 + e] : 1.f;
   }
-  double a1[V], a2[V], aslope = 0.0;
+  double a[2 * V], aslope = 0.0;
 #pragma unroll
-  for (int e = 0; e < V; ++e) a1[e] = a2[e] = 0.0;
-  int64_t p = tid / cv;
-  for (; p < P; p += 2 * pstep) {
-    const bool two = p + pstep < P;
-    float g0[V], x0[V], g1[V], x1[V];
-    Vec<T, V>::load(dy + p * lddy + c0, g0);
-    Vec<T, V>::load(x + p * ldx + c0, x0);
-    if (two) { Vec<T, V>::load(dy + (p + pstep) * lddy + c0, g1); Vec<T, V>::load(x + (p + pstep) * ldx + c0, x1); }
+  for (int e = 0; e < 2 * V; ++e) a[e] = 0.0;
+  constexpr int U = 4;
+  for (int64_t p = tid / cv; p < P; p += U * pstep) {
+    float g[U][V], xv[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p + u * pstep < P) {
+        Vec<T, V>::load(dy + (p + u * pstep) * lddy + c0, g[u]);
+        Vec<T, V>::load(x + (p + u * pstep) * ldx + c0, xv[u]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) { g[u][e] = 0.f; xv[u][e] = 0.f; }
+      }
+    }
     float fs = 0.f;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      float z = fmaf(x0[e], sc[e], sh[e]);
-      if (act == MPGAN_ACT_PRELU && z <= 0.f) fs = fmaf(g0[e], z, fs);
-      float gz = g0[e] * act_grad(z, act, slope);
-      float s1 = gz, s2 = gz * ((x0[e] - mu[e]) * is[e]);
-      if (two) {
-        float z1 = fmaf(x1[e], sc[e], sh[e]);
-        if (act == MPGAN_ACT_PRELU && z1 <= 0.f) fs = fmaf(g1[e], z1, fs);
-        float gz1 = g1[e] * act_grad(z1, act, slope);
-        s1 += gz1;
-        s2 = fmaf(gz1, (x1[e] - mu[e]) * is[e], s2);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float z = fmaf(xv[u][e], sc[e], sh[e]);
+        if (act == MPGAN_ACT_PRELU && z <= 0.f) fs = fmaf(g[u][e], z, fs);
+        const float gz = g[u][e] * act_grad(z, act, slope);
+        s1 += gz;
+        s2 = fmaf(gz, (xv[u][e] - mu[e]) * is[e], s2);
       }
-      a1[e] += (double)s1;
-      a2[e] += (double)s2;
+      a[e] += (double)s1;
+      a[V + e] += (double)s2;
     }
     aslope += (double)fs;
   }
-#pragma unroll
-  for (int e = 0; e < V; ++e) { atomicAdd(&sred[c0 + e], a1[e]); atomicAdd(&sred[C + c0 + e], a2[e]); }
+  group_reduce_to_global<V, 2 * V, double>(a, cv, C, tid, sm, sums);
   if (act == MPGAN_ACT_PRELU) {
     double w = warp_sum(aslope);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&sred[2 * C], w);
+    if ((threadIdx.x & 31) == 0) sslope[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < kThreads / 32; ++i) t += sslope[i];
+      atomicAdd(&sums[2 * C], t);
+    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C + 1; i += blockDim.x)
-    if (sred[i] != 0.0) atomicAdd(&sums[i], sred[i]);
 }
 
 // ---------------- backward pass 2: dx, parameter grads, and (optionally) the conv bias grad = sum_p dx ----------------
+// dx = k1*gz + k2*(x - mu) + k3 with k1 = scale, k2 = -scale*invstd*mean(g*xhat), k3 = -scale*mean(g)
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 bn_act_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ x, int64_t ldx, int64_t P,
@@ -250,11 +355,7 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restr
                         const float* __restrict__ scale, const float* __restrict__ shift, int act,
                         const float* __restrict__ alpha, float leaky, const double* __restrict__ sums,
                         float* dgamma, float* dbeta, float* dalpha, float* dbias, T* __restrict__ dx, int64_t lddx) {
-  extern __shared__ float sbias[];   // [C] when dbias
-  if (dbias) {
-    for (int i = threadIdx.x; i < C; i += blockDim.x) sbias[i] = 0.f;
-    __syncthreads();
-  }
+  __shared__ double sm[kThreads * V];
   const int cv = C / V;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
@@ -270,15 +371,20 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restr
     if (threadIdx.x == 0 && dalpha && act == MPGAN_ACT_PRELU) *dalpha += (float)sums[2 * C];
   }
   const bool train = mean != nullptr;
-  float sc[V], sh[V], mu[V], is[V], mg[V], mgx[V], bsum[V];
+  float sc[V], sh[V], mu[V], k2[V], k3[V];
 #pragma unroll
   for (int e = 0; e < V; ++e) {
     sc[e] = scale ? scale[c0 + e] : 1.f; sh[e] = shift ? shift[c0 + e] : 0.f;
-    mu[e] = train ? mean[c0 + e] : 0.f; is[e] = train ? invstd[c0 + e] : 1.f;
-    mg[e] = train ? (float)sums[c0 + e] * invP : 0.f;
-    mgx[e] = train ? (float)sums[C + c0 + e] * invP : 0.f;
-    bsum[e] = 0.f;
+    mu[e] = train ? mean[c0 + e] : 0.f;
+    const float is = train ? invstd[c0 + e] : 1.f;
+    const float mg = train ? (float)sums[c0 + e] * invP : 0.f;
+    const float mgx = train ? (float)sums[C + c0 + e] * invP : 0.f;
+    k2[e] = -sc[e] * is * mgx;
+    k3[e] = -sc[e] * mg;
   }
+  double bsum[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) bsum[e] = 0.0;
   int64_t p = tid / cv;
   for (; p < P; p += 2 * pstep) {
     const bool two = p + pstep < P;
@@ -288,15 +394,11 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restr
     if (two) { Vec<T, V>::load(dy + (p + pstep) * lddy + c0, g1); Vec<T, V>::load(x + (p + pstep) * ldx + c0, x1); }
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      float z = fmaf(x0[e], sc[e], sh[e]);
-      float gz = g0[e] * act_grad(z, act, slope);
-      gz = train ? sc[e] * (gz - mg[e] - ((x0[e] - mu[e]) * is[e]) * mgx[e]) : gz * sc[e];
-      g0[e] = gz;
+      const float z = fmaf(x0[e], sc[e], sh[e]);
+      g0[e] = fmaf(sc[e], g0[e] * act_grad(z, act, slope), fmaf(k2[e], x0[e] - mu[e], k3[e]));
       if (two) {
-        float z1 = fmaf(x1[e], sc[e], sh[e]);
-        float gz1 = g1[e] * act_grad(z1, act, slope);
-        gz1 = train ? sc[e] * (gz1 - mg[e] - ((x1[e] - mu[e]) * is[e]) * mgx[e]) : gz1 * sc[e];
-        g1[e] = gz1;
+        const float z1 = fmaf(x1[e], sc[e], sh[e]);
+        g1[e] = fmaf(sc[e], g1[e] * act_grad(z1, act, slope), fmaf(k2[e], x1[e] - mu[e], k3[e]));
       }
     }
     Vec<T, V>::store(dx + p * lddx + c0, g0);
@@ -304,18 +406,13 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restr
     if (dbias) {  // bias gradient of the producing conv: column sum of dx as stored (rounded to T)
 #pragma unroll
       for (int e = 0; e < V; ++e) {
-        bsum[e] += to_f(from_f<T>(g0[e]));
-        if (two) bsum[e] += to_f(from_f<T>(g1[e]));
+        float s = to_f(from_f<T>(g0[e]));
+        if (two) s += to_f(from_f<T>(g1[e]));
+        bsum[e] += (double)s;
       }
     }
   }
-  if (dbias) {
-#pragma unroll
-    for (int e = 0; e < V; ++e) atomicAdd(&sbias[c0 + e], bsum[e]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x)
-      if (sbias[i] != 0.f) atomicAdd(&dbias[i], sbias[i]);
-  }
+  if (dbias) group_reduce_to_global<V, V, float>(bsum, cv, C, tid, sm, dbias);
 }
 
 static inline bool vec_ok(const void* p, int64_t ld, int dtype) {
@@ -325,10 +422,11 @@ static inline bool vec_ok(const void* p, int64_t ld, int dtype) {
 
 static inline int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
 
-// grid for the fixed-channel-group mapping: gridDim*kThreads must be a multiple of cv
-static inline int ew_grid(int64_t pixels, int cv, int blocks_per_sm = 8) {
+// grid for the fixed-channel-group mapping: gridDim*kThreads must be a multiple of cv.
+// pix_per_thread: pixels each thread should walk (amortises the per-thread prologue / reduction epilogue).
+static inline int ew_grid(int64_t pixels, int cv, int blocks_per_sm = 8, int pix_per_thread = 2) {
   int64_t total = pixels * cv;
-  int64_t b = ceil_div(total, (int64_t)kThreads * 2);   // two pixels per thread-iteration
+  int64_t b = ceil_div(total, (int64_t)kThreads * pix_per_thread);
   int64_t cap = (int64_t)num_sms() * blocks_per_sm;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
@@ -367,6 +465,21 @@ extern "C" int mpgan_bn_finalize(const double* stats, int64_t pixels, int32_t c,
   return 0;
 }
 
+template <typename T>
+static int launch_apply(const void* x, int64_t ldx, int64_t pixels, int32_t c, const float* scale, const float* shift,
+                        const BnTrain& f, int act, const float* alpha, float leaky_slope, const void* res,
+                        int64_t ldres, void* y, int64_t ldy, bool vec, cudaStream_t s) {
+  const size_t smem = f.stats ? (size_t)2 * c * sizeof(float) : 0;
+  if (vec)
+    bn_act_apply_kernel<T, 8><<<ew_grid(pixels, c / 8, 8, 4), kThreads, smem, s>>>(
+        (const T*)x, ldx, pixels, c, scale, shift, f, act, alpha, leaky_slope, (const T*)res, ldres, (T*)y, ldy);
+  else
+    bn_act_apply_kernel<T, 1><<<ew_grid(pixels, c, 8, 4), kThreads, smem, s>>>(
+        (const T*)x, ldx, pixels, c, scale, shift, f, act, alpha, leaky_slope, (const T*)res, ldres, (T*)y, ldy);
+  MPGAN_CHECK_LAUNCH("bn_act_apply");
+  return 0;
+}
+
 extern "C" int mpgan_bn_act_apply(int dtype, const void* x, int64_t ldx, int64_t pixels, int32_t c,
                                   const float* scale, const float* shift, int act, const float* alpha,
                                   float leaky_slope, const void* res, int64_t ldres, void* y, int64_t ldy,
@@ -375,16 +488,28 @@ extern "C" int mpgan_bn_act_apply(int dtype, const void* x, int64_t ldx, int64_t
   MPGAN_REQUIRE((scale == nullptr) == (shift == nullptr), MPGAN_ERR_SHAPE, "scale/shift must both be given");
   MPGAN_REQUIRE(act != MPGAN_ACT_PRELU || alpha, MPGAN_ERR_SHAPE, "PReLU needs alpha");
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(y, ldy, dtype) && vec_ok(res, res ? ldres : 8, dtype);
-  MPGAN_DISPATCH_DTYPE(dtype, T, {
-    if (vec)
-      bn_act_apply_kernel<T, 8><<<ew_grid(pixels, c / 8), kThreads, 0, (cudaStream_t)stream>>>(
-          (const T*)x, ldx, pixels, c, scale, shift, act, alpha, leaky_slope, (const T*)res, ldres, (T*)y, ldy);
-    else
-      bn_act_apply_kernel<T, 1><<<ew_grid(pixels, c), kThreads, 0, (cudaStream_t)stream>>>(
-          (const T*)x, ldx, pixels, c, scale, shift, act, alpha, leaky_slope, (const T*)res, ldres, (T*)y, ldy);
-    MPGAN_CHECK_LAUNCH("bn_act_apply");
-    return 0;
-  });
+  BnTrain f;
+  memset(&f, 0, sizeof(f));
+  MPGAN_DISPATCH_DTYPE(dtype, T, return launch_apply<T>(x, ldx, pixels, c, scale, shift, f, act, alpha, leaky_slope,
+                                                        res, ldres, y, ldy, vec, (cudaStream_t)stream));
+}
+
+extern "C" int mpgan_bn_train_apply(int dtype, const void* x, int64_t ldx, int64_t pixels, int32_t c,
+                                    const double* stats, const float* gamma, const float* beta, float eps,
+                                    float momentum, float* running_mean, float* running_var,
+                                    int64_t* num_batches_tracked, float* mean, float* invstd, float* scale,
+                                    float* shift, int act, const float* alpha, float leaky_slope, const void* res,
+                                    int64_t ldres, void* y, int64_t ldy, void* stream) {
+  MPGAN_REQUIRE(pixels > 0 && c > 0 && ldx >= c && ldy >= c, MPGAN_ERR_SHAPE, "bn_train_apply: bad shape");
+  MPGAN_REQUIRE(stats && scale && shift, MPGAN_ERR_SHAPE, "bn_train_apply: stats, scale and shift are required");
+  MPGAN_REQUIRE(act != MPGAN_ACT_PRELU || alpha, MPGAN_ERR_SHAPE, "PReLU needs alpha");
+  const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(y, ldy, dtype) && vec_ok(res, res ? ldres : 8, dtype);
+  BnTrain f;
+  f.stats = stats; f.gamma = gamma; f.beta = beta; f.eps = eps; f.momentum = momentum;
+  f.running_mean = running_mean; f.running_var = running_var; f.nbt = num_batches_tracked;
+  f.mean_out = mean; f.invstd_out = invstd; f.scale_out = scale; f.shift_out = shift;
+  MPGAN_DISPATCH_DTYPE(dtype, T, return launch_apply<T>(x, ldx, pixels, c, nullptr, nullptr, f, act, alpha,
+                                                        leaky_slope, res, ldres, y, ldy, vec, (cudaStream_t)stream));
 }
 
 extern "C" int mpgan_bn_act_bwd_reduce(int dtype, const void* dy, int64_t lddy, const void* x, int64_t ldx,
@@ -393,14 +518,12 @@ extern "C" int mpgan_bn_act_bwd_reduce(int dtype, const void* dy, int64_t lddy, 
                                        float leaky_slope, double* sums, void* stream) {
   MPGAN_REQUIRE(pixels > 0 && c > 0 && ldx >= c && lddy >= c && sums, MPGAN_ERR_SHAPE, "bn_act_bwd_reduce: bad shape");
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(dy, lddy, dtype);
-  const size_t smem = (size_t)(2 * c + 1) * sizeof(double);
-  MPGAN_REQUIRE(smem <= 48 * 1024, MPGAN_ERR_UNSUPPORTED, "bn_act_bwd_reduce: too many channels (%d)", c);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     if (vec)
-      bn_act_bwd_reduce_kernel<T, 8><<<ew_grid(pixels, c / 8, 4), kThreads, smem, (cudaStream_t)stream>>>(
+      bn_act_bwd_reduce_kernel<T, 8><<<ew_grid(pixels, c / 8, 4, 16), kThreads, 0, (cudaStream_t)stream>>>(
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums);
     else
-      bn_act_bwd_reduce_kernel<T, 1><<<ew_grid(pixels, c, 4), kThreads, smem, (cudaStream_t)stream>>>(
+      bn_act_bwd_reduce_kernel<T, 1><<<ew_grid(pixels, c, 8, 32), kThreads, 0, (cudaStream_t)stream>>>(
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums);
     MPGAN_CHECK_LAUNCH("bn_act_bwd_reduce");
     return 0;
@@ -417,13 +540,12 @@ extern "C" int mpgan_bn_act_bwd_apply(int dtype, const void* dy, int64_t lddy, c
   MPGAN_REQUIRE((mean == nullptr) == (invstd == nullptr), MPGAN_ERR_SHAPE, "mean/invstd must both be given");
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(dy, lddy, dtype) && vec_ok(dx, lddx, dtype);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    const size_t smem = dbias ? (size_t)c * sizeof(float) : 0;
     if (vec)
-      bn_act_bwd_apply_kernel<T, 8><<<ew_grid(pixels, c / 8), kThreads, smem, (cudaStream_t)stream>>>(
+      bn_act_bwd_apply_kernel<T, 8><<<ew_grid(pixels, c / 8, 6, 8), kThreads, 0, (cudaStream_t)stream>>>(
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums,
           dgamma, dbeta, dalpha, dbias, (T*)dx, lddx);
     else
-      bn_act_bwd_apply_kernel<T, 1><<<ew_grid(pixels, c), kThreads, smem, (cudaStream_t)stream>>>(
+      bn_act_bwd_apply_kernel<T, 1><<<ew_grid(pixels, c, 8, 16), kThreads, 0, (cudaStream_t)stream>>>(
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums,
           dgamma, dbeta, dalpha, dbias, (T*)dx, lddx);
     MPGAN_CHECK_LAUNCH("bn_act_bwd_apply");

@@ -172,6 +172,16 @@ wgrad_x1_kernel(C1Geom p, const T* __restrict__ x, int64_t ldx, const T* __restr
 
 }  // namespace mpgan
 
+namespace mpgan {
+// conv_c1_fast.cu: rank-2 3x3 fast paths; return 1 when they do not cover the call
+int c1f_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* w, const float* bias, void* y,
+              int64_t ldy, double* stats, cudaStream_t s);
+int c1f_bprop(const MpganConvGeom* g, int dtype, const void* y, int64_t ldy, const void* w, const float* bias, void* x,
+              int64_t ldx, double* stats, cudaStream_t s);
+int c1f_wgrad(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* y, int64_t ldy, float* dw,
+              cudaStream_t s);
+}  // namespace mpgan
+
 using namespace mpgan;
 
 // 1 if the direct one-channel kernels cover (geometry, direction): 0 fprop with cy == 1, 1 bprop with cx == 1,
@@ -179,7 +189,12 @@ using namespace mpgan;
 extern "C" int mpgan_c1_supported(const MpganConvGeom* g, int direction) {
   if (!g) return 0;
   int taps = g->k[0] * g->k[1] * g->k[2];
-  if (direction == 0) return g->cy == 1 && taps * g->cx * 4 <= 48 * 1024;
+  if (direction == 0) {
+    if (g->cx == 1 && g->rank == 2 && g->k[1] == 3 && g->k[2] == 3 && g->stride[1] == g->stride[2] &&
+        g->stride[1] <= 2 && g->pad[1] == g->pad[2] && g->pad[1] <= 1 && (g->cy == 1 || (g->cy % 8 == 0 && (g->cy / 8 <= 32 ? 32 % (g->cy / 8) == 0 : 256 % (g->cy / 8) == 0))))
+      return 1;   // rank-2 3x3 one-input-channel layer: conv_c1_fast.cu
+    return g->cy == 1 && taps * g->cx * 4 <= 48 * 1024;
+  }
   if (direction == 1) return g->cx == 1 && taps * g->cy * 4 <= 48 * 1024;
   if (direction == 2) return g->cx == 1 && g->cy * taps <= 1024 && (256 * (g->cy + 1) + taps * 256) * 4 <= 160 * 1024;
   return 0;
@@ -203,21 +218,32 @@ static int launch_to1(const C1Geom& p, const void* in, int64_t ldi, const void* 
 }
 
 extern "C" int mpgan_c1_conv_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* w,
-                                   const float* bias, void* y, int64_t ldy, void* stream) {
+                                   const float* bias, void* y, int64_t ldy, double* stats, void* stream) {
   C1Geom p;
   int rc = make_c1(g, &p);
   if (rc) return rc;
-  MPGAN_REQUIRE(mpgan_c1_supported(g, 0), MPGAN_ERR_UNSUPPORTED, "c1 fprop needs cy == 1");
-  MPGAN_DISPATCH_DTYPE(dtype, T, return (launch_to1<T, 0>(p, x, ldx, w, bias, y, ldy, (cudaStream_t)stream)));
+  rc = c1f_fprop(g, dtype, x, ldx, w, bias, y, ldy, stats, (cudaStream_t)stream);   // rank-2 3x3, cx == 1
+  if (rc != 1) return rc;
+  if (g->cy == 1 && (size_t)p.taps * g->cx * 4 <= 48 * 1024) {
+    MPGAN_DISPATCH_DTYPE(dtype, T, rc = (launch_to1<T, 0>(p, x, ldx, w, bias, y, ldy, (cudaStream_t)stream)));
+  } else {  // e.g. an unaligned channel slice: the generic implicit-GEMM kernel covers everything
+    rc = mpgan_conv_fprop(g, dtype, x, ldx, w, bias, y, ldy, stream);
+  }
+  if (rc || !stats) return rc;
+  return mpgan_bn_stats(dtype, y, ldy, (int64_t)p.n * p.ys[0] * p.ys[1] * p.ys[2], p.cy, stats, stream);
 }
 
 extern "C" int mpgan_c1_conv_bprop(const MpganConvGeom* g, int dtype, const void* y, int64_t ldy, const void* w,
-                                   const float* bias, void* x, int64_t ldx, void* stream) {
+                                   const float* bias, void* x, int64_t ldx, double* stats, void* stream) {
   C1Geom p;
   int rc = make_c1(g, &p);
   if (rc) return rc;
   MPGAN_REQUIRE(mpgan_c1_supported(g, 1), MPGAN_ERR_UNSUPPORTED, "c1 bprop needs cx == 1");
-  MPGAN_DISPATCH_DTYPE(dtype, T, return (launch_to1<T, 1>(p, y, ldy, w, bias, x, ldx, (cudaStream_t)stream)));
+  rc = c1f_bprop(g, dtype, y, ldy, w, bias, x, ldx, stats, (cudaStream_t)stream);
+  if (rc != 1) return rc;
+  MPGAN_DISPATCH_DTYPE(dtype, T, rc = (launch_to1<T, 1>(p, y, ldy, w, bias, x, ldx, (cudaStream_t)stream)));
+  if (rc || !stats) return rc;
+  return mpgan_bn_stats(dtype, x, ldx, (int64_t)p.n * p.xs[0] * p.xs[1] * p.xs[2], p.cx, stats, stream);
 }
 
 extern "C" int mpgan_c1_conv_wgrad(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* y,
@@ -226,6 +252,8 @@ extern "C" int mpgan_c1_conv_wgrad(const MpganConvGeom* g, int dtype, const void
   int rc = make_c1(g, &p);
   if (rc) return rc;
   MPGAN_REQUIRE(mpgan_c1_supported(g, 2), MPGAN_ERR_UNSUPPORTED, "c1 wgrad needs cx == 1 and cy*taps <= 1024");
+  rc = c1f_wgrad(g, dtype, x, ldx, y, ldy, dw, (cudaStream_t)stream);
+  if (rc != 1) return rc;
   const int64_t P = (int64_t)p.n * p.ys[0] * p.ys[1] * p.ys[2];
   int64_t want = (int64_t)num_sms() * 4;
   int64_t ppb = ceil_div(ceil_div(P, want), 256) * 256;

@@ -70,7 +70,7 @@ template <int BN, int KC> struct TapCfg {
   static constexpr int B_TX = BN * KC * 2;
   static constexpr int B_BYTES = B_TX < 1024 ? 1024 : B_TX;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int AUX_BYTES = 256 + 2 * 512 * 4;  // barriers + stats[2*n_total<=1024 floats]
+  static constexpr int AUX_BYTES = 256 + 4 * 2 * 512 * 4;  // barriers + per-epilogue-warp stats[2*n_total<=1024 floats]
   static constexpr int MAX_STAGES = (kSmemLimit - 1024 - AUX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + AUX_BYTES;
@@ -122,7 +122,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < 2 * P.n_total; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * 2 * P.n_total; i += blockDim.x) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -253,9 +253,10 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
           }
           float s1 = warp_transpose_reduce32(v, lane);
           float s2 = warp_transpose_reduce32(sq, lane);
-          if (lane < CH) {
-            atomicAdd(&s_stats[nbase + c0 + lane], s1);
-            atomicAdd(&s_stats[P.n_total + nbase + c0 + lane], s2);
+          if (lane < CH) {  // slot owned by (this warp, this lane): fixed accumulation order, run-to-run reproducible
+            float* sl = s_stats + q * 2 * P.n_total;
+            sl[nbase + c0 + lane] += s1;
+            sl[P.n_total + nbase + c0 + lane] += s2;
           }
         }
       }
@@ -269,8 +270,9 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
   __syncthreads();
   if (P.stats) {
     for (int i = threadIdx.x; i < 2 * P.n_total; i += blockDim.x) {
-      float s = s_stats[i];
-      if (s != 0.f) atomicAdd(&P.stats[i], (double)s);
+      const double s = ((double)s_stats[i] + (double)s_stats[2 * P.n_total + i]) +
+                       ((double)s_stats[4 * P.n_total + i] + (double)s_stats[6 * P.n_total + i]);
+      if (s != 0.0) atomicAdd(&P.stats[i], s);
     }
   }
   if (warp == 2) {

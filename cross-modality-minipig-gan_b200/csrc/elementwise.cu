@@ -28,6 +28,48 @@ __global__ void add_copy_kernel(const TI* __restrict__ a, int64_t lda, const TI*
   }
 }
 
+// 8 channels per thread (16-byte bf16 / 2 x 16-byte fp32 accesses); C, lda, ldb, ldy multiples of 8, 16-byte bases
+__device__ __forceinline__ void ld8(const float* p, float* o) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float* o) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void st8(float* p, const float* o) {
+  *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float* o) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+add_copy_vec_kernel(const TI* __restrict__ a, int64_t lda, const TI* __restrict__ b, int64_t ldb, TO* __restrict__ y,
+                    int64_t ldy, int64_t P, int cv) {
+  const int64_t total = P * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / cv;
+    const int c = (int)(i - p * cv) * 8;
+    float v[8], w[8];
+    ld8(a + p * lda + c, v);
+    if (b) {
+      ld8(b + p * ldb + c, w);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += w[e];
+    }
+    st8(y + p * ldy + c, v);
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void tanh_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -139,9 +181,15 @@ extern "C" int mpgan_device_ok(void) {
 extern "C" int mpgan_add_copy(int dtype_in, const void* a, int64_t lda, const void* b, int64_t ldb, int dtype_out,
                               void* y, int64_t ldy, int64_t pixels, int32_t c, void* stream) {
   MPGAN_REQUIRE(pixels > 0 && c > 0 && lda >= c && ldy >= c && (!b || ldb >= c), MPGAN_ERR_SHAPE, "add_copy: bad shape");
+  const bool vec = c % 8 == 0 && lda % 8 == 0 && ldy % 8 == 0 && (!b || ldb % 8 == 0) && ((uintptr_t)a % 16) == 0 &&
+                   ((uintptr_t)y % 16) == 0 && (!b || ((uintptr_t)b % 16) == 0);
   DISPATCH2(dtype_in, dtype_out, TI, TO, {
-    add_copy_kernel<TI, TO><<<ew_grid(pixels * c), 256, 0, (cudaStream_t)stream>>>((const TI*)a, lda, (const TI*)b,
-                                                                                 ldb, (TO*)y, ldy, pixels, c);
+    if (vec)
+      add_copy_vec_kernel<TI, TO><<<ew_grid(pixels * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+          (const TI*)a, lda, (const TI*)b, ldb, (TO*)y, ldy, pixels, c / 8);
+    else
+      add_copy_kernel<TI, TO><<<ew_grid(pixels * c), 256, 0, (cudaStream_t)stream>>>((const TI*)a, lda, (const TI*)b,
+                                                                                   ldb, (TO*)y, ldy, pixels, c);
     MPGAN_CHECK_LAUNCH("add_copy");
     return 0;
   });
@@ -168,7 +216,9 @@ extern "C" int mpgan_tanh_bwd(int dtype, const void* dy, const void* y, void* dx
 extern "C" int mpgan_colsum(int dtype, const void* x, int64_t ldx, int64_t pixels, int32_t c, float* out,
                             void* stream) {
   MPGAN_REQUIRE(pixels > 0 && c > 0 && ldx >= c, MPGAN_ERR_SHAPE, "colsum: bad shape");
-  const int ppb = 2048;
+  // enough blocks to cover the machine twice; each block walks >= 64 pixels
+  int64_t ppb64 = ceil_div(pixels, (int64_t)num_sms() * 2);
+  const int ppb = (int)(ppb64 < 64 ? 64 : (ppb64 > 2048 ? 2048 : ppb64));
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     colsum_kernel<T><<<(int)ceil_div(pixels, ppb), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, pixels, c, out, ppb);
     MPGAN_CHECK_LAUNCH("colsum");

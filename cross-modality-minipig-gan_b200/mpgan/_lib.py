@@ -30,8 +30,8 @@ _SIGS = {
     "mpgan_conv_bprop": (c_int, [_G, c_int, _P, c_int64, _P, _P, _P, c_int64, _P]),
     "mpgan_conv_wgrad": (c_int, [_G, c_int, _P, c_int64, _P, c_int64, _P, _P]),
     "mpgan_c1_supported": (c_int, [_G, c_int]),
-    "mpgan_c1_conv_fprop": (c_int, [_G, c_int, _P, c_int64, _P, _P, _P, c_int64, _P]),
-    "mpgan_c1_conv_bprop": (c_int, [_G, c_int, _P, c_int64, _P, _P, _P, c_int64, _P]),
+    "mpgan_c1_conv_fprop": (c_int, [_G, c_int, _P, c_int64, _P, _P, _P, c_int64, _P, _P]),
+    "mpgan_c1_conv_bprop": (c_int, [_G, c_int, _P, c_int64, _P, _P, _P, c_int64, _P, _P]),
     "mpgan_c1_conv_wgrad": (c_int, [_G, c_int, _P, c_int64, _P, c_int64, _P, _P]),
     "mpgan_tc_supported": (c_int, [_G, c_int]),
     "mpgan_tc_conv_fprop": (c_int, [_G, _P, c_int64, _P, _P, _P, c_int64, _P, _P]),
@@ -42,6 +42,8 @@ _SIGS = {
     "mpgan_bn_finalize": (c_int, [_P, c_int64, c_int32, _P, _P, c_float, c_float, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mpgan_bn_act_apply": (c_int, [c_int, _P, c_int64, c_int64, c_int32, _P, _P, c_int, _P, c_float, _P, c_int64, _P,
                                    c_int64, _P]),
+    "mpgan_bn_train_apply": (c_int, [c_int, _P, c_int64, c_int64, c_int32, _P, _P, _P, c_float, c_float, _P, _P, _P,
+                                     _P, _P, _P, _P, c_int, _P, c_float, _P, c_int64, _P, c_int64, _P]),
     "mpgan_bn_act_bwd_reduce": (c_int, [c_int, _P, c_int64, _P, c_int64, c_int64, c_int32, _P, _P, _P, _P, c_int, _P,
                                         c_float, _P, _P]),
     "mpgan_bn_act_bwd_apply": (c_int, [c_int, _P, c_int64, _P, c_int64, c_int64, c_int32, _P, _P, _P, _P, c_int, _P,

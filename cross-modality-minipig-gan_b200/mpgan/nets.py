@@ -37,6 +37,21 @@ class Plan:
         self.dtype = rt.dtype
         self.tape = []
         self.extra = {}
+        self._arena = None
+        self._arena_used = 0
+
+    ARENA = 1 << 15  # fp64 slots: every BatchNorm statistic / backward sum of one pass, zeroed by ONE memset
+
+    def zeros64(self, n, device):
+        """n zeroed fp64 accumulators (a slice of the per-pass arena)."""
+        if self._arena is None:
+            self._arena = torch.zeros(self.ARENA, dtype=torch.float64, device=device)
+        n8 = (n + 7) // 8 * 8
+        if self._arena_used + n8 > self.ARENA:
+            return torch.zeros(n, dtype=torch.float64, device=device)
+        out = self._arena[self._arena_used:self._arena_used + n]
+        self._arena_used += n8
+        return out
 
 
 def _new(ref, shape, dtype=None):
@@ -78,10 +93,13 @@ def bn_act_forward(c, bn, act, alpha, leaky, res, out, plan, stats, fused_stats)
         ops.bn_stats(c, stats)
     buf = torch.empty((4, ch), dtype=torch.float32, device=c.device)
     mean, invstd, scale, shift = buf[0], buf[1], buf[2], buf[3]
-    ops.bn_finalize(stats if plan.training else None, ops.pixels(c), bn, plan.training, mean, invstd, scale, shift)
     if out is None:
         out = _new(c, c.shape)
-    ops.bn_act_apply(c, scale, shift, act, alpha, leaky, res, out)
+    if plan.training:
+        ops.bn_train_apply(c, stats, bn, buf, act, alpha, leaky, res, out)
+    else:
+        ops.bn_finalize(None, ops.pixels(c), bn, False, mean, invstd, scale, shift)
+        ops.bn_act_apply(c, scale, shift, act, alpha, leaky, res, out)
     return out, (mean, invstd, scale, shift)
 
 
@@ -89,7 +107,7 @@ def bn_act_backward(dy, c, saved, bn, act, alpha_param, leaky, plan, trained, co
     """conv_db: bias-gradient buffer of the convolution that produced c (accumulated in the same pass)."""
     mean, invstd, scale, shift = saved
     ch = c.shape[-1]
-    sums = torch.zeros(2 * ch + 1, dtype=torch.float64, device=c.device)
+    sums = plan.zeros64(2 * ch + 1, c.device)
     dc = _new(c, c.shape)
     wg = plan.need_wgrad
     ops.bn_act_bwd(dy, c, mean if trained else None, invstd if trained else None, scale, shift, act, alpha_param,
@@ -140,7 +158,7 @@ class Convolution(nn.Sequential):
                 plan.tape.append((x,))
             return y
         ch = self.out_channels
-        stats = torch.zeros(2 * ch, dtype=torch.float64, device=x.device) if plan.training else None
+        stats = plan.zeros64(2 * ch, x.device) if plan.training else None
         c, fused = conv_apply(rec, x, stats=stats)
         y, saved = bn_act_forward(c, self.norm, ACT_PRELU, self.act.weight, 0.0, res, out, plan, stats, fused)
         if plan.save:
@@ -457,7 +475,7 @@ class _ConvBnLeakyStack(_PlanNet):
         for conv, bn in zip(convs, bns):
             rec = rt.rec[conv]
             ch = conv.out_channels
-            stats = torch.zeros(2 * ch, dtype=torch.float64, device=x.device) if plan.training else None
+            stats = plan.zeros64(2 * ch, x.device) if plan.training else None
             c, fused = conv_apply(rec, h, stats=stats)
             if want_acts:  # test_runs/GAN.py:186-190 clones conv, bn and (in-place) lrelu outputs separately
                 bn_out, saved = bn_act_forward(c, bn, ACT_NONE, None, 0.0, None, None, plan, stats, fused)

@@ -115,8 +115,8 @@ def conv_fprop(spec, x, w, bias, out=None, stats=None, use_tc=True, use_c1=True)
         return out, stats is not None
     if use_c1 and lib.mpgan_c1_supported(ctypes.byref(g), 0):
         check(lib.mpgan_c1_conv_fprop(ctypes.byref(g), dt(x), ptr(x), ld(x), ptr(w), ptr(bias), ptr(out), ld(out),
-                                      _stream()), "c1_conv_fprop")
-        return out, False
+                                      ptr(stats), _stream()), "c1_conv_fprop")
+        return out, stats is not None
     check(lib.mpgan_conv_fprop(ctypes.byref(g), dt(x), ptr(x), ld(x), ptr(w), ptr(bias), ptr(out), ld(out), _stream()),
           "conv_fprop")
     return out, False
@@ -139,8 +139,8 @@ def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True,
         return out, stats is not None
     if use_c1 and lib.mpgan_c1_supported(ctypes.byref(g), 1):
         check(lib.mpgan_c1_conv_bprop(ctypes.byref(g), dt(y), ptr(y), ld(y), ptr(w), ptr(bias), ptr(out), ld(out),
-                                      _stream()), "c1_conv_bprop")
-        return out, False
+                                      ptr(stats), _stream()), "c1_conv_bprop")
+        return out, stats is not None
     check(lib.mpgan_conv_bprop(ctypes.byref(g), dt(y), ptr(y), ld(y), ptr(w), ptr(bias), ptr(out), ld(out), _stream()),
           "conv_bprop")
     return out, False
@@ -192,6 +192,20 @@ def bn_act_apply(x, scale, shift, act, alpha, leaky, res, out):
     check(lib.mpgan_bn_act_apply(dt(x), ptr(x), ld(x), pixels(x), x.shape[-1], ptr(scale), ptr(shift), act,
                                  ptr(alpha), leaky, ptr(res), ld(res) if res is not None else 0, ptr(out), ld(out),
                                  _stream()), "bn_act_apply")
+    return out
+
+
+def bn_train_apply(x, stats, bn, saved, act, alpha, leaky, res, out):
+    """Training-mode BatchNorm finalize + normalise + activation (+ residual) in one launch.
+    saved: (4, C) fp32 buffer receiving mean, invstd, scale, shift."""
+    lib = _lib.require_device()
+    check_act(x), check_act(out)
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    check(lib.mpgan_bn_train_apply(dt(x), ptr(x), ld(x), pixels(x), x.shape[-1], ptr(stats), ptr(bn.weight),
+                                   ptr(bn.bias), bn.eps, mom, ptr(bn.running_mean), ptr(bn.running_var),
+                                   ptr(bn.num_batches_tracked), ptr(saved[0]), ptr(saved[1]), ptr(saved[2]),
+                                   ptr(saved[3]), act, ptr(alpha), leaky, ptr(res), ld(res) if res is not None else 0,
+                                   ptr(out), ld(out), _stream()), "bn_train_apply")
     return out
 
 

@@ -77,14 +77,16 @@ size_t mpgan_tc_conv_wgrad_workspace(const MpganConvGeom* g);
 int mpgan_tc_conv_wgrad(const MpganConvGeom* g, const void* x, int64_t ldx, const void* y, int64_t ldy, float* dw,
                         void* workspace, size_t workspace_bytes, void* stream);
 /* ---- convolution, one-channel edge layers: bandwidth-bound direct kernels, rank 2/3, f32 or bf16 ----
- * fprop with cy == 1 (e.g. ConvTranspose 32->1 data gradient / 1->1 conv), bprop with cx == 1 (ConvTranspose 32->1
+ * fprop with cy == 1 or (rank 2, 3x3) cx == 1 (G's 1->16 and D's 1->64 first convolutions), bprop with cx == 1 (ConvTranspose 32->1
  * forward, data gradient of the 1->16 / 1->64 first convolutions), wgrad with cx == 1.  Same contracts as the generic
  * entry points; mpgan_c1_supported() says whether a (geometry, direction) is covered. */
 int mpgan_c1_supported(const MpganConvGeom* g, int direction /*0 fprop,1 bprop,2 wgrad*/);
 int mpgan_c1_conv_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* w,
-                        const float* bias, void* y, int64_t ldy, void* stream);
+                        const float* bias, void* y, int64_t ldy, double* stats /* nullable: BN sums of y */,
+                        void* stream);
 int mpgan_c1_conv_bprop(const MpganConvGeom* g, int dtype, const void* y, int64_t ldy, const void* w,
-                        const float* bias, void* x, int64_t ldx, void* stream);
+                        const float* bias, void* x, int64_t ldx, double* stats /* nullable: BN sums of x */,
+                        void* stream);
 int mpgan_c1_conv_wgrad(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* y, int64_t ldy,
                         float* dw, void* stream);
 
@@ -103,6 +105,14 @@ int mpgan_bn_finalize(const double* stats, int64_t pixels, int32_t c, const floa
 int mpgan_bn_act_apply(int dtype, const void* x, int64_t ldx, int64_t pixels, int32_t c, const float* scale,
                        const float* shift, int act, const float* alpha, float leaky_slope, const void* res,
                        int64_t ldres, void* y, int64_t ldy, void* stream);
+/* training-mode finalize + apply in one launch: every thread derives scale/shift of its own channels from the fp64
+ * statistics (the arithmetic of mpgan_bn_finalize); the first block also writes mean/invstd/scale/shift (saved for
+ * the backward pass) and updates running_mean/var and num_batches_tracked. */
+int mpgan_bn_train_apply(int dtype, const void* x, int64_t ldx, int64_t pixels, int32_t c, const double* stats,
+                         const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                         float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd, float* scale,
+                         float* shift, int act, const float* alpha, float leaky_slope, const void* res,
+                         int64_t ldres, void* y, int64_t ldy, void* stream);
 /* backward of y = act(bn(x)): pass 1 reduces  sums[0:C]=sum g, sums[C:2C]=sum g*xhat, sums[2C]=sum dy*min(z,0)
  * (PReLU slope grad), all fp64 accumulating;  pass 2 writes dx and accumulates dgamma/dbeta/dalpha (fp32) and, when
  * dbias != NULL, the bias gradient of the convolution that produced x: dbias[c] += sum_p dx[p,c]. */

@@ -72,8 +72,14 @@ def test_conv_generic_fwd_dgrad_wgrad(case, dtype, use_c1):
     y.backward(dy)
     spec = ops.ConvSpec(rank, cin, cout, k, s, p)
     tol = 1e-5 if dtype == torch.float32 else 6e-3
-    yk, _ = ops.conv_fprop(spec, cl(x.detach(), dtype), oti(w.detach(), dtype), b, use_tc=False, use_c1=use_c1)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV) if use_c1 else None
+    yk, fused = ops.conv_fprop(spec, cl(x.detach(), dtype), oti(w.detach(), dtype), b, use_tc=False, use_c1=use_c1,
+                               stats=stats)
     assert rel_l2(uncl(yk), y) <= tol
+    if fused:  # BatchNorm statistics of the stored values, reduced by the same launch (one-channel fast path)
+        ykd = yk.double().reshape(-1, cout)
+        assert torch.allclose(stats[:cout], ykd.sum(0), rtol=1e-6, atol=1e-6)
+        assert torch.allclose(stats[cout:], (ykd * ykd).sum(0), rtol=1e-6, atol=1e-6)
     dxk, _ = ops.conv_bprop(spec, cl(dy, dtype), oti(w.detach(), dtype), None, None, xs=(size,) * rank, use_tc=False,
                             use_c1=use_c1)
     assert rel_l2(uncl(dxk), x.grad) <= tol
@@ -193,7 +199,10 @@ def test_tc_conv_full_size_linearity():
 # ------------------------------------------------------------------ batch norm / activations
 @pytest.mark.parametrize("c,act", [(1, ACT_PRELU), (16, ACT_PRELU), (64, ACT_LEAKY), (24, ACT_NONE), (512, ACT_LEAKY)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_bn_act_forward_backward(c, act, dtype):
+@pytest.mark.parametrize("fused", [False, True])
+def test_bn_act_forward_backward(c, act, dtype, fused):
+    """fused: mpgan_bn_train_apply (finalize + apply in one launch, the training path of the networks) instead of
+    mpgan_bn_finalize followed by mpgan_bn_act_apply."""
     n, h, w_ = 3, 9, 11
     x = (rnd(n, c, h, w_, seed=31) * 2 + 0.3)
     res = rnd(n, c, h, w_, seed=32)
@@ -218,9 +227,12 @@ def test_bn_act_forward_backward(c, act, dtype):
     stats = torch.zeros(2 * c, dtype=torch.float64, device=DEV)
     ops.bn_stats(xc, stats)
     buf = torch.empty(4, c, device=DEV)
-    ops.bn_finalize(stats, n * h * w_, bn_k, True, buf[0], buf[1], buf[2], buf[3])
     a = alpha.detach() if act == ACT_PRELU else None
-    y = ops.bn_act_apply(xc, buf[2], buf[3], act, a, 0.2, cl(res, dtype), torch.empty_like(xc))
+    if fused:
+        y = ops.bn_train_apply(xc, stats, bn_k, buf, act, a, 0.2, cl(res, dtype), torch.empty_like(xc))
+    else:
+        ops.bn_finalize(stats, n * h * w_, bn_k, True, buf[0], buf[1], buf[2], buf[3])
+        y = ops.bn_act_apply(xc, buf[2], buf[3], act, a, 0.2, cl(res, dtype), torch.empty_like(xc))
     tol = 2e-5 if dtype == torch.float32 else 8e-3
     assert rel_l2(uncl(y), yr) <= tol
     assert rel_l2(bn_k.running_mean, bn.running_mean) <= 1e-5 and rel_l2(bn_k.running_var, bn.running_var) <= 1e-5
