@@ -38,6 +38,30 @@ template <> struct Vec<bf16, 8> {
     *reinterpret_cast<uint4*>(p) = u;
   }
 };
+template <> struct Vec<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float* o) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* o) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+};
+template <> struct Vec<bf16, 4> {
+  static __device__ __forceinline__ void load(const bf16* p, float* o) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float* o) {
+    uint2 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
 template <typename T> struct Vec<T, 1> {
   static __device__ __forceinline__ void load(const T* p, float* o) { o[0] = to_f(*p); }
   static __device__ __forceinline__ void store(T* p, const float* o) { *p = from_f<T>(o[0]); }
@@ -57,6 +81,7 @@ __device__ __forceinline__ float act_grad(float z, int act, float slope) {
 
 constexpr int kThreads = 256;
 constexpr int kPixPerBlock = 2048;  // pixel run per block for the reductions
+constexpr int kMaxPixPerThread = 512;
 
 // ---------------- statistics: sum, sum of squares ----------------
 template <typename T, int V>
@@ -239,8 +264,8 @@ bn_act_apply_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, cons
 // Block-level reduction of NV per-thread fp64 partials that belong to channel group (tid % cv); the totals of
 // value i of group g are added to out[i_hi * C + g*V + i_lo] (i = i_hi*V + i_lo) with one global atomic each.
 // sm: kThreads*NV doubles.
-template <int V, int NV, typename OutT>
-__device__ __forceinline__ void group_reduce_to_global(double (&a)[NV], int cv, int C, int64_t tid, double* sm,
+template <int V, int NV, typename A, typename OutT>
+__device__ __forceinline__ void group_reduce_to_global(A (&a)[NV], int cv, int C, int64_t tid, A* sm,
                                                        OutT* __restrict__ out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (cv <= 32 && (32 % cv) == 0) {
@@ -257,7 +282,7 @@ __device__ __forceinline__ void group_reduce_to_global(double (&a)[NV], int cv, 
       const int g = j / NV, i = j - g * NV;
       double t = 0.0;
 #pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) t += sm[(w * cv + g) * NV + i];
+      for (int w = 0; w < kThreads / 32; ++w) t += (double)sm[(w * cv + g) * NV + i];
       atomicAdd(&out[(i / V) * C + g * V + (i % V)], (OutT)t);
     }
   } else if ((kThreads % cv) == 0) {
@@ -268,7 +293,7 @@ __device__ __forceinline__ void group_reduce_to_global(double (&a)[NV], int cv, 
     for (int j = threadIdx.x; j < cv * NV; j += kThreads) {
       const int g = j / NV, i = j - g * NV;
       double t = 0.0;
-      for (int k = 0; k < reps; ++k) t += sm[(g + k * cv) * NV + i];
+      for (int k = 0; k < reps; ++k) t += (double)sm[(g + k * cv) * NV + i];
       atomicAdd(&out[(i / V) * C + g * V + (i % V)], (OutT)t);
     }
   } else {  // channel group varies with the block: straight to global (odd channel counts; tests only)
@@ -280,12 +305,14 @@ __device__ __forceinline__ void group_reduce_to_global(double (&a)[NV], int cv, 
 
 // ---------------- backward pass 1: reductions ----------------
 template <typename T, int V>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ x, int64_t ldx, int64_t P,
                          int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ scale, const float* __restrict__ shift, int act,
                          const float* __restrict__ alpha, float leaky, double* __restrict__ sums) {
-  __shared__ double sm[kThreads * 2 * V];
+  // per-thread partials are fp32 (<= kMaxPixPerThread terms each, no cancellation structure in these sums),
+  // everything above the block level is fp64
+  __shared__ float sm[kThreads * 2 * V];
   __shared__ double sslope[kThreads / 32];
   const int cv = C / V;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,10 +326,10 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
     sc[e] = scale ? scale[c0 + e] : 1.f; sh[e] = shift ? shift[c0 + e] : 0.f;
     mu[e] = mean ? mean[c0 + e] : 0.f; is[e] = invstd ? invstd[c0 + e] : 1.f;
   }
-  double a[2 * V], aslope = 0.0;
+  float a[2 * V], fs = 0.f;
 #pragma unroll
-  for (int e = 0; e < 2 * V; ++e) a[e] = 0.0;
-  constexpr int U = 4;
+  for (int e = 0; e < 2 * V; ++e) a[e] = 0.f;
+  constexpr int U = V == 4 ? 4 : 2;
   for (int64_t p = tid / cv; p < P; p += U * pstep) {
     float g[U][V], xv[U][V];
 #pragma unroll
@@ -315,26 +342,21 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
         for (int e = 0; e < V; ++e) { g[u][e] = 0.f; xv[u][e] = 0.f; }
       }
     }
-    float fs = 0.f;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const float z = fmaf(xv[u][e], sc[e], sh[e]);
         if (act == MPGAN_ACT_PRELU && z <= 0.f) fs = fmaf(g[u][e], z, fs);
         const float gz = g[u][e] * act_grad(z, act, slope);
-        s1 += gz;
-        s2 = fmaf(gz, (xv[u][e] - mu[e]) * is[e], s2);
+        a[e] += gz;
+        a[V + e] = fmaf(gz, (xv[u][e] - mu[e]) * is[e], a[V + e]);
       }
-      a[e] += (double)s1;
-      a[V + e] += (double)s2;
     }
-    aslope += (double)fs;
   }
-  group_reduce_to_global<V, 2 * V, double>(a, cv, C, tid, sm, sums);
+  group_reduce_to_global<V, 2 * V, float, double>(a, cv, C, tid, sm, sums);
   if (act == MPGAN_ACT_PRELU) {
-    double w = warp_sum(aslope);
+    double w = warp_sum((double)fs);
     if ((threadIdx.x & 31) == 0) sslope[threadIdx.x >> 5] = w;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -349,13 +371,13 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
 // ---------------- backward pass 2: dx, parameter grads, and (optionally) the conv bias grad = sum_p dx ----------------
 // dx = k1*gz + k2*(x - mu) + k3 with k1 = scale, k2 = -scale*invstd*mean(g*xhat), k3 = -scale*mean(g)
 template <typename T, int V>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 bn_act_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ x, int64_t ldx, int64_t P,
                         int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ scale, const float* __restrict__ shift, int act,
                         const float* __restrict__ alpha, float leaky, const double* __restrict__ sums,
                         float* dgamma, float* dbeta, float* dalpha, float* dbias, T* __restrict__ dx, int64_t lddx) {
-  __shared__ double sm[kThreads * V];
+  __shared__ float sm[kThreads * V];
   const int cv = C / V;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
@@ -382,37 +404,36 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restr
     k2[e] = -sc[e] * is * mgx;
     k3[e] = -sc[e] * mg;
   }
-  double bsum[V];
+  float bsum[V];
 #pragma unroll
-  for (int e = 0; e < V; ++e) bsum[e] = 0.0;
-  int64_t p = tid / cv;
-  for (; p < P; p += 2 * pstep) {
-    const bool two = p + pstep < P;
-    float g0[V], x0[V], g1[V], x1[V];
-    Vec<T, V>::load(dy + p * lddy + c0, g0);
-    Vec<T, V>::load(x + p * ldx + c0, x0);
-    if (two) { Vec<T, V>::load(dy + (p + pstep) * lddy + c0, g1); Vec<T, V>::load(x + (p + pstep) * ldx + c0, x1); }
+  for (int e = 0; e < V; ++e) bsum[e] = 0.f;
+  constexpr int U = V == 4 ? 4 : 2;
+  for (int64_t p = tid / cv; p < P; p += U * pstep) {
+    float g[U][V], xv[U][V];
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const float z = fmaf(x0[e], sc[e], sh[e]);
-      g0[e] = fmaf(sc[e], g0[e] * act_grad(z, act, slope), fmaf(k2[e], x0[e] - mu[e], k3[e]));
-      if (two) {
-        const float z1 = fmaf(x1[e], sc[e], sh[e]);
-        g1[e] = fmaf(sc[e], g1[e] * act_grad(z1, act, slope), fmaf(k2[e], x1[e] - mu[e], k3[e]));
+    for (int u = 0; u < U; ++u) {
+      if (p + u * pstep < P) {
+        Vec<T, V>::load(dy + (p + u * pstep) * lddy + c0, g[u]);
+        Vec<T, V>::load(x + (p + u * pstep) * ldx + c0, xv[u]);
       }
     }
-    Vec<T, V>::store(dx + p * lddx + c0, g0);
-    if (two) Vec<T, V>::store(dx + (p + pstep) * lddx + c0, g1);
-    if (dbias) {  // bias gradient of the producing conv: column sum of dx as stored (rounded to T)
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        float s = to_f(from_f<T>(g0[e]));
-        if (two) s += to_f(from_f<T>(g1[e]));
-        bsum[e] += (double)s;
+    for (int u = 0; u < U; ++u) {
+      if (p + u * pstep < P) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float z = fmaf(xv[u][e], sc[e], sh[e]);
+          g[u][e] = fmaf(sc[e], g[u][e] * act_grad(z, act, slope), fmaf(k2[e], xv[u][e] - mu[e], k3[e]));
+        }
+        Vec<T, V>::store(dx + (p + u * pstep) * lddx + c0, g[u]);
+        if (dbias) {  // bias gradient of the producing conv: column sum of dx as stored (rounded to T)
+#pragma unroll
+          for (int e = 0; e < V; ++e) bsum[e] += to_f(from_f<T>(g[u][e]));
+        }
       }
     }
   }
-  if (dbias) group_reduce_to_global<V, V, float>(bsum, cv, C, tid, sm, dbias);
+  if (dbias) group_reduce_to_global<V, V, float, float>(bsum, cv, C, tid, sm, dbias);
 }
 
 static inline bool vec_ok(const void* p, int64_t ld, int dtype) {
@@ -428,6 +449,8 @@ static inline int ew_grid(int64_t pixels, int cv, int blocks_per_sm = 8, int pix
   int64_t total = pixels * cv;
   int64_t b = ceil_div(total, (int64_t)kThreads * pix_per_thread);
   int64_t cap = (int64_t)num_sms() * blocks_per_sm;
+  const int64_t floor_b = ceil_div(total, (int64_t)kThreads * kMaxPixPerThread);   // bounds the fp32 per-thread partials
+  if (cap < floor_b) cap = floor_b;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   int64_t mult = cv / gcd64(cv, kThreads);
@@ -519,8 +542,8 @@ extern "C" int mpgan_bn_act_bwd_reduce(int dtype, const void* dy, int64_t lddy, 
   MPGAN_REQUIRE(pixels > 0 && c > 0 && ldx >= c && lddy >= c && sums, MPGAN_ERR_SHAPE, "bn_act_bwd_reduce: bad shape");
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(dy, lddy, dtype);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    if (vec)
-      bn_act_bwd_reduce_kernel<T, 8><<<ew_grid(pixels, c / 8, 4, 16), kThreads, 0, (cudaStream_t)stream>>>(
+    if (vec)  // 4 channels per thread: the per-channel constants fit in registers at 3 blocks per SM
+      bn_act_bwd_reduce_kernel<T, 4><<<ew_grid(pixels, c / 4, 6, 16), kThreads, 0, (cudaStream_t)stream>>>(
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums);
     else
       bn_act_bwd_reduce_kernel<T, 1><<<ew_grid(pixels, c, 8, 32), kThreads, 0, (cudaStream_t)stream>>>(
@@ -541,7 +564,7 @@ extern "C" int mpgan_bn_act_bwd_apply(int dtype, const void* dy, int64_t lddy, c
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(dy, lddy, dtype) && vec_ok(dx, lddx, dtype);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     if (vec)
-      bn_act_bwd_apply_kernel<T, 8><<<ew_grid(pixels, c / 8, 6, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      bn_act_bwd_apply_kernel<T, 4><<<ew_grid(pixels, c / 4, 6, 16), kThreads, 0, (cudaStream_t)stream>>>(
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums,
           dgamma, dbeta, dalpha, dbias, (T*)dx, lddx);
     else

@@ -26,10 +26,10 @@ struct Geom {
 
 struct PixWalk {
   int img, h, w, dn, dh, dw, H, W;
-  __device__ __forceinline__ void init(int64_t p, int64_t step, int H_, int W_) {
+  __device__ __forceinline__ void init(int p, int step, int H_, int W_) {
     H = H_; W = W_;
-    w = (int)(p % W); p /= W; h = (int)(p % H); img = (int)(p / H);
-    dw = (int)(step % W); step /= W; dh = (int)(step % H); dn = (int)(step / H);
+    w = p % W; p /= W; h = p % H; img = p / H;
+    dw = step % W; step /= W; dh = step % H; dn = step / H;
   }
   __device__ __forceinline__ void next() {
     w += dw; int c = w >= W ? 1 : 0; w -= c * W;
@@ -93,75 +93,101 @@ __device__ __forceinline__ A group_total(const A* sm, int cv, int NV, int j) {  
   return t;
 }
 
+// Blackwell issues fp32 FMAs at full rate only in the packed form (FFMA2: two lanes of a 64-bit register pair)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+// V channels as V/2 packed pairs (V == 1: one pair with a dead upper lane)
+template <int V> struct Pairs { static constexpr int N = V / 2; };
+template <> struct Pairs<1> { static constexpr int N = 1; };
+
 // ------------------------------------------------------------------------------------------------------------
 // fprop: y[p][c] = bias[c] + sum_t x[pix(p) * s - pad + t] * w[c][t]          (w: [C][9], cx == 1)
+// All element offsets fit in int32 (checked on the host).
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, int V>
+template <typename T, int V, int S>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 1 : 2)
-fprop_kernel(Geom g, const T* __restrict__ x, int64_t ldx, const T* __restrict__ w, const float* __restrict__ bias,
-             T* __restrict__ y, int64_t ldy, double* __restrict__ stats) {
+fprop_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__ w, const float* __restrict__ bias,
+             T* __restrict__ y, int ldy, double* __restrict__ stats) {
   __shared__ double sm[(kThreads / 32) * 32 * 2 * V];   // statistics reduce: up to 32 channel groups of 2V doubles per warp
+  constexpr int NP = Pairs<V>::N;
   const int cv = g.C / V;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-  const int c0 = (int)(tid % cv) * V;
-  const int64_t P = (int64_t)g.n * g.yh * g.yw;
-  const int64_t pstep = nthr / cv;
-  float wr[kTaps][V], b[V];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthr = gridDim.x * blockDim.x;
+  const int c0 = (tid % cv) * V;
+  const int P = g.n * g.yh * g.yw;
+  const int pstep = nthr / cv;
+  float2 wr[kTaps][NP], b[NP];
 #pragma unroll
-  for (int e = 0; e < V; ++e) {
-    b[e] = bias ? bias[c0 + e] : 0.f;
+  for (int j = 0; j < NP; ++j) {
+    const int e0 = 2 * j, e1 = (2 * j + 1 < V) ? 2 * j + 1 : 2 * j;
+    b[j] = make_float2(bias ? bias[c0 + e0] : 0.f, bias ? bias[c0 + e1] : 0.f);
 #pragma unroll
-    for (int t = 0; t < kTaps; ++t) wr[t][e] = to_f(w[(c0 + e) * kTaps + t]);
+    for (int t = 0; t < kTaps; ++t)
+      wr[t][j] = make_float2(to_f(w[(c0 + e0) * kTaps + t]), to_f(w[(c0 + e1) * kTaps + t]));
   }
   // bf16 storage: fp32 partials over this thread's (<= 256, see grid_for) pixels, fp64 from the block level on;
   // fp32 storage (the 1e-4 parity mode): the fp32 partials are flushed into fp64 every 4 pixels, because
   // var = E[x^2] - mean^2 cancels badly when |mean| >> std (un-normalised hand-over between cascaded UNets)
   constexpr bool kExact = sizeof(T) == 4;
-  float s1[V], s2[V];
+  float2 s1[NP], s2[NP];
   double d1[kExact ? V : 1], d2[kExact ? V : 1];
 #pragma unroll
-  for (int e = 0; e < V; ++e) s1[e] = s2[e] = 0.f;
+  for (int j = 0; j < NP; ++j) s1[j] = s2[j] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int e = 0; e < (kExact ? V : 1); ++e) d1[e] = d2[e] = 0.0;
   int it = 0;
   PixWalk pw;
-  int64_t p = tid / cv;
+  int p = tid / cv;
   pw.init(p, pstep, g.yh, g.yw);
+  const int xrow = g.xw * ldx, ximg = g.xh * xrow;
   for (; p < P; p += pstep, pw.next()) {
-    const T* ximg = x + (int64_t)pw.img * g.xh * g.xw * ldx;
-    const int ih0 = pw.h * g.s - g.pad, iw0 = pw.w * g.s - g.pad;
+    const int ih0 = pw.h * S - g.pad, iw0 = pw.w * S - g.pad;
+    const T* xb = x + (pw.img * ximg + ih0 * xrow + iw0 * ldx);
+    bool vh[3], vw[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { vh[r] = (unsigned)(ih0 + r) < (unsigned)g.xh; vw[r] = (unsigned)(iw0 + r) < (unsigned)g.xw; }
     float xv[kTaps];
 #pragma unroll
     for (int rh = 0; rh < 3; ++rh)
 #pragma unroll
-      for (int rw = 0; rw < 3; ++rw) {
-        const int ih = ih0 + rh, iw = iw0 + rw;
-        const bool ok = ih >= 0 && ih < g.xh && iw >= 0 && iw < g.xw;
-        xv[rh * 3 + rw] = ok ? to_f(ximg[((int64_t)ih * g.xw + iw) * ldx]) : 0.f;
-      }
+      for (int rw = 0; rw < 3; ++rw)
+        xv[rh * 3 + rw] = (vh[rh] && vw[rw]) ? to_f(xb[rh * xrow + rw * ldx]) : 0.f;
+    float2 o2[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      float2 a = b[j];
+#pragma unroll
+      for (int t = 0; t < kTaps; ++t) a = ffma2(make_float2(xv[t], xv[t]), wr[t][j], a);
+      o2[j] = a;
+    }
     float o[V];
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      float a = b[e];
-#pragma unroll
-      for (int t = 0; t < kTaps; ++t) a = fmaf(xv[t], wr[t][e], a);
-      o[e] = a;
-    }
-    IO<T, V>::store(y + p * ldy + c0, o);
+    for (int e = 0; e < V; ++e) o[e] = (e & 1) ? o2[e / 2].y : o2[e / 2].x;
+    IO<T, V>::store(y + (p * ldy + c0), o);
     if (stats) {
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const float f = to_f(from_f<T>(o[e]));   // statistics of the values as stored
-        s1[e] += f;
-        s2[e] = fmaf(f, f, s2[e]);
+      for (int j = 0; j < NP; ++j) {   // statistics of the values as stored
+        const float2 f = make_float2(to_f(from_f<T>(o2[j].x)), to_f(from_f<T>(o2[j].y)));
+        s1[j].x += f.x; s1[j].y += f.y;
+        s2[j] = ffma2(f, f, s2[j]);
       }
       if (kExact && (++it & 3) == 0) {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-          d1[kExact ? e : 0] += (double)s1[e]; d2[kExact ? e : 0] += (double)s2[e];
-          s1[e] = s2[e] = 0.f;
+          d1[kExact ? e : 0] += (double)((e & 1) ? s1[e / 2].y : s1[e / 2].x);
+          d2[kExact ? e : 0] += (double)((e & 1) ? s2[e / 2].y : s2[e / 2].x);
         }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) s1[j] = s2[j] = make_float2(0.f, 0.f);
       }
     }
   }
@@ -169,8 +195,8 @@ fprop_kernel(Geom g, const T* __restrict__ x, int64_t ldx, const T* __restrict__
     double a[2 * V];
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      a[e] = (double)s1[e] + (kExact ? d1[kExact ? e : 0] : 0.0);
-      a[V + e] = (double)s2[e] + (kExact ? d2[kExact ? e : 0] : 0.0);
+      a[e] = (double)((e & 1) ? s1[e / 2].y : s1[e / 2].x) + (kExact ? d1[kExact ? e : 0] : 0.0);
+      a[V + e] = (double)((e & 1) ? s2[e / 2].y : s2[e / 2].x) + (kExact ? d2[kExact ? e : 0] : 0.0);
     }
     if (cv <= 32) {
       group_reduce<double, 2 * V>(a, cv, sm);
@@ -188,54 +214,66 @@ fprop_kernel(Geom g, const T* __restrict__ x, int64_t ldx, const T* __restrict__
 // ------------------------------------------------------------------------------------------------------------
 // bprop: x[q] = bias + sum_t sum_c y[(q + pad - t)/s][c] * w[c][t]            (cx == 1; cv = C/V lanes per pixel)
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, int V>
-__global__ void __launch_bounds__(kThreads)
-bprop_kernel(Geom g, const T* __restrict__ y, int64_t ldy, const T* __restrict__ w, const float* __restrict__ bias,
-             T* __restrict__ x, int64_t ldx, double* __restrict__ stats) {
+template <typename T, int V, int S>
+__global__ void __launch_bounds__(kThreads, 2)
+bprop_kernel(Geom g, const T* __restrict__ y, int ldy, const T* __restrict__ w, const float* __restrict__ bias,
+             T* __restrict__ x, int ldx, double* __restrict__ stats) {
   __shared__ double sred[2 * (kThreads / 32)];
+  constexpr int NP = Pairs<V>::N;
   const int cv = g.C / V;   // divides 32
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-  const int gl = (int)(tid % cv);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthr = gridDim.x * blockDim.x;
+  const int gl = tid % cv;
   const int c0 = gl * V;
-  const int64_t P = (int64_t)g.n * g.xh * g.xw;
-  const int64_t pstep = nthr / cv;
-  float wr[kTaps][V];
+  const int P = g.n * g.xh * g.xw;
+  const int pstep = nthr / cv;
+  float2 wr[kTaps][NP];
 #pragma unroll
-  for (int e = 0; e < V; ++e)
+  for (int j = 0; j < NP; ++j) {
+    const int e0 = 2 * j;
+    const bool has1 = 2 * j + 1 < V;
 #pragma unroll
-    for (int t = 0; t < kTaps; ++t) wr[t][e] = to_f(w[(c0 + e) * kTaps + t]);
+    for (int t = 0; t < kTaps; ++t)
+      wr[t][j] = make_float2(to_f(w[(c0 + e0) * kTaps + t]), has1 ? to_f(w[(c0 + e0 + 1) * kTaps + t]) : 0.f);
+  }
   const float b = bias ? bias[0] : 0.f;
   float s1 = 0.f, s2 = 0.f;
   PixWalk pw;
-  int64_t p = tid / cv;
+  int p = tid / cv;
   pw.init(p, pstep, g.xh, g.xw);
+  const int yrow = g.yw * ldy, yimg = g.yh * yrow;
   // all lanes of a warp run the same number of iterations (shuffles inside): bound by the warp's first pixel
-  const int64_t pwarp = (tid - (threadIdx.x & 31)) / cv;
-  for (int64_t pb = pwarp; pb < P; pb += pstep, p += pstep, pw.next()) {
+  const int pwarp = (tid - (int)(threadIdx.x & 31)) / cv;
+  for (int pb = pwarp; pb < P; pb += pstep, p += pstep, pw.next()) {
     const bool live = p < P;
-    float acc = 0.f;
-    if (live) {
-      const T* yimg = y + (int64_t)pw.img * g.yh * g.yw * ldy + c0;
+    bool vh[3], vw[3];
+    int oh[3], ow[3];
 #pragma unroll
-      for (int rh = 0; rh < 3; ++rh) {
-        const int qh = pw.h + g.pad - rh;
-        const bool okh = qh >= 0 && (g.s == 1 || (qh & 1) == 0);
-        const int yh_ = g.s == 1 ? qh : qh >> 1;
-        if (!okh || yh_ >= g.yh) continue;
-#pragma unroll
-        for (int rw = 0; rw < 3; ++rw) {
-          const int qw = pw.w + g.pad - rw;
-          const bool okw = qw >= 0 && (g.s == 1 || (qw & 1) == 0);
-          const int yw_ = g.s == 1 ? qw : qw >> 1;
-          if (!okw || yw_ >= g.yw) continue;
-          float v[V];
-          IO<T, V>::load(yimg + ((int64_t)yh_ * g.yw + yw_) * ldy, v);
-#pragma unroll
-          for (int e = 0; e < V; ++e) acc = fmaf(v[e], wr[rh * 3 + rw][e], acc);
-        }
-      }
+    for (int r = 0; r < 3; ++r) {
+      const int qh = pw.h + g.pad - r, qw = pw.w + g.pad - r;
+      const int yh_ = S == 1 ? qh : qh >> 1, yw_ = S == 1 ? qw : qw >> 1;
+      vh[r] = live && qh >= 0 && (S == 1 || (qh & 1) == 0) && yh_ < g.yh;
+      vw[r] = qw >= 0 && (S == 1 || (qw & 1) == 0) && yw_ < g.yw;
+      oh[r] = yh_ * yrow; ow[r] = yw_ * ldy;
     }
+    const T* yb = y + (pw.img * yimg + c0);
+    float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int rh = 0; rh < 3; ++rh)
+#pragma unroll
+      for (int rw = 0; rw < 3; ++rw) {
+        float v[V];
+        if (vh[rh] && vw[rw]) {
+          IO<T, V>::load(yb + (oh[rh] + ow[rw]), v);
+        } else {
+#pragma unroll
+          for (int e = 0; e < V; ++e) v[e] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+          acc2 = ffma2(make_float2(v[2 * j], (2 * j + 1 < V) ? v[(2 * j + 1 < V) ? 2 * j + 1 : 0] : 0.f), wr[rh * 3 + rw][j], acc2);
+      }
+    float acc = acc2.x + acc2.y;
     for (int off = cv >> 1; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (live && gl == 0) {
       const T o = from_f<T>(acc + b);
@@ -257,41 +295,150 @@ bprop_kernel(Geom g, const T* __restrict__ y, int64_t ldy, const T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// wgrad: dw[c][t] += sum_p y[p][c] * x[pix(p) * s - pad + t]                  (cx == 1)
+// bprop, stride 2, pad 1, X = 2*Y (ConvTranspose k3 s2 p1 op1 forward; data gradient of the s2 first convolutions):
+// Y-centric form -- the lane group of Y pixel (a,b) produces the 2x2 output block (2a..2a+1, 2b..2b+1):
+//   x(2a,  2b)   = Y(a,b).W11
+//   x(2a,  2b+1) = Y(a,b+1).W10 + Y(a,b).W12
+//   x(2a+1,2b)   = Y(a+1,b).W01 + Y(a,b).W21
+//   x(2a+1,2b+1) = Y(a+1,b+1).W00 + Y(a+1,b).W02 + Y(a,b+1).W20 + Y(a,b).W22
+// (no multiply by structural zeros, four coalesced 16-byte loads per lane, nine 8-channel dot products)
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, int V>
-__global__ void __launch_bounds__(kThreads)
-wgrad_kernel(Geom g, const T* __restrict__ x, int64_t ldx, const T* __restrict__ y, int64_t ldy,
-             float* __restrict__ dw) {
-  extern __shared__ float smf[];   // (kThreads/32) * cv * 72 floats
+__global__ void __launch_bounds__(kThreads, 2)
+bprop_s2_kernel(Geom g, const T* __restrict__ y, int ldy, const T* __restrict__ w, const float* __restrict__ bias,
+                T* __restrict__ x, int ldx, double* __restrict__ stats) {
+  __shared__ double sred[2 * (kThreads / 32)];
+  constexpr int NP = Pairs<V>::N;
   const int cv = g.C / V;   // divides 32
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-  const int c0 = (int)(tid % cv) * V;
-  const int64_t P = (int64_t)g.n * g.yh * g.yw;
-  const int64_t pstep = nthr / cv;
-  float acc[kTaps * V];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthr = gridDim.x * blockDim.x;
+  const int gl = tid % cv;
+  const int c0 = gl * V;
+  const int P = g.n * g.yh * g.yw;
+  const int pstep = nthr / cv;
+  float2 wr[kTaps][NP];
 #pragma unroll
-  for (int i = 0; i < kTaps * V; ++i) acc[i] = 0.f;
+  for (int j = 0; j < NP; ++j) {
+    const int e0 = 2 * j;
+    const bool has1 = 2 * j + 1 < V;
+#pragma unroll
+    for (int t = 0; t < kTaps; ++t)
+      wr[t][j] = make_float2(to_f(w[(c0 + e0) * kTaps + t]), has1 ? to_f(w[(c0 + e0 + 1) * kTaps + t]) : 0.f);
+  }
+  const float b = bias ? bias[0] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
   PixWalk pw;
-  int64_t p = tid / cv;
+  int p = tid / cv;
   pw.init(p, pstep, g.yh, g.yw);
+  const int yrow = g.yw * ldy;
+  const int xrow = g.xw * ldx;
+  const int pwarp = (tid - (int)(threadIdx.x & 31)) / cv;
+  for (int pb = pwarp; pb < P; pb += pstep, p += pstep, pw.next()) {
+    const bool live = p < P;
+    const bool r1 = live && pw.h + 1 < g.yh, c1 = pw.w + 1 < g.yw;
+    const T* yb = y + (live ? (p * ldy + c0) : 0);
+    float v[4][V];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool ok = q == 0 ? live : (q == 1 ? (live && c1) : (q == 2 ? r1 : (r1 && c1)));
+      if (ok) {
+        IO<T, V>::load(yb + ((q >> 1) * yrow + (q & 1) * ldy), v[q]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[q][e] = 0.f;
+      }
+    }
+    float2 o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      float2 u[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) u[q] = make_float2(v[q][2 * j], (2 * j + 1 < V) ? v[q][(2 * j + 1 < V) ? 2 * j + 1 : 0] : 0.f);
+      o[0] = ffma2(u[0], wr[4][j], o[0]);                                   // W11
+      o[1] = ffma2(u[1], wr[3][j], o[1]); o[1] = ffma2(u[0], wr[5][j], o[1]);   // W10, W12
+      o[2] = ffma2(u[2], wr[1][j], o[2]); o[2] = ffma2(u[0], wr[7][j], o[2]);   // W01, W21
+      o[3] = ffma2(u[3], wr[0][j], o[3]); o[3] = ffma2(u[2], wr[2][j], o[3]);   // W00, W02
+      o[3] = ffma2(u[1], wr[6][j], o[3]); o[3] = ffma2(u[0], wr[8][j], o[3]);   // W20, W22
+    }
+    float r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      r[q] = o[q].x + o[q].y;
+      for (int off = cv >> 1; off >= 1; off >>= 1) r[q] += __shfl_xor_sync(0xffffffffu, r[q], off);
+    }
+    if (live && gl == 0) {
+      T* xb = x + ((pw.img * g.xh + 2 * pw.h) * xrow + 2 * pw.w * ldx);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const T ov = from_f<T>(r[q] + b);
+        xb[(q >> 1) * xrow + (q & 1) * ldx] = ov;
+        if (stats) { const float f = to_f(ov); s1 += f; s2 = fmaf(f, f, s2); }
+      }
+    }
+  }
+  if (stats) {
+    double a1 = warp_sum((double)s1), a2 = warp_sum((double)s2);
+    if ((threadIdx.x & 31) == 0) { sred[threadIdx.x >> 5] = a1; sred[kThreads / 32 + (threadIdx.x >> 5)] = a2; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < kThreads / 32; ++i) t += sred[threadIdx.x * (kThreads / 32) + i];
+      atomicAdd(&stats[threadIdx.x], t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wgrad: dw[c][t] += sum_p y[p][c] * x[pix(p) * s - pad + t]                  (cx == 1)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int V, int S>
+__global__ void __launch_bounds__(kThreads, 2)
+wgrad_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__ y, int ldy, float* __restrict__ dw) {
+  extern __shared__ float smf[];   // (kThreads/32) * cv * 9 * V floats
+  constexpr int NP = Pairs<V>::N;
+  const int cv = g.C / V;   // divides 32
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthr = gridDim.x * blockDim.x;
+  const int c0 = (tid % cv) * V;
+  const int P = g.n * g.yh * g.yw;
+  const int pstep = nthr / cv;
+  float2 acc2[kTaps][NP];
+#pragma unroll
+  for (int t = 0; t < kTaps; ++t)
+#pragma unroll
+    for (int j = 0; j < NP; ++j) acc2[t][j] = make_float2(0.f, 0.f);
+  PixWalk pw;
+  int p = tid / cv;
+  pw.init(p, pstep, g.yh, g.yw);
+  const int xrow = g.xw * ldx, ximg = g.xh * xrow;
   for (; p < P; p += pstep, pw.next()) {
-    const T* ximg = x + (int64_t)pw.img * g.xh * g.xw * ldx;
-    const int ih0 = pw.h * g.s - g.pad, iw0 = pw.w * g.s - g.pad;
+    const int ih0 = pw.h * S - g.pad, iw0 = pw.w * S - g.pad;
+    const T* xb = x + (pw.img * ximg + ih0 * xrow + iw0 * ldx);
+    bool vh[3], vw[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { vh[r] = (unsigned)(ih0 + r) < (unsigned)g.xh; vw[r] = (unsigned)(iw0 + r) < (unsigned)g.xw; }
     float gy[V];
-    IO<T, V>::load(y + p * ldy + c0, gy);
+    IO<T, V>::load(y + (p * ldy + c0), gy);
+    float2 g2[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) g2[j] = make_float2(gy[2 * j], (2 * j + 1 < V) ? gy[(2 * j + 1 < V) ? 2 * j + 1 : 0] : 0.f);
 #pragma unroll
     for (int rh = 0; rh < 3; ++rh)
 #pragma unroll
       for (int rw = 0; rw < 3; ++rw) {
-        const int ih = ih0 + rh, iw = iw0 + rw;
-        const bool ok = ih >= 0 && ih < g.xh && iw >= 0 && iw < g.xw;
-        const float xv = ok ? to_f(ximg[((int64_t)ih * g.xw + iw) * ldx]) : 0.f;
+        const float xv = (vh[rh] && vw[rw]) ? to_f(xb[rh * xrow + rw * ldx]) : 0.f;
 #pragma unroll
-        for (int e = 0; e < V; ++e) acc[(rh * 3 + rw) * V + e] = fmaf(gy[e], xv, acc[(rh * 3 + rw) * V + e]);
+        for (int j = 0; j < NP; ++j) acc2[rh * 3 + rw][j] = ffma2(make_float2(xv, xv), g2[j], acc2[rh * 3 + rw][j]);
       }
   }
+  float acc[kTaps * V];
+#pragma unroll
+  for (int t = 0; t < kTaps; ++t)
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[t * V + e] = (e & 1) ? acc2[t][e / 2].y : acc2[t][e / 2].x;
   group_reduce<float, kTaps * V>(acc, cv, smf);
   for (int j = threadIdx.x; j < cv * kTaps * V; j += kThreads) {
     const int gq = j / (kTaps * V), i = j - gq * (kTaps * V);
@@ -334,6 +481,17 @@ static int vec_of(int C, const void* p, int64_t ld) {
   return 0;
 }
 
+// every element offset of a tensor with `pixels` pixels of stride ld must fit in int32
+static inline bool fits32(int64_t pixels, int64_t ld) { return pixels * ld < ((int64_t)1 << 31) - 4096; }
+
+#define C1F_LAUNCH(KERNEL, V_, S_, ...)                                               \
+  do {                                                                                \
+    if (V_ == 8 && S_ == 1) KERNEL<T, 8, 1> __VA_ARGS__;                              \
+    else if (V_ == 8) KERNEL<T, 8, 2> __VA_ARGS__;                                    \
+    else if (S_ == 1) KERNEL<T, 1, 1> __VA_ARGS__;                                    \
+    else KERNEL<T, 1, 2> __VA_ARGS__;                                                 \
+  } while (0)
+
 }  // namespace c1f
 
 // Return 0 on success, MPGAN_ERR_* on failure, 1 when the fast path does not cover the call (caller falls back).
@@ -348,10 +506,11 @@ int c1f_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, con
   if (cv <= 32 && (32 % cv) != 0) return 1;
   if (cv > 32 && (kThreads % cv) != 0) return 1;
   const int64_t P = (int64_t)q.n * q.yh * q.yw;
+  if (!fits32(P, ldy) || !fits32((int64_t)q.n * q.xh * q.xw, ldx) || P * cv >= ((int64_t)1 << 30)) return 1;
   const int grid = grid_for(P, cv, 8, 8);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    if (V == 8) fprop_kernel<T, 8><<<grid, kThreads, 0, s>>>(q, (const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, stats);
-    else fprop_kernel<T, 1><<<grid, kThreads, 0, s>>>(q, (const T*)x, ldx, (const T*)w, bias, (T*)y, ldy, stats);
+    C1F_LAUNCH(fprop_kernel, V, q.s, <<<grid, kThreads, 0, s>>>(q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y,
+                                                               (int)ldy, stats));
     MPGAN_CHECK_LAUNCH("c1f_fprop");
     return 0;
   });
@@ -367,10 +526,21 @@ int c1f_bprop(const MpganConvGeom* g, int dtype, const void* y, int64_t ldy, con
   const int cv = q.C / V;
   if (cv > 32 || (32 % cv) != 0) return 1;
   const int64_t P = (int64_t)q.n * q.xh * q.xw;
+  if (!fits32(P, ldx) || !fits32((int64_t)q.n * q.yh * q.yw, ldy) || P * cv >= ((int64_t)1 << 30)) return 1;
+  if (q.s == 2 && q.pad == 1 && q.xh == 2 * q.yh && q.xw == 2 * q.yw) {   // Y-centric 2x2-block form
+    const int64_t PY = (int64_t)q.n * q.yh * q.yw;
+    const int grid2 = grid_for(PY, cv, 2, 8);
+    MPGAN_DISPATCH_DTYPE(dtype, T, {
+      if (V == 8) bprop_s2_kernel<T, 8><<<grid2, kThreads, 0, s>>>(q, (const T*)y, (int)ldy, (const T*)w, bias, (T*)x, (int)ldx, stats);
+      else bprop_s2_kernel<T, 1><<<grid2, kThreads, 0, s>>>(q, (const T*)y, (int)ldy, (const T*)w, bias, (T*)x, (int)ldx, stats);
+      MPGAN_CHECK_LAUNCH("c1f_bprop_s2");
+      return 0;
+    });
+  }
   const int grid = grid_for(P, cv, 4, 8);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    if (V == 8) bprop_kernel<T, 8><<<grid, kThreads, 0, s>>>(q, (const T*)y, ldy, (const T*)w, bias, (T*)x, ldx, stats);
-    else bprop_kernel<T, 1><<<grid, kThreads, 0, s>>>(q, (const T*)y, ldy, (const T*)w, bias, (T*)x, ldx, stats);
+    C1F_LAUNCH(bprop_kernel, V, q.s, <<<grid, kThreads, 0, s>>>(q, (const T*)y, (int)ldy, (const T*)w, bias, (T*)x,
+                                                               (int)ldx, stats));
     MPGAN_CHECK_LAUNCH("c1f_bprop");
     return 0;
   });
@@ -386,11 +556,11 @@ int c1f_wgrad(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, con
   const int cv = q.C / V;
   if (cv > 8 || (32 % cv) != 0) return 1;
   const int64_t P = (int64_t)q.n * q.yh * q.yw;
+  if (!fits32(P, ldy) || !fits32((int64_t)q.n * q.xh * q.xw, ldx) || P * cv >= ((int64_t)1 << 30)) return 1;
   const int grid = grid_for(P, cv, 32, 4);
   const size_t smem = (size_t)(kThreads / 32) * cv * kTaps * V * sizeof(float);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    if (V == 8) wgrad_kernel<T, 8><<<grid, kThreads, smem, s>>>(q, (const T*)x, ldx, (const T*)y, ldy, dw);
-    else wgrad_kernel<T, 1><<<grid, kThreads, smem, s>>>(q, (const T*)x, ldx, (const T*)y, ldy, dw);
+    C1F_LAUNCH(wgrad_kernel, V, q.s, <<<grid, kThreads, smem, s>>>(q, (const T*)x, (int)ldx, (const T*)y, (int)ldy, dw));
     MPGAN_CHECK_LAUNCH("c1f_wgrad");
     return 0;
   });

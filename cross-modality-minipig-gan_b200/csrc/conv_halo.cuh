@@ -1,0 +1,313 @@
+// "Halo-resident" tcgen05 implicit GEMM for stride-1 3x3 convolutions (forward, and the data gradient of a stride-1
+// 3x3 convolution, which is the same operation with flipped taps and transposed weights).  Included by conv_tc.cu.
+//
+// Why a second conv engine: tapgemm_kernel re-reads the activation tile once per filter tap through TMA (9 x 128
+// rows per 128 output pixels).  For the generator's 16/32-channel layers that is TMA-row-rate bound (32/64-byte
+// rows), and for the discriminator's 64->128 layer it is L2->SM bandwidth bound.  Here every CTA
+//   * keeps ALL weights of the layer resident in shared memory (9*C*N bf16 <= 147 KB), loaded once,
+//   * loads each activation halo tile ((16+2) x (8+2) pixels, <= 64 channels per plane) ONCE with a single TMA box
+//     (out-of-bounds zero fill = padding) into a ring of planes; the box lands as the swizzled canonical K-major
+//     UMMA operand [180 halo pixels][min(C,64) channels] (128/64/32-byte rows), and
+//   * issues the 9*(C/16) tcgen05.mma of a tile straight from those planes: a filter tap is nothing but a
+//     whole-pixel shift of the descriptor start address (rows of the 128-row A operand = 16 tile rows of 8
+//     consecutive pixels, SBO = one halo row of 10 pixels).  The swizzle XOR is a function of the absolute
+//     shared-memory address on both the TMA-write and the MMA-read side (verified on B200: base_offset = 0 with
+//     start addresses that are not multiples of the swizzle period gives exact results), so shifted windows of one
+//     plane are legal operands.
+// Accumulators: 128 x N fp32 in TMEM, double buffered; 8 epilogue warps (2 per TMEM lane quarter, alternating
+// 32-column chunks): bias, bf16 store at a channel offset, BatchNorm statistics via a shared-memory transpose.
+// Replaces cuDNN behind nn.Conv2d (k3 s1) at /root/reference/code/GAN/GAN_final.py:173-176 (D layer 2) and the MONAI
+// UNet's stride-1 units (GAN_final.py:106-114).
+#pragma once
+
+namespace mpgan {
+namespace tc {
+
+constexpr int HT_W = 8, HT_H = 16;              // output tile (M = 128 rows: 16 groups of 8 consecutive pixels)
+constexpr int HH = HT_H + 2, HW = HT_W + 2;     // halo tile
+constexpr int HPIX = HH * HW;                   // 180 pixels
+constexpr int kHaloThreads = 384;               // warp 0 TMA, 1 MMA, 2 TMEM owner, 3 idle, 4-11 epilogue
+constexpr int kMaxBuf = 8;
+constexpr int kHaloAux = 256;                   // barriers + tmem slot
+constexpr int kTrW = 17;                        // padded row of the per-warp transpose scratch (bf16x2 words)
+
+struct HaloParams {
+  int nimg, oh, ow;
+  int C, N, pad, flip;
+  int tiles_w, tiles_h, total_tiles;
+  int nbuf;
+  const bf16* w;       // [N][9][C]
+  bf16* out;
+  long long out_sn, out_sh, out_sw;
+  const float* bias;
+  double* stats;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int N>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUtensorMap tmA) {
+  constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int C = P.C;
+  const int KC = C < 64 ? C : 64;                        // channels per plane (one swizzle span)
+  const int nkc = C / KC;
+  const int rowb = KC * 2;                               // bytes per pixel row of a plane: 128 / 64 / 32
+  const int cpr = rowb >> 4;                             // 16-byte chunks per row
+  const uint32_t swz_mask = (uint32_t)(cpr - 1);         // Swizzle<log2(cpr),4,3>: chunk ^= (offset >> 7) & mask
+  const int w_bytes = 9 * C * N * 2;
+  const int a_bytes = (HPIX * rowb + 1023) & ~1023;      // one plane, padded to the swizzle period
+  uint8_t* w_sm = smem;
+  uint8_t* a_sm = smem + ((w_bytes + 1023) & ~1023);
+  uint8_t* aux = a_sm + P.nbuf * a_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* a_empty = a_full + kMaxBuf;
+  uint64_t* tfull = a_empty + kMaxBuf;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_stats = reinterpret_cast<float*>(aux + kHaloAux);   // [8 epilogue warps][2*N]
+  uint32_t* s_tr = reinterpret_cast<uint32_t*>(s_stats + 8 * 2 * N);   // [8 epilogue warps][32][kTrW] bf16x2
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) prefetch_tmap(&tmA);
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < kMaxBuf; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < 8 * 2 * N; i += blockDim.x) s_stats[i] = 0.f;
+  // resident weights: global [n][tap][C] -> smem [tap][kc][n][KC channels], rows swizzled exactly like a TMA box
+  {
+    const int cpp = C >> 3;
+    const int total = N * 9 * cpp;
+    for (int g = threadIdx.x; g < total; g += blockDim.x) {
+      const int chunk = g % cpp;
+      const int r = g / cpp;
+      const int tap = r % 9, n = r / 9;
+      const int kc = chunk / cpr, cc = chunk - kc * cpr;
+      const uint32_t blk = (uint32_t)((tap * nkc + kc) * N) * rowb;   // multiple of the swizzle period
+      uint32_t off = (uint32_t)n * rowb + cc * 16;
+      off ^= ((off >> 7) & swz_mask) << 4;
+      cp_async16(smem_u32(w_sm + blk + off), P.w + (size_t)g * 8);
+    }
+    cp_async_wait_all();
+    fence_proxy_async();   // these generic-proxy writes are read by tcgen05.mma (async proxy)
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = P.tiles_w * P.tiles_h;
+
+  if (warp == 0) {
+    if (elect_one()) {  // ================= TMA producer: one box per (tile, 64-channel plane) =================
+      int pi = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_per_img;
+        const int tr = tile - img * tiles_per_img;
+        const int thi = tr / P.tiles_w, twi = tr - thi * P.tiles_w;
+        const int h0 = thi * HT_H - P.pad, w0 = twi * HT_W - P.pad;
+        for (int kc = 0; kc < nkc; ++kc, ++pi) {
+          const int buf = pi % P.nbuf;
+          const uint32_t par = (uint32_t)(pi / P.nbuf) & 1u;
+          mbar_wait(&a_empty[buf], par ^ 1);
+          mbar_expect_tx(&a_full[buf], (uint32_t)(HPIX * rowb));
+          tma_load_4d(a_sm + buf * a_bytes, &tmA, &a_full[buf], kc * KC, w0, h0, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {  // ================= MMA issuer =================
+      const uint32_t w_addr = smem_u32(w_sm);
+      const uint32_t layout = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);   // SW128 / SW64 / SW32
+      const uint32_t sbo_a = HW * rowb, sbo_b = 8 * rowb;
+      const int ksteps = KC >> 4;
+      int it = 0, pi = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t tpar = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tempty[acc], tpar ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+        for (int kc = 0; kc < nkc; ++kc, ++pi) {
+          const int buf = pi % P.nbuf;
+          const uint32_t apar = (uint32_t)(pi / P.nbuf) & 1u;
+          mbar_wait(&a_full[buf], apar);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_sm + buf * a_bytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int rh = tap / 3, rw = tap - rh * 3;
+            const int wt = P.flip ? 8 - tap : tap;
+            const uint32_t a_tap = a_addr + (uint32_t)(rh * HW + rw) * rowb;
+            const uint32_t b_tap = w_addr + (uint32_t)((wt * nkc + kc) * N) * rowb;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t adesc = make_smem_desc(a_tap + ks * 32, 16, sbo_a, layout);
+              const uint64_t bdesc = make_smem_desc(b_tap + ks * 32, 16, sbo_b, layout);
+              umma_bf16(d_tmem, adesc, bdesc, P.idesc, (kc | tap | ks) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&a_empty[buf]);
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 4) {  // ================= epilogue (8 warps) =================
+    const int ew = warp - 4;
+    const int q = ew & 3;          // TMEM lane quarter (== warp % 4)
+    const int half = ew >> 2;      // alternating column chunks
+    const int row = q * 32 + lane;
+    const int lh = row >> 3, lw = row & 7;
+    uint32_t* tr = s_tr + ew * 32 * kTrW;
+    float* sl = s_stats + ew * 2 * N;
+    constexpr int CH = N >= 64 ? 32 : 16;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int img = tile / tiles_per_img;
+      const int trm = tile - img * tiles_per_img;
+      const int thi = trm / P.tiles_w, twi = trm - thi * P.tiles_w;
+      const int oh = thi * HT_H + lh, ow = twi * HT_W + lw;
+      const bool valid = oh < P.oh && ow < P.ow;
+      bf16* orow = P.out + (long long)img * P.out_sn + (long long)oh * P.out_sh + (long long)ow * P.out_sw;
+      const int acc = it & 1;
+      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tfull[acc], par);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
+#pragma unroll 1
+      for (int c0 = half * CH; c0 < N; c0 += 2 * CH) {
+        uint32_t r[32];
+        if (CH == 32) tmem_ld_32x32(t_addr + c0, r);
+        else tmem_ld_32x16(t_addr + c0, r);
+        tmem_ld_wait();
+        uint32_t packed[CH / 2];
+#pragma unroll
+        for (int j = 0; j < CH / 2; ++j) {
+          float f0 = __uint_as_float(r[2 * j]), f1 = __uint_as_float(r[2 * j + 1]);
+          if (P.bias) { f0 += __ldg(&P.bias[c0 + 2 * j]); f1 += __ldg(&P.bias[c0 + 2 * j + 1]); }
+          __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+          packed[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < CH / 8; ++j)
+            *reinterpret_cast<uint4*>(orow + c0 + j * 8) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+        if (P.stats) {  // statistics of the values as stored: transpose through shared memory
+          constexpr int WPR = CH / 2;           // bf16x2 words per row; lane = (row part, column pair)
+#pragma unroll
+          for (int j = 0; j < WPR; ++j) tr[lane * kTrW + j] = valid ? packed[j] : 0u;
+          __syncwarp();
+          const int cp = lane % WPR, part = lane / WPR;
+          float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+          for (int i = 0; i < WPR; ++i) {
+            const uint32_t u = tr[(part * WPR + i) * kTrW + cp];
+            const float fa = __uint_as_float(u << 16), fb = __uint_as_float(u & 0xffff0000u);
+            s1a += fa; s1b += fb;
+            s2a = fmaf(fa, fa, s2a); s2b = fmaf(fb, fb, s2b);
+          }
+#pragma unroll
+          for (int off = WPR; off < 32; off <<= 1) {
+            s1a += __shfl_xor_sync(0xffffffffu, s1a, off); s1b += __shfl_xor_sync(0xffffffffu, s1b, off);
+            s2a += __shfl_xor_sync(0xffffffffu, s2a, off); s2b += __shfl_xor_sync(0xffffffffu, s2b, off);
+          }
+          if (lane < WPR) {   // slots owned by (this warp, this lane): fixed accumulation order
+            sl[c0 + 2 * lane] += s1a; sl[c0 + 2 * lane + 1] += s1b;
+            sl[N + c0 + 2 * lane] += s2a; sl[N + c0 + 2 * lane + 1] += s2b;
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (P.stats) {
+    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) {
+      double s = 0.0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += (double)s_stats[e * 2 * N + i];
+      if (s != 0.0) atomicAdd(&P.stats[i], s);
+    }
+  }
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int N>
+static int launch_halo(const HaloParams& P, const CUtensorMap& mA, size_t smem, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(halo3x3_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    MPGAN_REQUIRE(e == cudaSuccess, MPGAN_ERR_CUDA, "cudaFuncSetAttribute(halo3x3): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+  halo3x3_kernel<N><<<grid, kHaloThreads, smem, s>>>(P, mA);
+  MPGAN_CHECK_LAUNCH("halo3x3_kernel");
+  return 0;
+}
+
+// Stride-1 3x3 convolution through the halo-resident kernel.  dir 0: fprop (w = [N=cy][9][C=cx]); dir 1: data
+// gradient (w = transposed shadow [N=cx][9][C=cy], taps flipped).  Returns 1 when the layer is not covered.
+static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, int N, int pad, const void* in,
+                       int64_t ldi, const void* w, const float* bias, void* out, int64_t ldo, double* stats,
+                       cudaStream_t s) {
+  if (!(C == 16 || C == 32 || C == 64 || C == 128)) return 1;
+  if (!(N == 16 || N == 32 || N == 64 || N == 128)) return 1;
+  if (ldi % 8 != 0 || ldo % 8 != 0 || ((uintptr_t)in & 15) || ((uintptr_t)out & 15) || ((uintptr_t)w & 15)) return 1;
+  const int KC = C < 64 ? C : 64;
+  const size_t w_bytes = ((size_t)9 * C * N * 2 + 1023) & ~(size_t)1023;
+  const size_t a_bytes = ((size_t)HPIX * KC * 2 + 1023) & ~(size_t)1023;   // one <= 64-channel plane
+  const size_t aux = kHaloAux + (size_t)8 * 2 * N * 4 + (size_t)8 * 32 * kTrW * 4;   // barriers, stats slots, transpose scratch
+  const size_t budget = 227 * 1024 - 1024;
+  if (w_bytes + 2 * a_bytes + aux > budget) return 1;
+  int nbuf = (int)((budget - w_bytes - aux) / a_bytes);
+  if (nbuf > kMaxBuf) nbuf = kMaxBuf;
+  HaloParams P;
+  memset(&P, 0, sizeof(P));
+  P.nimg = n; P.oh = oh; P.ow = ow; P.C = C; P.N = N;
+  P.pad = dir == 0 ? pad : 2 - pad;
+  P.flip = dir;
+  P.tiles_w = (ow + HT_W - 1) / HT_W; P.tiles_h = (oh + HT_H - 1) / HT_H;
+  P.total_tiles = n * P.tiles_w * P.tiles_h;
+  P.nbuf = nbuf;
+  P.w = (const bf16*)w; P.out = (bf16*)out;
+  P.out_sn = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo; P.out_sw = ldo;
+  P.bias = bias; P.stats = stats;
+  P.idesc = make_idesc_bf16(128, N, 0, 0);
+  CUtensorMap mA;
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)iw, (uint64_t)ih, (uint64_t)n};
+    uint64_t str[3] = {(uint64_t)ldi, (uint64_t)ldi * iw, (uint64_t)ldi * iw * ih};
+    uint32_t box[4] = {(uint32_t)KC, (uint32_t)HW, (uint32_t)HH, 1u};
+    int rc = encode_map(&mA, in, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  const size_t smem = w_bytes + nbuf * a_bytes + aux + 1024;
+  switch (N) {
+    case 16: return launch_halo<16>(P, mA, smem, s);
+    case 32: return launch_halo<32>(P, mA, smem, s);
+    case 64: return launch_halo<64>(P, mA, smem, s);
+    default: return launch_halo<128>(P, mA, smem, s);
+  }
+}
+
+}  // namespace tc
+}  // namespace mpgan

@@ -129,6 +129,13 @@ TC_CASES = [
     (2, 128, 128, 8, 8, 3, 1, 1),
     (5, 256, 512, 10, 10, 3, 1, 0),     # patch-D layer 4: two N tiles, tiny images
     (1, 192, 32, 6, 6, 3, 1, 1),        # three 64-channel chunks
+    # stride-1 3x3 layers covered by the halo-resident kernel (conv_halo.cu): ragged 8x16 tiles, every C / N width
+    (2, 32, 32, 20, 24, 3, 1, 1),
+    (3, 64, 64, 17, 9, 3, 1, 1),
+    (2, 32, 64, 19, 21, 3, 1, 0),
+    (1, 64, 16, 40, 40, 3, 1, 1),
+    (2, 128, 64, 12, 12, 3, 1, 1),
+    (2, 16, 128, 33, 7, 3, 1, 1),
 ]
 
 
