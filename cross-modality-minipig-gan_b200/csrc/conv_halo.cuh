@@ -28,7 +28,8 @@ constexpr int HH = HT_H + 2, HW = HT_W + 2;     // halo tile
 constexpr int HPIX = HH * HW;                   // 180 pixels
 constexpr int kHaloThreads = 384;               // warp 0 TMA, 1 MMA, 2 TMEM owner, 3 idle, 4-11 epilogue
 constexpr int kMaxBuf = 8;
-constexpr int kHaloAux = 256;                   // barriers + tmem slot
+constexpr int kHaloAux = 512;                   // barriers + tmem slot
+constexpr int kMaxAcc = 8;                      // TMEM accumulator stages
 constexpr int kTrW = 17;                        // padded row of the per-warp transpose scratch (bf16x2 words)
 
 struct HaloParams {
@@ -53,7 +54,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <int N>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUtensorMap tmA) {
-  constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+  // accumulator ring: as many 128 x N fp32 tiles as fit in 512 TMEM columns (<= 8): small layers are bound by the
+  // MMA -> epilogue -> MMA round trip, not by throughput, so the ring must be deep
+  constexpr int NACC = 512 / N > kMaxAcc ? kMaxAcc : 512 / N;
+  constexpr int TMEM_COLS = NACC * N < 32 ? 32 : NACC * N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int C = P.C;
@@ -70,8 +74,8 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
   uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);
   uint64_t* a_empty = a_full + kMaxBuf;
   uint64_t* tfull = a_empty + kMaxBuf;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tempty = tfull + kMaxAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxAcc);
   float* s_stats = reinterpret_cast<float*>(aux + kHaloAux);   // [8 epilogue warps][2*N]
   uint32_t* s_tr = reinterpret_cast<uint32_t*>(s_stats + 8 * 2 * N);   // [8 epilogue warps][32][kTrW] bf16x2
 
@@ -80,7 +84,7 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
   if (warp == 0 && elect_one()) prefetch_tmap(&tmA);
   if (threadIdx.x == 32) {
     for (int i = 0; i < kMaxBuf; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < kMaxAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -133,8 +137,8 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
       const int ksteps = KC >> 4;
       int it = 0, pi = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t tpar = (uint32_t)(it >> 1) & 1u;
+        const int acc = it % NACC;
+        const uint32_t tpar = (uint32_t)(it / NACC) & 1u;
         mbar_wait(&tempty[acc], tpar ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
@@ -177,8 +181,8 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
       const int oh = thi * HT_H + lh, ow = twi * HT_W + lw;
       const bool valid = oh < P.oh && ow < P.ow;
       bf16* orow = P.out + (long long)img * P.out_sn + (long long)oh * P.out_sh + (long long)ow * P.out_sw;
-      const int acc = it & 1;
-      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      const int acc = it % NACC;
+      const uint32_t par = (uint32_t)(it / NACC) & 1u;
       mbar_wait(&tfull[acc], par);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);

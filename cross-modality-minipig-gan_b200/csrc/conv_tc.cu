@@ -390,7 +390,6 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, NX, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < my_tiles; ++i) {
@@ -400,13 +399,20 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-          for (int q = 0; q < nt; ++q) {
+          // The tap tiles of a stage are contiguous in shared memory and their accumulators are adjacent TMEM
+          // columns, so up to 256/NX taps are ONE MMA with N = taps*NX: the cost of an MMA is dominated by the fetch
+          // of its 128 A rows (the dY tile, shared by all taps), not by N.
+          constexpr int TPM = (256 / NX) < B::TPS ? (256 / NX) : B::TPS;   // taps per MMA
+          constexpr uint32_t LBO_N = NX >= 64 ? (uint32_t)B::LBO : (uint32_t)B::BYTES;   // stride between N atoms
+          for (int q = 0; q < nt; q += TPM) {
+            const int ntm = min(TPM, nt - q);
+            const uint32_t idesc_q = make_idesc_bf16(128, ntm * NX, 1, 1);
             const uint32_t d_tmem = tmem_base + (uint32_t)((tl0 + q) * NX);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {  // 64 pixels = 4 x K16
               const uint64_t adesc = make_smem_desc(a_addr + k * 2048, 8192, 1024, 2);
-              const uint64_t bdesc = make_smem_desc(b_addr + q * B::BYTES + k * B::KSTEP, B::LBO, B::SBO, B::LAYOUT);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+              const uint64_t bdesc = make_smem_desc(b_addr + q * B::BYTES + k * B::KSTEP, LBO_N, B::SBO, B::LAYOUT);
+              umma_bf16(d_tmem, adesc, bdesc, idesc_q, (i | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(&empty[stage]);

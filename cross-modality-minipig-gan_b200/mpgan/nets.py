@@ -9,6 +9,8 @@ reference).  Arithmetic never goes through torch: ``forward`` runs a static plan
 (channels-last, bf16 or fp32) and records a tape; ``backward`` replays the tape in reverse with hand-written
 gradient kernels, writing parameter gradients straight into the flat gradient buffer.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -37,6 +39,7 @@ class Plan:
         self.dtype = rt.dtype
         self.tape = []
         self.extra = {}
+        self.fork = os.environ.get("MPGAN_NO_FORK", "0") != "1"
         self._arena = None
         self._arena_used = 0
 
@@ -67,23 +70,52 @@ def conv_apply(rec, x, out=None, stats=None):
     return ops.conv_fprop(rec.spec, x, rec.w, rec.bias, out=out, stats=stats)
 
 
+_SIDE = {}
+
+
+def side_stream(device):
+    """One auxiliary stream per device: independent kernels of a layer (weight gradient vs data gradient) are
+    issued on two streams; under CUDA-graph capture the fork/join becomes two parallel graph branches."""
+    key = torch.device(device).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 def conv_backward(rec, x, dy, plan, need_dx, bias_done=False):
     """x: the layer's input, dy: gradient of its output (contiguous or sliced).  Returns dx or None.
-    bias_done: the bias gradient was already accumulated by the fused BatchNorm backward."""
+    bias_done: the bias gradient was already accumulated by the fused BatchNorm backward.
+    The weight gradient and the data gradient only share inputs, so they run concurrently (fork/join)."""
     spec = rec.spec
-    if plan.need_wgrad:
+
+    def wgrad():
         if spec.transposed:
             ops.conv_wgrad(spec, dy, x, rec.dw)
         else:
             ops.conv_wgrad(spec, x, dy, rec.dw)
         if rec.db is not None and not bias_done:
             ops.colsum(dy, rec.db)
+
+    def dgrad():
+        if spec.transposed:
+            return ops.conv_fprop(spec, dy, rec.w, None)[0]
+        return ops.conv_bprop(spec, dy, rec.w, rec.wt, None, xs=tuple(x.shape[1:-1]))[0]
+
+    if not plan.need_wgrad:
+        return dgrad() if need_dx else None
     if not need_dx:
+        wgrad()
         return None
-    if spec.transposed:
-        dx, _ = ops.conv_fprop(spec, dy, rec.w, None)
-    else:
-        dx, _ = ops.conv_bprop(spec, dy, rec.w, rec.wt, None, xs=tuple(x.shape[1:-1]))
+    if not plan.fork:
+        wgrad()
+        return dgrad()
+    cur = torch.cuda.current_stream()
+    side = side_stream(dy.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        wgrad()
+    dx = dgrad()
+    cur.wait_stream(side)   # join before anything downstream can recycle dy / x
     return dx
 
 
@@ -205,14 +237,27 @@ class ResidualUnit(nn.Module):
 
     def _fwd(self, x, plan, out=None):
         has_res_conv = not isinstance(self.residual, nn.Identity)
-        if has_res_conv:
-            r, _ = conv_apply(plan.rt.rec[self.residual], x)
+        forked = False
+        if has_res_conv:  # the residual convolution only shares its input with the main path: run it alongside
+            rrec = plan.rt.rec[self.residual]
+            sp = rrec.spec.y_of_x(tuple(x.shape[1:-1]))
+            r = _new(x, (x.shape[0],) + tuple(sp) + (rrec.spec.cy,))
+            if plan.fork:
+                cur, side = torch.cuda.current_stream(), side_stream(x.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    conv_apply(rrec, x, out=r)
+                forked = True
+            else:
+                conv_apply(rrec, x, out=r)
         else:
             r = x
         units = list(self.conv)
         h = x
         for u in units[:-1]:
             h = u._fwd(h, plan)
+        if forked:
+            cur.wait_stream(side)
         y = units[-1]._fwd(h, plan, out=out, res=r)
         if plan.save:
             plan.tape.append((x,))
@@ -222,13 +267,23 @@ class ResidualUnit(nn.Module):
         (x,) = plan.tape.pop()
         has_res_conv = not isinstance(self.residual, nn.Identity)
         units = list(self.conv)
+        forked = False
+        if has_res_conv:
+            if plan.fork:
+                cur, side = torch.cuda.current_stream(), side_stream(dy.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    dr = conv_backward(plan.rt.rec[self.residual], x, dy, plan, need_dx)
+                forked = True
+            else:
+                dr = conv_backward(plan.rt.rec[self.residual], x, dy, plan, need_dx)
+        else:
+            dr = dy
         dh = dy
         for i in range(len(units) - 1, -1, -1):
             dh = units[i]._bwd(dh, plan, need_dx=(need_dx or i > 0))
-        if has_res_conv:
-            dr = conv_backward(plan.rt.rec[self.residual], x, dy, plan, need_dx)
-        else:
-            dr = dy
+        if forked:
+            cur.wait_stream(side)
         if not need_dx:
             return None
         return ops.add_copy(dh, dr, _new(dh, dh.shape))
