@@ -87,6 +87,8 @@ constexpr int kMaxPixPerThread = 512;
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 bn_stats_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, double* __restrict__ stats) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   // fp64 partial sums: var = E[x^2] - mean^2 cancels catastrophically in fp32 when |mean| >> std (the un-normalised
   // hand-over between cascaded UNets produces exactly that)
   __shared__ double s1[kThreads * V], s2[kThreads * V];
@@ -131,6 +133,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t P, 
                                    const float* beta, float eps, float momentum, int training,
                                    float* running_mean, float* running_var, int64_t* nbt, float* mean_out,
                                    float* invstd_out, float* scale, float* shift) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && training && nbt) *nbt += 1;
   if (c >= C) return;
@@ -208,6 +212,8 @@ __global__ void __launch_bounds__(kThreads)
 bn_act_apply_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, const float* __restrict__ scale,
                     const float* __restrict__ shift, const BnTrain f, int act, const float* __restrict__ alpha,
                     float leaky, const T* __restrict__ res, int64_t ldres, T* __restrict__ y, int64_t ldy) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   const int cv = C / V;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
@@ -310,6 +316,8 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __rest
                          int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ scale, const float* __restrict__ shift, int act,
                          const float* __restrict__ alpha, float leaky, double* __restrict__ sums) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   // per-thread partials are fp32 (<= kMaxPixPerThread terms each, no cancellation structure in these sums),
   // everything above the block level is fp64
   __shared__ float sm[kThreads * 2 * V];
@@ -377,6 +385,8 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restr
                         const float* __restrict__ scale, const float* __restrict__ shift, int act,
                         const float* __restrict__ alpha, float leaky, const double* __restrict__ sums,
                         float* dgamma, float* dbeta, float* dalpha, float* dbias, T* __restrict__ dx, int64_t lddx) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   __shared__ float sm[kThreads * V];
   const int cv = C / V;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -467,8 +477,8 @@ extern "C" int mpgan_bn_stats(int dtype, const void* x, int64_t ldx, int64_t pix
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype);
   const int grid = (int)ceil_div(pixels, kPixPerBlock);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    if (vec) bn_stats_kernel<T, 8><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const T*)x, ldx, pixels, c, stats);
-    else bn_stats_kernel<T, 1><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const T*)x, ldx, pixels, c, stats);
+    if (vec) launch_k(bn_stats_kernel<T, 8>, grid, kThreads, 0, (cudaStream_t)stream, (const T*)x, ldx, pixels, c, stats);
+    else launch_k(bn_stats_kernel<T, 1>, grid, kThreads, 0, (cudaStream_t)stream, (const T*)x, ldx, pixels, c, stats);
     MPGAN_CHECK_LAUNCH("bn_stats");
     return 0;
   });
@@ -481,7 +491,7 @@ extern "C" int mpgan_bn_finalize(const double* stats, int64_t pixels, int32_t c,
   MPGAN_REQUIRE(c > 0 && scale && shift, MPGAN_ERR_SHAPE, "bn_finalize: bad arguments");
   MPGAN_REQUIRE(training ? (stats != nullptr && pixels > 0) : (running_mean && running_var), MPGAN_ERR_SHAPE,
                 "bn_finalize: missing statistics");
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  launch_k(bn_finalize_kernel, (c + 127) / 128, 128, 0, (cudaStream_t)stream, 
       stats, pixels, c, gamma, beta, eps, momentum, training, running_mean, running_var, num_batches_tracked, mean,
       invstd, scale, shift);
   MPGAN_CHECK_LAUNCH("bn_finalize");
@@ -494,10 +504,10 @@ static int launch_apply(const void* x, int64_t ldx, int64_t pixels, int32_t c, c
                         int64_t ldres, void* y, int64_t ldy, bool vec, cudaStream_t s) {
   const size_t smem = f.stats ? (size_t)2 * c * sizeof(float) : 0;
   if (vec)
-    bn_act_apply_kernel<T, 8><<<ew_grid(pixels, c / 8, 8, 4), kThreads, smem, s>>>(
+    launch_k(bn_act_apply_kernel<T, 8>, ew_grid(pixels, c / 8, 8, 4), kThreads, smem, s, 
         (const T*)x, ldx, pixels, c, scale, shift, f, act, alpha, leaky_slope, (const T*)res, ldres, (T*)y, ldy);
   else
-    bn_act_apply_kernel<T, 1><<<ew_grid(pixels, c, 8, 4), kThreads, smem, s>>>(
+    launch_k(bn_act_apply_kernel<T, 1>, ew_grid(pixels, c, 8, 4), kThreads, smem, s, 
         (const T*)x, ldx, pixels, c, scale, shift, f, act, alpha, leaky_slope, (const T*)res, ldres, (T*)y, ldy);
   MPGAN_CHECK_LAUNCH("bn_act_apply");
   return 0;
@@ -543,10 +553,10 @@ extern "C" int mpgan_bn_act_bwd_reduce(int dtype, const void* dy, int64_t lddy, 
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(dy, lddy, dtype);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     if (vec)  // 4 channels per thread: the per-channel constants fit in registers at 3 blocks per SM
-      bn_act_bwd_reduce_kernel<T, 4><<<ew_grid(pixels, c / 4, 6, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      launch_k(bn_act_bwd_reduce_kernel<T, 4>, ew_grid(pixels, c / 4, 6, 16), kThreads, 0, (cudaStream_t)stream, 
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums);
     else
-      bn_act_bwd_reduce_kernel<T, 1><<<ew_grid(pixels, c, 8, 32), kThreads, 0, (cudaStream_t)stream>>>(
+      launch_k(bn_act_bwd_reduce_kernel<T, 1>, ew_grid(pixels, c, 8, 32), kThreads, 0, (cudaStream_t)stream, 
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums);
     MPGAN_CHECK_LAUNCH("bn_act_bwd_reduce");
     return 0;
@@ -564,11 +574,11 @@ extern "C" int mpgan_bn_act_bwd_apply(int dtype, const void* dy, int64_t lddy, c
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(dy, lddy, dtype) && vec_ok(dx, lddx, dtype);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     if (vec)
-      bn_act_bwd_apply_kernel<T, 4><<<ew_grid(pixels, c / 4, 6, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      launch_k(bn_act_bwd_apply_kernel<T, 4>, ew_grid(pixels, c / 4, 6, 16), kThreads, 0, (cudaStream_t)stream, 
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums,
           dgamma, dbeta, dalpha, dbias, (T*)dx, lddx);
     else
-      bn_act_bwd_apply_kernel<T, 1><<<ew_grid(pixels, c, 8, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      launch_k(bn_act_bwd_apply_kernel<T, 1>, ew_grid(pixels, c, 8, 16), kThreads, 0, (cudaStream_t)stream, 
           (const T*)dy, lddy, (const T*)x, ldx, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums,
           dgamma, dbeta, dalpha, dbias, (T*)dx, lddx);
     MPGAN_CHECK_LAUNCH("bn_act_bwd_apply");

@@ -4,6 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <utility>
 
 #include "../../include/mpgan.h"
 
@@ -60,6 +64,33 @@ __device__ __forceinline__ float block_sum(float v, float* smem32) {
   }
   __syncthreads();
   return r;
+}
+
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the library starts with pdl_wait(); pdl_launch();  and is launched with the programmatic stream
+// serialization attribute: the next kernel of the stream (or of the captured CUDA graph) is launched and scheduled
+// while this one is still running and starts the moment this one has completed and flushed -- the launch latency
+// between the ~1000 small dependent kernels of a training step disappears.  Correctness only needs the wait to
+// precede the first global-memory access (it is the first instruction).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MPGAN_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through MPGAN_CHECK_LAUNCH
 }
 
 inline int num_sms() {

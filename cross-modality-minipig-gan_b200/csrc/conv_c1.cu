@@ -52,6 +52,8 @@ template <typename T, int MODE, bool VEC>
 __global__ void __launch_bounds__(256)
 conv_to1_kernel(C1Geom p, const T* __restrict__ in, int64_t ldi, const T* __restrict__ w,
                 const float* __restrict__ bias, T* __restrict__ out, int64_t ldo) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   extern __shared__ float ws[];  // [taps][C]
   const int C = MODE == 0 ? p.cx : p.cy;
   for (int i = threadIdx.x; i < p.taps * C; i += blockDim.x) {
@@ -108,6 +110,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 wgrad_x1_kernel(C1Geom p, const T* __restrict__ x, int64_t ldx, const T* __restrict__ y, int64_t ldy,
                 float* __restrict__ dw, int64_t pix_per_block) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   extern __shared__ float sm[];
   const int CY = p.cy, TP = p.taps;
   float* ysm = sm;                    // [256][CY + 1]
@@ -211,8 +215,8 @@ static int launch_to1(const C1Geom& p, const void* in, int64_t ldi, const void* 
   int grid = (int)(blocks > cap ? cap : blocks);
   size_t smem = (size_t)p.taps * C * sizeof(float);
   const bool vec = (C % LoadVec<T>::V == 0) && (ldi % LoadVec<T>::V == 0) && (((uintptr_t)in) % 16 == 0);
-  if (vec) conv_to1_kernel<T, MODE, true><<<grid, 256, smem, s>>>(p, (const T*)in, ldi, (const T*)w, bias, (T*)out, ldo);
-  else conv_to1_kernel<T, MODE, false><<<grid, 256, smem, s>>>(p, (const T*)in, ldi, (const T*)w, bias, (T*)out, ldo);
+  if (vec) launch_k(conv_to1_kernel<T, MODE, true>, grid, 256, smem, s, p, (const T*)in, ldi, (const T*)w, bias, (T*)out, ldo);
+  else launch_k(conv_to1_kernel<T, MODE, false>, grid, 256, smem, s, p, (const T*)in, ldi, (const T*)w, bias, (T*)out, ldo);
   MPGAN_CHECK_LAUNCH("conv_to1_kernel");
   return 0;
 }
@@ -266,7 +270,7 @@ extern "C" int mpgan_c1_conv_wgrad(const MpganConvGeom* g, int dtype, const void
       cudaFuncSetAttribute(wgrad_x1_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
       attr_done = true;
     }
-    wgrad_x1_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(p, (const T*)x, ldx, (const T*)y, ldy, dw, ppb);
+    launch_k(wgrad_x1_kernel<T>, grid, 256, smem, (cudaStream_t)stream, p, (const T*)x, ldx, (const T*)y, ldy, dw, ppb);
     MPGAN_CHECK_LAUNCH("wgrad_x1_kernel");
     return 0;
   });

@@ -117,6 +117,8 @@ template <typename T, int V, int S>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 1 : 2)
 fprop_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__ w, const float* __restrict__ bias,
              T* __restrict__ y, int ldy, double* __restrict__ stats) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   __shared__ double sm[(kThreads / 32) * 32 * 2 * V];   // statistics reduce: up to 32 channel groups of 2V doubles per warp
   constexpr int NP = Pairs<V>::N;
   const int cv = g.C / V;
@@ -218,6 +220,8 @@ template <typename T, int V, int S>
 __global__ void __launch_bounds__(kThreads, 2)
 bprop_kernel(Geom g, const T* __restrict__ y, int ldy, const T* __restrict__ w, const float* __restrict__ bias,
              T* __restrict__ x, int ldx, double* __restrict__ stats) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   __shared__ double sred[2 * (kThreads / 32)];
   constexpr int NP = Pairs<V>::N;
   const int cv = g.C / V;   // divides 32
@@ -307,6 +311,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kThreads, 2)
 bprop_s2_kernel(Geom g, const T* __restrict__ y, int ldy, const T* __restrict__ w, const float* __restrict__ bias,
                 T* __restrict__ x, int ldx, double* __restrict__ stats) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   __shared__ double sred[2 * (kThreads / 32)];
   constexpr int NP = Pairs<V>::N;
   const int cv = g.C / V;   // divides 32
@@ -397,6 +403,8 @@ bprop_s2_kernel(Geom g, const T* __restrict__ y, int ldy, const T* __restrict__ 
 template <typename T, int V, int S>
 __global__ void __launch_bounds__(kThreads, 2)
 wgrad_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__ y, int ldy, float* __restrict__ dw) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   extern __shared__ float smf[];   // (kThreads/32) * cv * 9 * V floats
   constexpr int NP = Pairs<V>::N;
   const int cv = g.C / V;   // divides 32
@@ -484,12 +492,12 @@ static int vec_of(int C, const void* p, int64_t ld) {
 // every element offset of a tensor with `pixels` pixels of stride ld must fit in int32
 static inline bool fits32(int64_t pixels, int64_t ld) { return pixels * ld < ((int64_t)1 << 31) - 4096; }
 
-#define C1F_LAUNCH(KERNEL, V_, S_, ...)                                               \
-  do {                                                                                \
-    if (V_ == 8 && S_ == 1) KERNEL<T, 8, 1> __VA_ARGS__;                              \
-    else if (V_ == 8) KERNEL<T, 8, 2> __VA_ARGS__;                                    \
-    else if (S_ == 1) KERNEL<T, 1, 1> __VA_ARGS__;                                    \
-    else KERNEL<T, 1, 2> __VA_ARGS__;                                                 \
+#define C1F_LAUNCH(KERNEL, V_, S_, GRID, SMEM, STREAM, ...)                                        \
+  do {                                                                                             \
+    if (V_ == 8 && S_ == 1) launch_k(KERNEL<T, 8, 1>, GRID, kThreads, SMEM, STREAM, __VA_ARGS__);    \
+    else if (V_ == 8) launch_k(KERNEL<T, 8, 2>, GRID, kThreads, SMEM, STREAM, __VA_ARGS__);          \
+    else if (S_ == 1) launch_k(KERNEL<T, 1, 1>, GRID, kThreads, SMEM, STREAM, __VA_ARGS__);          \
+    else launch_k(KERNEL<T, 1, 2>, GRID, kThreads, SMEM, STREAM, __VA_ARGS__);                       \
   } while (0)
 
 }  // namespace c1f
@@ -509,8 +517,8 @@ int c1f_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, con
   if (!fits32(P, ldy) || !fits32((int64_t)q.n * q.xh * q.xw, ldx) || P * cv >= ((int64_t)1 << 30)) return 1;
   const int grid = grid_for(P, cv, 8, 8);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    C1F_LAUNCH(fprop_kernel, V, q.s, <<<grid, kThreads, 0, s>>>(q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y,
-                                                               (int)ldy, stats));
+    C1F_LAUNCH(fprop_kernel, V, q.s, grid, 0, s, q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y,
+                                                               (int)ldy, stats);
     MPGAN_CHECK_LAUNCH("c1f_fprop");
     return 0;
   });
@@ -531,16 +539,16 @@ int c1f_bprop(const MpganConvGeom* g, int dtype, const void* y, int64_t ldy, con
     const int64_t PY = (int64_t)q.n * q.yh * q.yw;
     const int grid2 = grid_for(PY, cv, 2, 8);
     MPGAN_DISPATCH_DTYPE(dtype, T, {
-      if (V == 8) bprop_s2_kernel<T, 8><<<grid2, kThreads, 0, s>>>(q, (const T*)y, (int)ldy, (const T*)w, bias, (T*)x, (int)ldx, stats);
-      else bprop_s2_kernel<T, 1><<<grid2, kThreads, 0, s>>>(q, (const T*)y, (int)ldy, (const T*)w, bias, (T*)x, (int)ldx, stats);
+      if (V == 8) launch_k(bprop_s2_kernel<T, 8>, grid2, kThreads, 0, s, q, (const T*)y, (int)ldy, (const T*)w, bias, (T*)x, (int)ldx, stats);
+      else launch_k(bprop_s2_kernel<T, 1>, grid2, kThreads, 0, s, q, (const T*)y, (int)ldy, (const T*)w, bias, (T*)x, (int)ldx, stats);
       MPGAN_CHECK_LAUNCH("c1f_bprop_s2");
       return 0;
     });
   }
   const int grid = grid_for(P, cv, 4, 8);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    C1F_LAUNCH(bprop_kernel, V, q.s, <<<grid, kThreads, 0, s>>>(q, (const T*)y, (int)ldy, (const T*)w, bias, (T*)x,
-                                                               (int)ldx, stats));
+    C1F_LAUNCH(bprop_kernel, V, q.s, grid, 0, s, q, (const T*)y, (int)ldy, (const T*)w, bias, (T*)x,
+                                                               (int)ldx, stats);
     MPGAN_CHECK_LAUNCH("c1f_bprop");
     return 0;
   });
@@ -560,7 +568,7 @@ int c1f_wgrad(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, con
   const int grid = grid_for(P, cv, 32, 4);
   const size_t smem = (size_t)(kThreads / 32) * cv * kTaps * V * sizeof(float);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    C1F_LAUNCH(wgrad_kernel, V, q.s, <<<grid, kThreads, smem, s>>>(q, (const T*)x, (int)ldx, (const T*)y, (int)ldy, dw));
+    C1F_LAUNCH(wgrad_kernel, V, q.s, grid, smem, s, q, (const T*)x, (int)ldx, (const T*)y, (int)ldy, dw);
     MPGAN_CHECK_LAUNCH("c1f_wgrad");
     return 0;
   });

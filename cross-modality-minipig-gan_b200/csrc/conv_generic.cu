@@ -47,6 +47,8 @@ template <typename T, int BM, int BN, int MODE>
 __global__ void __launch_bounds__(256)
 conv_gather_kernel(ConvP p, const T* __restrict__ in, int64_t ldi, const T* __restrict__ w,
                    const float* __restrict__ bias, T* __restrict__ out, int64_t ldo) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   constexpr int TX = BN / 4, TY = BM / 4;
   static_assert(TX * TY == 256, "tile/thread mismatch");
   __shared__ float As[BK][BM + 4];
@@ -169,6 +171,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 conv_wgrad_kernel(ConvP p, const T* __restrict__ x, int64_t ldx, const T* __restrict__ y, int64_t ldy,
                   float* __restrict__ dw, int64_t pix_per_block) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   constexpr int BM = 64, BN = 64;
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
@@ -287,10 +291,10 @@ static int launch_gather(const ConvP& p, const void* in, int64_t ldi, const void
   const int64_t P = (int64_t)p.n * os[0] * os[1] * os[2];
   if (N <= 16) {
     dim3 grid((unsigned)ceil_div(P, 256), (unsigned)ceil_div(N, 16));
-    conv_gather_kernel<T, 256, 16, MODE><<<grid, 256, 0, s>>>(p, (const T*)in, ldi, (const T*)w, bias, (T*)out, ldo);
+    launch_k(conv_gather_kernel<T, 256, 16, MODE>, grid, 256, 0, s, p, (const T*)in, ldi, (const T*)w, bias, (T*)out, ldo);
   } else {
     dim3 grid((unsigned)ceil_div(P, 64), (unsigned)ceil_div(N, 64));
-    conv_gather_kernel<T, 64, 64, MODE><<<grid, 256, 0, s>>>(p, (const T*)in, ldi, (const T*)w, bias, (T*)out, ldo);
+    launch_k(conv_gather_kernel<T, 64, 64, MODE>, grid, 256, 0, s, p, (const T*)in, ldi, (const T*)w, bias, (T*)out, ldo);
   }
   MPGAN_CHECK_LAUNCH("conv_gather_kernel");
   return 0;
@@ -333,7 +337,7 @@ extern "C" int mpgan_conv_wgrad(const MpganConvGeom* g, int dtype, const void* x
   const int gz = (int)ceil_div(P, ppb);
   dim3 grid(gx, gy, gz);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    conv_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(p, (const T*)x, ldx, (const T*)y, ldy, dw, ppb);
+    launch_k(conv_wgrad_kernel<T>, grid, 256, 0, (cudaStream_t)stream, p, (const T*)x, ldx, (const T*)y, ldy, dw, ppb);
     MPGAN_CHECK_LAUNCH("conv_wgrad_kernel");
     return 0;
   });

@@ -89,6 +89,8 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
   for (int i = threadIdx.x; i < 8 * 2 * N; i += blockDim.x) s_stats[i] = 0.f;
+  pdl_wait();      // PDL: barrier init / TMEM allocation above overlap the previous kernel; global reads start here
+  pdl_launch();
   // resident weights: global [n][tap][C] -> smem [tap][kc][n][KC channels], rows swizzled exactly like a TMA box
   {
     const int cpp = C >> 3;
@@ -263,7 +265,7 @@ static int launch_halo(const HaloParams& P, const CUtensorMap& mA, size_t smem, 
     attr_done = true;
   }
   const int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  halo3x3_kernel<N><<<grid, kHaloThreads, smem, s>>>(P, mA);
+  launch_k(halo3x3_kernel<N>, grid, kHaloThreads, smem, s, P, mA);
   MPGAN_CHECK_LAUNCH("halo3x3_kernel");
   return 0;
 }

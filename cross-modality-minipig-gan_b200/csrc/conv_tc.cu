@@ -138,6 +138,8 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // PDL: barrier init / TMEM allocation / descriptor prefetch above overlap the previous kernel
+  pdl_launch();
 
   const int tn_log2 = 7 - P.tw_log2 - P.th_log2;
   const int per_cls = P.tiles_n * P.tiles_h * P.tiles_w * P.n_tiles;
@@ -347,6 +349,8 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // PDL: the on-chip prologue above overlaps the previous kernel
+  pdl_launch();
 
   int b = blockIdx.x;
   const int mb = b % P.m_blocks; b /= P.m_blocks;
@@ -568,7 +572,7 @@ static int launch_tapgemm_t(const TapGemmParams& P, const CUtensorMap* mA, const
   }
   const long long total = (long long)P.ncls * P.tiles_n * P.tiles_h * P.tiles_w * P.n_tiles;
   int grid = (int)(total < num_sms() ? total : num_sms());
-  tapgemm_kernel<BN, KC><<<grid, 256, Cfg::SMEM_BYTES, s>>>(P, mA[0], mA[1], mA[2], mA[3], mB);
+  launch_k(tapgemm_kernel<BN, KC>, grid, 256, Cfg::SMEM_BYTES, s, P, mA[0], mA[1], mA[2], mA[3], mB);
   MPGAN_CHECK_LAUNCH("tapgemm_kernel");
   return 0;
 }
@@ -713,7 +717,7 @@ static int launch_wgrad_t(const WgradParams& P, const CUtensorMap& mY, const CUt
     attr_done = true;
   }
   int grid = P.m_blocks * P.ngroups * P.splits;
-  wgrad_kernel<NX><<<grid, 256, Cfg::SMEM_BYTES, s>>>(P, mY, mX[0], mX[1], mX[2], mX[3]);
+  launch_k(wgrad_kernel<NX>, grid, 256, Cfg::SMEM_BYTES, s, P, mY, mX[0], mX[1], mX[2], mX[3]);
   MPGAN_CHECK_LAUNCH("wgrad_kernel");
   return 0;
 }

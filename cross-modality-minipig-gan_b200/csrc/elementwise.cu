@@ -18,6 +18,8 @@ void set_error(const char* fmt, ...) {
 template <typename TI, typename TO>
 __global__ void add_copy_kernel(const TI* __restrict__ a, int64_t lda, const TI* __restrict__ b, int64_t ldb,
                                 TO* __restrict__ y, int64_t ldy, int64_t P, int C) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   const int64_t total = P * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t p = i / C;
@@ -55,6 +57,8 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 add_copy_vec_kernel(const TI* __restrict__ a, int64_t lda, const TI* __restrict__ b, int64_t ldb, TO* __restrict__ y,
                     int64_t ldy, int64_t P, int cv) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   const int64_t total = P * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / cv;
@@ -72,11 +76,15 @@ add_copy_vec_kernel(const TI* __restrict__ a, int64_t lda, const TI* __restrict_
 
 template <typename TI, typename TO>
 __global__ void tanh_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t n) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = from_f<TO>(tanhf(to_f(x[i])));
 }
 template <typename T>
 __global__ void tanh_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t n) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float t = to_f(y[i]);
     dx[i] = from_f<T>(to_f(dy[i]) * (1.f - t * t));
@@ -87,6 +95,8 @@ __global__ void tanh_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, float* __restrict__ out, int pix_per_block) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   __shared__ float sm[256];
   const int CL = C < 256 ? C : 256, PL = 256 / CL;
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
@@ -108,6 +118,8 @@ colsum_kernel(const T* __restrict__ x, int64_t ldx, int64_t P, int C, float* __r
 
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ s, TO* __restrict__ d, int64_t n) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     d[i] = from_f<TO>(to_f(s[i]));
 }
@@ -115,6 +127,8 @@ __global__ void cast_kernel(const TI* __restrict__ s, TO* __restrict__ d, int64_
 // [cy][taps][cx] -> [cx][taps][cy]
 template <typename TI, typename TO>
 __global__ void weight_transpose_kernel(const TI* __restrict__ s, TO* __restrict__ d, int cy, int taps, int cx) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   const int64_t total = (int64_t)cy * taps * cx;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int y = (int)(i % cy);  // destination-major enumeration: i = (x*taps + t)*cy + y
@@ -129,6 +143,8 @@ __global__ void weight_transpose_kernel(const TI* __restrict__ s, TO* __restrict
 template <typename TI, typename TO>
 __global__ void permute_flatten_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int rows, int C,
                                        int64_t S, int to_cl, int accumulate) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   const int64_t total = (int64_t)rows * C * S;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / (C * S);
@@ -185,10 +201,10 @@ extern "C" int mpgan_add_copy(int dtype_in, const void* a, int64_t lda, const vo
                    ((uintptr_t)y % 16) == 0 && (!b || ((uintptr_t)b % 16) == 0);
   DISPATCH2(dtype_in, dtype_out, TI, TO, {
     if (vec)
-      add_copy_vec_kernel<TI, TO><<<ew_grid(pixels * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+      launch_k(add_copy_vec_kernel<TI, TO>, ew_grid(pixels * (c / 8)), 256, 0, (cudaStream_t)stream, 
           (const TI*)a, lda, (const TI*)b, ldb, (TO*)y, ldy, pixels, c / 8);
     else
-      add_copy_kernel<TI, TO><<<ew_grid(pixels * c), 256, 0, (cudaStream_t)stream>>>((const TI*)a, lda, (const TI*)b,
+      launch_k(add_copy_kernel<TI, TO>, ew_grid(pixels * c), 256, 0, (cudaStream_t)stream, (const TI*)a, lda, (const TI*)b,
                                                                                    ldb, (TO*)y, ldy, pixels, c);
     MPGAN_CHECK_LAUNCH("add_copy");
     return 0;
@@ -198,7 +214,7 @@ extern "C" int mpgan_add_copy(int dtype_in, const void* a, int64_t lda, const vo
 extern "C" int mpgan_tanh_fwd(int dtype_in, const void* x, int dtype_out, void* y, int64_t n, void* stream) {
   MPGAN_REQUIRE(n > 0, MPGAN_ERR_SHAPE, "tanh: empty");
   DISPATCH2(dtype_in, dtype_out, TI, TO, {
-    tanh_fwd_kernel<TI, TO><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const TI*)x, (TO*)y, n);
+    launch_k(tanh_fwd_kernel<TI, TO>, ew_grid(n), 256, 0, (cudaStream_t)stream, (const TI*)x, (TO*)y, n);
     MPGAN_CHECK_LAUNCH("tanh_fwd");
     return 0;
   });
@@ -207,7 +223,7 @@ extern "C" int mpgan_tanh_fwd(int dtype_in, const void* x, int dtype_out, void* 
 extern "C" int mpgan_tanh_bwd(int dtype, const void* dy, const void* y, void* dx, int64_t n, void* stream) {
   MPGAN_REQUIRE(n > 0, MPGAN_ERR_SHAPE, "tanh: empty");
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    tanh_bwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)y, (T*)dx, n);
+    launch_k(tanh_bwd_kernel<T>, ew_grid(n), 256, 0, (cudaStream_t)stream, (const T*)dy, (const T*)y, (T*)dx, n);
     MPGAN_CHECK_LAUNCH("tanh_bwd");
     return 0;
   });
@@ -220,7 +236,7 @@ extern "C" int mpgan_colsum(int dtype, const void* x, int64_t ldx, int64_t pixel
   int64_t ppb64 = ceil_div(pixels, (int64_t)num_sms() * 2);
   const int ppb = (int)(ppb64 < 64 ? 64 : (ppb64 > 2048 ? 2048 : ppb64));
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    colsum_kernel<T><<<(int)ceil_div(pixels, ppb), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, pixels, c, out, ppb);
+    launch_k(colsum_kernel<T>, (int)ceil_div(pixels, ppb), 256, 0, (cudaStream_t)stream, (const T*)x, ldx, pixels, c, out, ppb);
     MPGAN_CHECK_LAUNCH("colsum");
     return 0;
   });
@@ -229,7 +245,7 @@ extern "C" int mpgan_colsum(int dtype, const void* x, int64_t ldx, int64_t pixel
 extern "C" int mpgan_cast(int dtype_src, const void* src, int dtype_dst, void* dst, int64_t n, void* stream) {
   MPGAN_REQUIRE(n > 0, MPGAN_ERR_SHAPE, "cast: empty");
   DISPATCH2(dtype_src, dtype_dst, TI, TO, {
-    cast_kernel<TI, TO><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const TI*)src, (TO*)dst, n);
+    launch_k(cast_kernel<TI, TO>, ew_grid(n), 256, 0, (cudaStream_t)stream, (const TI*)src, (TO*)dst, n);
     MPGAN_CHECK_LAUNCH("cast");
     return 0;
   });
@@ -239,7 +255,7 @@ extern "C" int mpgan_weight_transpose(int dtype_src, const void* src, int dtype_
                                       int32_t taps, int32_t cx, void* stream) {
   MPGAN_REQUIRE(cy > 0 && taps > 0 && cx > 0, MPGAN_ERR_SHAPE, "weight_transpose: bad shape");
   DISPATCH2(dtype_src, dtype_dst, TI, TO, {
-    weight_transpose_kernel<TI, TO><<<ew_grid((int64_t)cy * taps * cx), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(weight_transpose_kernel<TI, TO>, ew_grid((int64_t)cy * taps * cx), 256, 0, (cudaStream_t)stream, 
         (const TI*)src, (TO*)dst, cy, taps, cx);
     MPGAN_CHECK_LAUNCH("weight_transpose");
     return 0;
@@ -250,7 +266,7 @@ extern "C" int mpgan_permute_flatten(int dtype_src, const void* src, int dtype_d
                                      int32_t c, int64_t spatial, int to_cl, int accumulate, void* stream) {
   MPGAN_REQUIRE(rows > 0 && c > 0 && spatial > 0, MPGAN_ERR_SHAPE, "permute_flatten: bad shape");
   DISPATCH2(dtype_src, dtype_dst, TI, TO, {
-    permute_flatten_kernel<TI, TO><<<ew_grid((int64_t)rows * c * spatial), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(permute_flatten_kernel<TI, TO>, ew_grid((int64_t)rows * c * spatial), 256, 0, (cudaStream_t)stream, 
         (const TI*)src, (TO*)dst, rows, c, spatial, to_cl, accumulate);
     MPGAN_CHECK_LAUNCH("permute_flatten");
     return 0;

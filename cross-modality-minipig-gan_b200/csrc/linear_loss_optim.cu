@@ -13,6 +13,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 linear_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ y, int64_t K, int J) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   __shared__ float part[8];
   const int b = blockIdx.y;
   const int64_t k0 = (int64_t)blockIdx.x * kLinK;
@@ -44,6 +46,8 @@ linear_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const float*
 template <typename T>
 __global__ void linear_dx_kernel(const T* __restrict__ w, const float* __restrict__ dy, T* __restrict__ dx,
                                  int B, int64_t K, int J) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   const int64_t total = (int64_t)B * K;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = i / K, k = i - b * K;
@@ -57,6 +61,8 @@ __global__ void linear_dx_kernel(const T* __restrict__ w, const float* __restric
 template <typename T>
 __global__ void linear_dw_kernel(const T* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
                                  int B, int64_t K, int J) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   const int64_t total = (int64_t)J * K;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t j = i / K, k = i - j * K;
@@ -67,6 +73,8 @@ __global__ void linear_dw_kernel(const T* __restrict__ x, const float* __restric
 }
 
 __global__ void linear_db_kernel(const float* __restrict__ dy, float* __restrict__ db, int B, int J) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= J) return;
   float acc = 0.f;
@@ -76,11 +84,15 @@ __global__ void linear_db_kernel(const float* __restrict__ dy, float* __restrict
 
 // ---- sigmoid, BCE on probabilities ----
 __global__ void sigmoid_fwd_kernel(const float* __restrict__ z, float* __restrict__ p, int n) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 1.f / (1.f + expf(-z[i]));
 }
 __global__ void sigmoid_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ p, float* __restrict__ dz,
                                    int n) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dz[i] = dp[i] * p[i] * (1.f - p[i]);
 }
@@ -88,6 +100,8 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ dp, const float* __
 __global__ void __launch_bounds__(256)
 bce_fwd_kernel(const float* __restrict__ prob, const float* __restrict__ target, float weight,
                float* __restrict__ loss, int n) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   __shared__ float part[8];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -102,6 +116,8 @@ bce_fwd_kernel(const float* __restrict__ prob, const float* __restrict__ target,
 
 __global__ void bce_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ target, float weight,
                                const float* __restrict__ gscale, float* __restrict__ dprob, int n) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float g = (gscale ? *gscale : 1.f) * weight / (float)n;
@@ -113,6 +129,8 @@ __global__ void bce_bwd_kernel(const float* __restrict__ prob, const float* __re
 template <typename T>
 __global__ void __launch_bounds__(256)
 l1_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n, float scale, float* __restrict__ loss) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   __shared__ float part[8];
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -124,6 +142,8 @@ l1_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n, float
 template <typename T>
 __global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n, float scale,
                               const float* __restrict__ gscale, T* __restrict__ da, int accumulate) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   const float g = (gscale ? *gscale : 1.f) * scale;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float d = to_f(a[i]) - to_f(b[i]);
@@ -137,6 +157,8 @@ __global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, 
 // state[0] = step count (as int bits), state[1] = step_size = lr/(1-beta1^t), state[2] = sqrt(1-beta2^t).
 // The step counter lives on the device so a captured CUDA graph advances it on every replay.
 __global__ void adam_prep_kernel(float* __restrict__ state, float lr, float beta1, float beta2) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   int step = __float_as_int(state[0]) + 1;
   state[0] = __int_as_float(step);
   double bc1 = 1.0 - pow((double)beta1, (double)step);
@@ -148,6 +170,8 @@ __global__ void adam_prep_kernel(float* __restrict__ state, float lr, float beta
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float beta1, float beta2, float eps,
                             const float* __restrict__ state, bf16* __restrict__ shadow) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   const float step_size = state[1], bc2_sqrt = state[2];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i];
@@ -165,6 +189,8 @@ template <typename T>
 __global__ void patch_gather_kernel(const T* __restrict__ vol, int rank, int s0, int s1, int s2, int C,
                                     const int* __restrict__ origins, int num_samples, int roi, T* __restrict__ out,
                                     int64_t total) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   const int r0 = rank == 3 ? roi : 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C); int64_t r = i / C;
@@ -185,6 +211,8 @@ template <typename T>
 __global__ void patch_scatter_kernel(const T* __restrict__ dpatch, int rank, int s0, int s1, int s2, int C,
                                      const int* __restrict__ origins, int num_samples, int roi,
                                      T* __restrict__ dvol, int64_t total) {
+  pdl_wait();      // programmatic dependent launch: everything before this overlaps the previous kernel
+  pdl_launch();
   const int r0 = rank == 3 ? roi : 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C); int64_t r = i / C;
@@ -220,7 +248,7 @@ extern "C" int mpgan_linear_fwd(int dtype, const void* x, const void* w, const f
   MPGAN_REQUIRE(batch > 0 && k > 0 && j > 0 && batch <= 65535, MPGAN_ERR_SHAPE, "linear_fwd: bad shape");
   dim3 grid((unsigned)ceil_div(k, kLinK), (unsigned)batch);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    linear_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)w, bias, y, k, j);
+    launch_k(linear_fwd_kernel<T>, grid, 256, 0, (cudaStream_t)stream, (const T*)x, (const T*)w, bias, y, k, j);
     MPGAN_CHECK_LAUNCH("linear_fwd");
     return 0;
   });
@@ -232,15 +260,15 @@ extern "C" int mpgan_linear_bwd(int dtype, const void* x, const void* w, const f
   cudaStream_t s = (cudaStream_t)stream;
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     if (dx) {
-      linear_dx_kernel<T><<<ew_grid((int64_t)batch * k), 256, 0, s>>>((const T*)w, dy, (T*)dx, batch, k, j);
+      launch_k(linear_dx_kernel<T>, ew_grid((int64_t)batch * k), 256, 0, s, (const T*)w, dy, (T*)dx, batch, k, j);
       MPGAN_CHECK_LAUNCH("linear_dx");
     }
     if (dw) {
-      linear_dw_kernel<T><<<ew_grid((int64_t)j * k), 256, 0, s>>>((const T*)x, dy, dw, batch, k, j);
+      launch_k(linear_dw_kernel<T>, ew_grid((int64_t)j * k), 256, 0, s, (const T*)x, dy, dw, batch, k, j);
       MPGAN_CHECK_LAUNCH("linear_dw");
     }
     if (db) {
-      linear_db_kernel<<<(j + 63) / 64, 64, 0, s>>>(dy, db, batch, j);
+      launch_k(linear_db_kernel, (j + 63) / 64, 64, 0, s, dy, db, batch, j);
       MPGAN_CHECK_LAUNCH("linear_db");
     }
     return 0;
@@ -249,14 +277,14 @@ extern "C" int mpgan_linear_bwd(int dtype, const void* x, const void* w, const f
 
 extern "C" int mpgan_sigmoid_fwd(const float* z, float* prob, int32_t n, void* stream) {
   MPGAN_REQUIRE(n > 0 && z && prob, MPGAN_ERR_SHAPE, "sigmoid_fwd: bad arguments");
-  sigmoid_fwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(z, prob, n);
+  launch_k(sigmoid_fwd_kernel, (n + 127) / 128, 128, 0, (cudaStream_t)stream, z, prob, n);
   MPGAN_CHECK_LAUNCH("sigmoid_fwd");
   return 0;
 }
 
 extern "C" int mpgan_sigmoid_bwd(const float* dprob, const float* prob, float* dz, int32_t n, void* stream) {
   MPGAN_REQUIRE(n > 0 && dprob && prob && dz, MPGAN_ERR_SHAPE, "sigmoid_bwd: bad arguments");
-  sigmoid_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dprob, prob, dz, n);
+  launch_k(sigmoid_bwd_kernel, (n + 127) / 128, 128, 0, (cudaStream_t)stream, dprob, prob, dz, n);
   MPGAN_CHECK_LAUNCH("sigmoid_bwd");
   return 0;
 }
@@ -264,7 +292,7 @@ extern "C" int mpgan_sigmoid_bwd(const float* dprob, const float* prob, float* d
 extern "C" int mpgan_bce_fwd(const float* prob, const float* target, float weight, float* loss, int32_t n,
                              void* stream) {
   MPGAN_REQUIRE(n > 0 && prob && target && loss, MPGAN_ERR_SHAPE, "bce_fwd: bad arguments");
-  bce_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(prob, target, weight, loss, n);
+  launch_k(bce_fwd_kernel, 1, 256, 0, (cudaStream_t)stream, prob, target, weight, loss, n);
   MPGAN_CHECK_LAUNCH("bce_fwd");
   return 0;
 }
@@ -272,7 +300,7 @@ extern "C" int mpgan_bce_fwd(const float* prob, const float* target, float weigh
 extern "C" int mpgan_bce_bwd(const float* prob, const float* target, float weight, const float* gscale,
                              float* dprob, int32_t n, void* stream) {
   MPGAN_REQUIRE(n > 0 && prob && target && dprob, MPGAN_ERR_SHAPE, "bce_bwd: bad arguments");
-  bce_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prob, target, weight, gscale, dprob, n);
+  launch_k(bce_bwd_kernel, (n + 127) / 128, 128, 0, (cudaStream_t)stream, prob, target, weight, gscale, dprob, n);
   MPGAN_CHECK_LAUNCH("bce_bwd");
   return 0;
 }
@@ -283,7 +311,7 @@ extern "C" int mpgan_l1_fwd(int dtype, const void* a, const void* b, int64_t n, 
   int grid = ew_grid(n);
   if (grid > num_sms() * 4) grid = num_sms() * 4;
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    l1_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, n, weight / (float)n, loss);
+    launch_k(l1_fwd_kernel<T>, grid, 256, 0, (cudaStream_t)stream, (const T*)a, (const T*)b, n, weight / (float)n, loss);
     MPGAN_CHECK_LAUNCH("l1_fwd");
     return 0;
   });
@@ -293,7 +321,7 @@ extern "C" int mpgan_l1_bwd(int dtype, const void* a, const void* b, int64_t n, 
                             void* da, int accumulate, void* stream) {
   MPGAN_REQUIRE(n > 0 && a && b && da, MPGAN_ERR_SHAPE, "l1_bwd: bad arguments");
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    l1_bwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, n, weight / (float)n,
+    launch_k(l1_bwd_kernel<T>, ew_grid(n), 256, 0, (cudaStream_t)stream, (const T*)a, (const T*)b, n, weight / (float)n,
                                                                  gscale, (T*)da, accumulate);
     MPGAN_CHECK_LAUNCH("l1_bwd");
     return 0;
@@ -304,9 +332,9 @@ extern "C" int mpgan_adam_step(float* param, const float* grad, float* exp_avg, 
                                float lr, float beta1, float beta2, float eps, float* state, void* bf16_shadow,
                                void* stream) {
   MPGAN_REQUIRE(n > 0 && state && param && grad && exp_avg && exp_avg_sq, MPGAN_ERR_SHAPE, "adam: bad arguments");
-  adam_prep_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2);
+  launch_k(adam_prep_kernel, 1, 1, 0, (cudaStream_t)stream, state, lr, beta1, beta2);
   MPGAN_CHECK_LAUNCH("adam_prep");
-  adam_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
+  launch_k(adam_kernel, ew_grid(n), 256, 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
                                                            state, (bf16*)bf16_shadow);
   MPGAN_CHECK_LAUNCH("adam");
   return 0;
@@ -320,7 +348,7 @@ extern "C" int mpgan_patch_gather(int dtype, const void* vol, int32_t batch, int
   int s0 = rank == 3 ? spatial[0] : 1, s1 = spatial[rank - 2], s2 = spatial[rank - 1];
   int64_t total = (int64_t)batch * num_samples * (rank == 3 ? roi : 1) * roi * roi * c;
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    patch_gather_kernel<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)vol, rank, s0, s1, s2, c,
+    launch_k(patch_gather_kernel<T>, ew_grid(total), 256, 0, (cudaStream_t)stream, (const T*)vol, rank, s0, s1, s2, c,
                                                                            origins, num_samples, roi, (T*)out, total);
     MPGAN_CHECK_LAUNCH("patch_gather");
     return 0;
@@ -335,7 +363,7 @@ extern "C" int mpgan_patch_scatter_add(int dtype, const void* dpatch, int32_t ba
   int s0 = rank == 3 ? spatial[0] : 1, s1 = spatial[rank - 2], s2 = spatial[rank - 1];
   int64_t total = (int64_t)batch * s0 * s1 * s2 * c;
   MPGAN_DISPATCH_DTYPE(dtype, T, {
-    patch_scatter_kernel<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const T*)dpatch, rank, s0, s1, s2, c,
+    launch_k(patch_scatter_kernel<T>, ew_grid(total), 256, 0, (cudaStream_t)stream, (const T*)dpatch, rank, s0, s1, s2, c,
                                                                             origins, num_samples, roi, (T*)dvol, total);
     MPGAN_CHECK_LAUNCH("patch_scatter_add");
     return 0;
