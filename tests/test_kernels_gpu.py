@@ -257,6 +257,38 @@ def test_bn_act_forward_backward(c, act, dtype, fused):
         assert rel_l2(da, alpha.grad) <= 1e-4
 
 
+@pytest.mark.parametrize("n,c,h,w_", [(3, 64, 384, 384), (2, 256, 256, 256), (1, 128, 451, 443)])
+def test_bn_streaming_kernels_large_bf16(n, c, h, w_):
+    """Tensors >= 48 MB (contiguous bf16, LeakyReLU) take the bulk-copy streaming kernels of bn_stream.cu; the last
+    shape ends in a partial 16 KB chunk."""
+    x = (rnd(n, c, h, w_, seed=51) * 2 + 0.3).bfloat16().float().requires_grad_(True)
+    dy = rnd(n, c, h, w_, seed=52).bfloat16().float()
+    bn = torch.nn.BatchNorm2d(c).to(DEV)
+    with torch.no_grad():
+        bn.weight.copy_(rnd(c, seed=53) + 1.5), bn.bias.copy_(rnd(c, seed=54))
+    bn_k = torch.nn.BatchNorm2d(c).to(DEV)
+    bn_k.load_state_dict(bn.state_dict())
+    yr = F.leaky_relu(bn(x), 0.2)
+    yr.backward(dy)
+    xc = cl(x.detach(), torch.bfloat16)
+    assert xc.numel() * 2 >= 48 << 20
+    stats = torch.zeros(2 * c, dtype=torch.float64, device=DEV)
+    ops.bn_stats(xc, stats)
+    buf = torch.empty(4, c, device=DEV)
+    y = ops.bn_train_apply(xc, stats, bn_k, buf, ACT_LEAKY, None, 0.2, None, torch.empty_like(xc))
+    assert rel_l2(uncl(y), yr) <= 8e-3
+    assert rel_l2(bn_k.running_mean, bn.running_mean) <= 1e-5 and rel_l2(bn_k.running_var, bn.running_var) <= 1e-5
+    y2 = ops.bn_act_apply(xc, buf[2], buf[3], ACT_LEAKY, None, 0.2, None, torch.empty_like(xc))
+    assert torch.equal(y, y2)
+    sums = torch.zeros(2 * c + 1, dtype=torch.float64, device=DEV)
+    dg, db, dbias = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+    dx = ops.bn_act_bwd(cl(dy, torch.bfloat16), xc, buf[0], buf[1], buf[2], buf[3], ACT_LEAKY, None, 0.2, sums, dg, db,
+                        None, torch.empty_like(xc), dbias=dbias)
+    assert rel_l2(uncl(dx), x.grad) <= 1e-2
+    assert rel_l2(dg, bn.weight.grad) <= 1e-4 and rel_l2(db, bn.bias.grad) <= 1e-4
+    assert torch.allclose(dbias, dx.float().sum(dim=(0, 1, 2)), rtol=1e-3, atol=1e-3 * float(dx.float().abs().max()))
+
+
 def test_bn_eval_mode():
     c = 16
     bn = torch.nn.BatchNorm2d(c).to(DEV).eval()
