@@ -467,18 +467,20 @@ static inline int ew_grid(int64_t pixels, int cv, int blocks_per_sm = 8, int pix
   return (int)(ceil_div(b, mult) * mult);
 }
 
-// bn_stream.cu: bulk-copy streaming variants for large contiguous bf16 tensors
-bool bn_stream_ok(int dtype, const void* a, const void* b, const void* c, int64_t ld_a, int64_t ld_b, int64_t ld_c,
+// bn_stream.cu: bulk-copy streaming variants for contiguous bf16 tensors
+bool bn_stream_ok(int dtype, const void* in0, const void* in1, const void* out, int64_t ld0, int64_t ld1, int64_t ldo,
                   int64_t pixels, int32_t C, int act);
 int bn_stream_fwd(const void* x, int64_t pixels, int32_t C, const float* scale, const float* shift,
                   const double* stats, const float* gamma, const float* beta, float eps, float momentum,
                   float* running_mean, float* running_var, int64_t* nbt, float* mean, float* invstd, float* scale_out,
-                  float* shift_out, int act, float slope, void* y, cudaStream_t s);
+                  float* shift_out, int act, const float* alpha, float slope, const void* res, void* y, int64_t ldy,
+                  cudaStream_t s);
 int bn_stream_reduce(const void* dy, const void* x, int64_t pixels, int32_t C, const float* mean, const float* invstd,
-                     const float* scale, const float* shift, int act, float slope, double* sums, cudaStream_t s);
+                     const float* scale, const float* shift, int act, const float* alpha, float slope, double* sums,
+                     cudaStream_t s);
 int bn_stream_bwd(const void* dy, const void* x, int64_t pixels, int32_t C, const float* mean, const float* invstd,
-                  const float* scale, const float* shift, int act, float slope, const double* sums, float* dgamma,
-                  float* dbeta, float* dbias, void* dx, cudaStream_t s);
+                  const float* scale, const float* shift, int act, const float* alpha, float slope, const double* sums,
+                  float* dgamma, float* dbeta, float* dalpha, float* dbias, void* dx, int64_t lddx, cudaStream_t s);
 
 }  // namespace mpgan
 
@@ -533,9 +535,9 @@ extern "C" int mpgan_bn_act_apply(int dtype, const void* x, int64_t ldx, int64_t
   MPGAN_REQUIRE(pixels > 0 && c > 0 && ldx >= c && ldy >= c, MPGAN_ERR_SHAPE, "bn_act_apply: bad shape");
   MPGAN_REQUIRE((scale == nullptr) == (shift == nullptr), MPGAN_ERR_SHAPE, "scale/shift must both be given");
   MPGAN_REQUIRE(act != MPGAN_ACT_PRELU || alpha, MPGAN_ERR_SHAPE, "PReLU needs alpha");
-  if (!res && !alpha && bn_stream_ok(dtype, x, y, nullptr, ldx, ldy, 0, pixels, c, act))   // large contiguous bf16
+  if (bn_stream_ok(dtype, x, res, y, ldx, ldres, ldy, pixels, c, act))   // contiguous bf16: bulk-copy streaming kernel
     return bn_stream_fwd(x, pixels, c, scale, shift, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr,
-                         nullptr, nullptr, nullptr, act, leaky_slope, y, (cudaStream_t)stream);
+                         nullptr, nullptr, nullptr, act, alpha, leaky_slope, res, y, ldy, (cudaStream_t)stream);
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(y, ldy, dtype) && vec_ok(res, res ? ldres : 8, dtype);
   BnTrain f;
   memset(&f, 0, sizeof(f));
@@ -552,9 +554,10 @@ extern "C" int mpgan_bn_train_apply(int dtype, const void* x, int64_t ldx, int64
   MPGAN_REQUIRE(pixels > 0 && c > 0 && ldx >= c && ldy >= c, MPGAN_ERR_SHAPE, "bn_train_apply: bad shape");
   MPGAN_REQUIRE(stats && scale && shift, MPGAN_ERR_SHAPE, "bn_train_apply: stats, scale and shift are required");
   MPGAN_REQUIRE(act != MPGAN_ACT_PRELU || alpha, MPGAN_ERR_SHAPE, "PReLU needs alpha");
-  if (!res && !alpha && bn_stream_ok(dtype, x, y, nullptr, ldx, ldy, 0, pixels, c, act))   // large contiguous bf16
+  if (bn_stream_ok(dtype, x, res, y, ldx, ldres, ldy, pixels, c, act))   // contiguous bf16: bulk-copy streaming kernel
     return bn_stream_fwd(x, pixels, c, nullptr, nullptr, stats, gamma, beta, eps, momentum, running_mean, running_var,
-                         num_batches_tracked, mean, invstd, scale, shift, act, leaky_slope, y, (cudaStream_t)stream);
+                         num_batches_tracked, mean, invstd, scale, shift, act, alpha, leaky_slope, res, y, ldy,
+                         (cudaStream_t)stream);
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(y, ldy, dtype) && vec_ok(res, res ? ldres : 8, dtype);
   BnTrain f;
   f.stats = stats; f.gamma = gamma; f.beta = beta; f.eps = eps; f.momentum = momentum;
@@ -569,8 +572,9 @@ extern "C" int mpgan_bn_act_bwd_reduce(int dtype, const void* dy, int64_t lddy, 
                                        const float* scale, const float* shift, int act, const float* alpha,
                                        float leaky_slope, double* sums, void* stream) {
   MPGAN_REQUIRE(pixels > 0 && c > 0 && ldx >= c && lddy >= c && sums, MPGAN_ERR_SHAPE, "bn_act_bwd_reduce: bad shape");
-  if (!alpha && bn_stream_ok(dtype, dy, x, nullptr, lddy, ldx, 0, pixels, c, act))   // large contiguous bf16
-    return bn_stream_reduce(dy, x, pixels, c, mean, invstd, scale, shift, act, leaky_slope, sums, (cudaStream_t)stream);
+  if (bn_stream_ok(dtype, dy, x, nullptr, lddy, ldx, 0, pixels, c, act))   // contiguous bf16: bulk-copy streaming kernel
+    return bn_stream_reduce(dy, x, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums,
+                            (cudaStream_t)stream);
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(dy, lddy, dtype);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     if (vec)  // 4 channels per thread: the per-channel constants fit in registers at 3 blocks per SM
@@ -592,9 +596,9 @@ extern "C" int mpgan_bn_act_bwd_apply(int dtype, const void* dy, int64_t lddy, c
   MPGAN_REQUIRE(pixels > 0 && c > 0 && ldx >= c && lddy >= c && lddx >= c && sums, MPGAN_ERR_SHAPE,
                 "bn_act_bwd_apply: bad shape");
   MPGAN_REQUIRE((mean == nullptr) == (invstd == nullptr), MPGAN_ERR_SHAPE, "mean/invstd must both be given");
-  if (!alpha && bn_stream_ok(dtype, dy, x, dx, lddy, ldx, lddx, pixels, c, act))   // large contiguous bf16
-    return bn_stream_bwd(dy, x, pixels, c, mean, invstd, scale, shift, act, leaky_slope, sums, dgamma, dbeta, dbias, dx,
-                         (cudaStream_t)stream);
+  if (bn_stream_ok(dtype, dy, x, dx, lddy, ldx, lddx, pixels, c, act))   // contiguous bf16: bulk-copy streaming kernel
+    return bn_stream_bwd(dy, x, pixels, c, mean, invstd, scale, shift, act, alpha, leaky_slope, sums, dgamma, dbeta,
+                         dalpha, dbias, dx, lddx, (cudaStream_t)stream);
   const bool vec = (c % 8 == 0) && vec_ok(x, ldx, dtype) && vec_ok(dy, lddy, dtype) && vec_ok(dx, lddx, dtype);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     if (vec)

@@ -63,6 +63,12 @@ struct StreamParams {
   // per-channel constants (fp32, length C each)
   const float* scale; const float* shift; const float* mean; const float* invstd;
   float slope;         // LeakyReLU slope; 1 = no activation
+  const float* alpha;  // device slope (PReLU, or LeakyReLU with a learnable slope); overrides `slope`
+  int prelu;           // accumulate / apply the PReLU slope gradient
+  int has_res;         // forward: in1 is a residual added after the activation
+  int64_t ldo;         // output pixel stride in elements (>= C)
+  int log2cv;
+  float* dalpha;
   int64_t P;
   // reduce mode
   double* sums;        // [2C + 1]
@@ -89,9 +95,11 @@ bn_stream_kernel(const StreamParams p) {
   uint64_t* empty = full + kMaxStages;
   float* s_coef = reinterpret_cast<float*>(empty + kMaxStages);     // [4][C]
   float* s_red = s_coef + 4 * p.C;                                  // [16 warps][...] reduction scratch
+  float* s_slope = s_red + kConsumers * 16;                         // [16 warps]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.C, cv = C >> 3;
+  const float slope = p.alpha ? *p.alpha : p.slope;
   const int64_t total_bytes = p.total * 2;
   const int64_t nchunks = (total_bytes + kChunkBytes - 1) / kChunkBytes;
 
@@ -151,6 +159,7 @@ bn_stream_kernel(const StreamParams p) {
         if (p.dgamma) p.dgamma[c] += (float)p.sums_in[C + c];
       }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.dalpha && p.prelu) *p.dalpha += (float)p.sums_in[2 * C];
   }
   __syncthreads();
 
@@ -188,6 +197,7 @@ bn_stream_kernel(const StreamParams p) {
       }
     }
     float2 acc1[4], acc2[4];
+    float fs = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc1[j] = acc2[j] = make_float2(0.f, 0.f);
     int stage = 0;
@@ -207,11 +217,17 @@ bn_stream_kernel(const StreamParams p) {
           const uint32_t w0[4] = {u0.x, u0.y, u0.z, u0.w};
           uint32_t o[4];
           if (MODE == MODE_FWD) {
+            uint32_t w1[4] = {0u, 0u, 0u, 0u};
+            if (p.has_res) {
+              const uint4 u1 = *reinterpret_cast<const uint4*>(src + kChunkBytes + (size_t)i * 16);
+              w1[0] = u1.x; w1[1] = u1.y; w1[2] = u1.z; w1[3] = u1.w;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 z = ffma2(unpack2(w0[j]), ka[j], kb[j]);
-              z.x = z.x > 0.f ? z.x : z.x * p.slope;
-              z.y = z.y > 0.f ? z.y : z.y * p.slope;
+              z.x = z.x > 0.f ? z.x : z.x * slope;
+              z.y = z.y > 0.f ? z.y : z.y * slope;
+              if (p.has_res) { const float2 r = unpack2(w1[j]); z.x += r.x; z.y += r.y; }
               o[j] = pack2(z);
             }
           } else {
@@ -221,9 +237,13 @@ bn_stream_kernel(const StreamParams p) {
             for (int j = 0; j < 4; ++j) {
               const float2 g = unpack2(w0[j]), x = unpack2(w1[j]);
               const float2 z = ffma2(x, ka[j], kb[j]);
-              const float2 f = agrad2(z, p.slope);
+              const float2 f = agrad2(z, slope);
               const float2 gz = make_float2(g.x * f.x, g.y * f.y);
               if (MODE == MODE_REDUCE) {
+                if (p.prelu) {
+                  fs = fmaf(g.x, fminf(z.x, 0.f), fs);
+                  fs = fmaf(g.y, fminf(z.y, 0.f), fs);
+                }
                 const float2 xh = ffma2(x, kc[j], kd[j]);
                 acc1[j].x += gz.x; acc1[j].y += gz.y;
                 acc2[j] = ffma2(gz, xh, acc2[j]);
@@ -237,9 +257,16 @@ bn_stream_kernel(const StreamParams p) {
               }
             }
           }
-          if (MODE != MODE_REDUCE)
-            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + off + (size_t)i * 16) =
-                make_uint4(o[0], o[1], o[2], o[3]);
+          if (MODE != MODE_REDUCE) {
+            bf16* dst;
+            if (p.ldo == C) {
+              dst = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(p.out) + off + (size_t)i * 16);
+            } else {  // channel slice of a wider (concat) buffer
+              const int64_t pix = (ch * kItems + i) >> p.log2cv;
+              dst = p.out + pix * p.ldo + cg * 8;
+            }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
         }
       }
       __syncwarp();
@@ -264,13 +291,22 @@ bn_stream_kernel(const StreamParams p) {
 #pragma unroll
           for (int i = 0; i < NV; ++i) s_red[(warp * cv + lane) * NV + i] = a[i];
         }
-      } else {   // cv == 64: lanes of a warp hold 32 different groups; two warps parities
+      } else {   // cv == 64: the 32 lanes of a warp hold 32 different groups
 #pragma unroll
         for (int i = 0; i < NV; ++i) s_red[t * NV + i] = a[i];
       }
     }
+    if (MODE == MODE_REDUCE && p.prelu) {
+      const float wsum = warp_sum(fs);
+      if (lane == 0) s_slope[warp] = wsum;
+    }
   }
   __syncthreads();
+  if (MODE == MODE_REDUCE && p.prelu && threadIdx.x == 0) {
+    double tsl = 0.0;
+    for (int w = 0; w < kConsumers / 32; ++w) tsl += (double)s_slope[w];
+    atomicAdd(&p.sums[2 * C], tsl);
+  }
   if (MODE == MODE_REDUCE || (MODE == MODE_BWD && p.dbias)) {
     constexpr int NV = MODE == MODE_REDUCE ? 16 : 8;
     const int nw = kConsumers / 32;
@@ -291,28 +327,29 @@ bn_stream_kernel(const StreamParams p) {
 
 }  // namespace bns
 
-// Whether the streaming kernels cover a call: bf16, contiguous (ld == C), 8 | C, C/8 divides 512 and 1024 items per
-// chunk (so a thread's channel group never changes), 16-byte aligned, no residual, large enough to be HBM bound,
-// no PReLU slope gradient (the discriminator uses LeakyReLU).
-bool bn_stream_ok(int dtype, const void* a, const void* b, const void* c, int64_t ld_a, int64_t ld_b, int64_t ld_c,
+// Whether the streaming kernels cover a call: bf16, inputs contiguous (ld == C), the output possibly a channel slice
+// (ld >= C), 8 | C with C/8 a power of two <= 64 (so a thread's channel group never changes), 16-byte aligned, and
+// not tiny.
+bool bn_stream_ok(int dtype, const void* in0, const void* in1, const void* out, int64_t ld0, int64_t ld1, int64_t ldo,
                   int64_t pixels, int32_t C, int act) {
   if (dtype != MPGAN_BF16) return false;
   if (C % 8 != 0 || C > 512) return false;
   const int cv = C / 8;
-  if ((512 % cv) != 0) return false;
-  if (ld_a != C || (b && ld_b != C) || (c && ld_c != C)) return false;
-  if (((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)c & 15)) return false;
-  if (act == MPGAN_ACT_PRELU || act == MPGAN_ACT_TANH) return false;
+  if ((cv & (cv - 1)) != 0) return false;
+  if (ld0 != C || (in1 && ld1 != C)) return false;
+  if (out && (ldo < C || ldo % 8 != 0)) return false;
+  if (((uintptr_t)in0 & 15) || ((uintptr_t)in1 & 15) || ((uintptr_t)out & 15)) return false;
+  if (act == MPGAN_ACT_TANH) return false;
   static int64_t min_bytes = -1;
   if (min_bytes < 0) {
     const char* e = getenv("MPGAN_BN_STREAM_MIN_MB");
-    min_bytes = (e ? atoll(e) : 48) << 20;
+    min_bytes = (e ? atoll(e) : 2) << 20;
   }
   return pixels * C * 2 >= min_bytes;
 }
 
 static size_t stream_smem(int C, int nin, int* stages) {
-  const size_t fixed = 128 + 2 * bns::kMaxStages * 8 + (size_t)4 * C * 4 + (size_t)bns::kConsumers * 16 * 4 + 256;
+  const size_t fixed = 128 + 2 * bns::kMaxStages * 8 + (size_t)4 * C * 4 + (size_t)bns::kConsumers * 16 * 4 + 64 + 256;
   int s = (int)((227 * 1024 - fixed) / ((size_t)nin * bns::kChunkBytes));
   if (s > bns::kMaxStages) s = bns::kMaxStages;
   *stages = s;
@@ -337,39 +374,51 @@ static int launch_stream(bns::StreamParams& p, cudaStream_t s) {
   return 0;
 }
 
+static int ilog2i(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
 int bn_stream_fwd(const void* x, int64_t pixels, int32_t C, const float* scale, const float* shift,
                   const double* stats, const float* gamma, const float* beta, float eps, float momentum,
                   float* running_mean, float* running_var, int64_t* nbt, float* mean, float* invstd, float* scale_out,
-                  float* shift_out, int act, float slope, void* y, cudaStream_t s) {
+                  float* shift_out, int act, const float* alpha, float slope, const void* res, void* y, int64_t ldy,
+                  cudaStream_t s) {
   bns::StreamParams p;
   memset(&p, 0, sizeof(p));
-  p.in0 = (const bf16*)x; p.out = (bf16*)y; p.total = pixels * C; p.C = C; p.nin = 1; p.P = pixels;
+  p.in0 = (const bf16*)x; p.in1 = (const bf16*)res; p.out = (bf16*)y; p.total = pixels * C; p.C = C;
+  p.nin = res ? 2 : 1; p.has_res = res ? 1 : 0; p.P = pixels; p.ldo = ldy; p.log2cv = ilog2i(C / 8);
   p.scale = scale; p.shift = shift; p.stats = stats; p.gamma = gamma; p.beta = beta; p.eps = eps; p.momentum = momentum;
   p.running_mean = running_mean; p.running_var = running_var; p.nbt = (long long*)nbt;
   p.mean_out = mean; p.invstd_out = invstd; p.scale_out = scale_out; p.shift_out = shift_out;
   p.slope = act == MPGAN_ACT_NONE ? 1.f : slope;
+  p.alpha = act == MPGAN_ACT_NONE ? nullptr : alpha;
   return launch_stream<bns::MODE_FWD>(p, s);
 }
 
 int bn_stream_reduce(const void* dy, const void* x, int64_t pixels, int32_t C, const float* mean, const float* invstd,
-                     const float* scale, const float* shift, int act, float slope, double* sums, cudaStream_t s) {
+                     const float* scale, const float* shift, int act, const float* alpha, float slope, double* sums,
+                     cudaStream_t s) {
   bns::StreamParams p;
   memset(&p, 0, sizeof(p));
   p.in0 = (const bf16*)dy; p.in1 = (const bf16*)x; p.total = pixels * C; p.C = C; p.nin = 2; p.P = pixels;
+  p.ldo = C; p.log2cv = ilog2i(C / 8);
   p.mean = mean; p.invstd = invstd; p.scale = scale; p.shift = shift; p.sums = sums;
   p.slope = act == MPGAN_ACT_NONE ? 1.f : slope;
+  p.alpha = act == MPGAN_ACT_NONE ? nullptr : alpha;
+  p.prelu = act == MPGAN_ACT_PRELU ? 1 : 0;
   return launch_stream<bns::MODE_REDUCE>(p, s);
 }
 
 int bn_stream_bwd(const void* dy, const void* x, int64_t pixels, int32_t C, const float* mean, const float* invstd,
-                  const float* scale, const float* shift, int act, float slope, const double* sums, float* dgamma,
-                  float* dbeta, float* dbias, void* dx, cudaStream_t s) {
+                  const float* scale, const float* shift, int act, const float* alpha, float slope, const double* sums,
+                  float* dgamma, float* dbeta, float* dalpha, float* dbias, void* dx, int64_t lddx, cudaStream_t s) {
   bns::StreamParams p;
   memset(&p, 0, sizeof(p));
   p.in0 = (const bf16*)dy; p.in1 = (const bf16*)x; p.out = (bf16*)dx; p.total = pixels * C; p.C = C; p.nin = 2;
-  p.P = pixels; p.mean = mean; p.invstd = invstd; p.scale = scale; p.shift = shift; p.sums_in = sums;
-  p.dgamma = dgamma; p.dbeta = dbeta; p.dbias = dbias;
+  p.P = pixels; p.ldo = lddx; p.log2cv = ilog2i(C / 8);
+  p.mean = mean; p.invstd = invstd; p.scale = scale; p.shift = shift; p.sums_in = sums;
+  p.dgamma = dgamma; p.dbeta = dbeta; p.dalpha = dalpha; p.dbias = dbias;
   p.slope = act == MPGAN_ACT_NONE ? 1.f : slope;
+  p.alpha = act == MPGAN_ACT_NONE ? nullptr : alpha;
+  p.prelu = act == MPGAN_ACT_PRELU ? 1 : 0;
   return launch_stream<bns::MODE_BWD>(p, s);
 }
 

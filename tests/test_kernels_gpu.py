@@ -257,35 +257,49 @@ def test_bn_act_forward_backward(c, act, dtype, fused):
         assert rel_l2(da, alpha.grad) <= 1e-4
 
 
-@pytest.mark.parametrize("n,c,h,w_", [(3, 64, 384, 384), (2, 256, 256, 256), (1, 128, 451, 443)])
-def test_bn_streaming_kernels_large_bf16(n, c, h, w_):
-    """Tensors >= 48 MB (contiguous bf16, LeakyReLU) take the bulk-copy streaming kernels of bn_stream.cu; the last
-    shape ends in a partial 16 KB chunk."""
+@pytest.mark.parametrize("n,c,h,w_,act,with_res", [(3, 64, 384, 384, ACT_LEAKY, False), (2, 256, 256, 256, ACT_LEAKY, False),
+                                                   (1, 128, 451, 443, ACT_LEAKY, False), (4, 16, 128, 128, ACT_PRELU, True),
+                                                   (9, 32, 67, 64, ACT_PRELU, False), (2, 512, 64, 64, ACT_NONE, True)])
+def test_bn_streaming_kernels_bf16(n, c, h, w_, act, with_res):
+    """Contiguous bf16 tensors >= 2 MB take the bulk-copy streaming kernels of bn_stream.cu (LeakyReLU / PReLU with its
+    slope gradient / none; residual input; output written into a channel slice of a wider buffer; partial last chunk)."""
     x = (rnd(n, c, h, w_, seed=51) * 2 + 0.3).bfloat16().float().requires_grad_(True)
     dy = rnd(n, c, h, w_, seed=52).bfloat16().float()
+    res = rnd(n, c, h, w_, seed=55).bfloat16().float() if with_res else None
     bn = torch.nn.BatchNorm2d(c).to(DEV)
     with torch.no_grad():
         bn.weight.copy_(rnd(c, seed=53) + 1.5), bn.bias.copy_(rnd(c, seed=54))
     bn_k = torch.nn.BatchNorm2d(c).to(DEV)
     bn_k.load_state_dict(bn.state_dict())
-    yr = F.leaky_relu(bn(x), 0.2)
+    alpha = torch.nn.Parameter(torch.tensor([0.25], device=DEV))
+    z = bn(x)
+    yr = F.prelu(z, alpha) if act == ACT_PRELU else (F.leaky_relu(z, 0.2) if act == ACT_LEAKY else z)
+    if with_res:
+        yr = yr + res
     yr.backward(dy)
     xc = cl(x.detach(), torch.bfloat16)
-    assert xc.numel() * 2 >= 48 << 20
+    assert xc.numel() * 2 >= 2 << 20
     stats = torch.zeros(2 * c, dtype=torch.float64, device=DEV)
     ops.bn_stats(xc, stats)
     buf = torch.empty(4, c, device=DEV)
-    y = ops.bn_train_apply(xc, stats, bn_k, buf, ACT_LEAKY, None, 0.2, None, torch.empty_like(xc))
+    a = alpha.detach() if act == ACT_PRELU else None
+    resc = cl(res, torch.bfloat16) if with_res else None
+    wide = torch.zeros(n, h, w_, c + 16, dtype=torch.bfloat16, device=DEV)   # concat buffer: write into [..., 8:8+c]
+    y = ops.bn_train_apply(xc, stats, bn_k, buf, act, a, 0.2, resc, wide[..., 8:8 + c])
     assert rel_l2(uncl(y), yr) <= 8e-3
+    assert float(wide[..., :8].abs().max()) == 0 and float(wide[..., 8 + c:].abs().max()) == 0
     assert rel_l2(bn_k.running_mean, bn.running_mean) <= 1e-5 and rel_l2(bn_k.running_var, bn.running_var) <= 1e-5
-    y2 = ops.bn_act_apply(xc, buf[2], buf[3], ACT_LEAKY, None, 0.2, None, torch.empty_like(xc))
-    assert torch.equal(y, y2)
+    y2 = ops.bn_act_apply(xc, buf[2], buf[3], act, a, 0.2, resc, torch.empty_like(xc))
+    assert torch.equal(y.contiguous(), y2)
     sums = torch.zeros(2 * c + 1, dtype=torch.float64, device=DEV)
     dg, db, dbias = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
-    dx = ops.bn_act_bwd(cl(dy, torch.bfloat16), xc, buf[0], buf[1], buf[2], buf[3], ACT_LEAKY, None, 0.2, sums, dg, db,
-                        None, torch.empty_like(xc), dbias=dbias)
+    da = torch.zeros(1, device=DEV)
+    dx = ops.bn_act_bwd(cl(dy, torch.bfloat16), xc, buf[0], buf[1], buf[2], buf[3], act, a, 0.2, sums, dg, db,
+                        da if act == ACT_PRELU else None, torch.empty_like(xc), dbias=dbias)
     assert rel_l2(uncl(dx), x.grad) <= 1e-2
     assert rel_l2(dg, bn.weight.grad) <= 1e-4 and rel_l2(db, bn.bias.grad) <= 1e-4
+    if act == ACT_PRELU:
+        assert rel_l2(da, alpha.grad) <= 1e-4
     assert torch.allclose(dbias, dx.float().sum(dim=(0, 1, 2)), rtol=1e-3, atol=1e-3 * float(dx.float().abs().max()))
 
 
