@@ -214,6 +214,121 @@ fprop_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__ w, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Run-based variant of fprop for C % 8 == 0: a thread owns 8 channels and walks RUN consecutive output
+// pixels of one row; the 3 x (RUN*S + 2) input window is loaded once per run, so the inner loop is 36 packed FMAs
+// per (pixel, 8 channels) plus one 16-byte access -- the per-pixel index arithmetic and tap predicates of the
+// pixel-at-a-time kernels (which made them instruction-issue bound at ~5x the FMA floor) are amortised over the run.
+// ------------------------------------------------------------------------------------------------------------
+template <int S> struct RunOf { static constexpr int RUN = S == 1 ? 8 : 4; static constexpr int WIN = (RUN - 1) * S + 3; };
+
+template <typename T, int S>
+__device__ __forceinline__ void load_window(const Geom& g, const T* __restrict__ x, int ldx, int img, int h, int w0,
+                                            float (&xv)[3][RunOf<S>::WIN]) {
+  constexpr int WIN = RunOf<S>::WIN;
+  const int ih0 = h * S - g.pad, iw0 = w0 * S - g.pad;
+  const T* xi = x + img * (g.xh * g.xw) * ldx;
+#pragma unroll
+  for (int rh = 0; rh < 3; ++rh) {
+    const int ih = ih0 + rh;
+    const bool okh = (unsigned)ih < (unsigned)g.xh;
+    const T* xr = xi + (ih * g.xw + iw0) * ldx;
+#pragma unroll
+    for (int j = 0; j < WIN; ++j)
+      xv[rh][j] = (okh && (unsigned)(iw0 + j) < (unsigned)g.xw) ? to_f(xr[j * ldx]) : 0.f;
+  }
+}
+
+template <typename T, int S>
+__global__ void __launch_bounds__(kThreads, 1)
+fprop_run_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__ w, const float* __restrict__ bias,
+                 T* __restrict__ y, int ldy, double* __restrict__ stats) {
+  pdl_wait();
+  pdl_launch();
+  constexpr int RUN = RunOf<S>::RUN, WIN = RunOf<S>::WIN;
+  __shared__ double sm[(kThreads / 32) * 32 * 16];
+  const int cv = g.C / 8;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthr = gridDim.x * blockDim.x;
+  const int c0 = (tid % cv) * 8;
+  const int rpr = (g.yw + RUN - 1) / RUN;                  // runs per output row
+  const int nruns = g.n * g.yh * rpr;
+  const int rstep = nthr / cv;
+  float2 wr[kTaps][4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    b[j] = make_float2(bias ? bias[c0 + 2 * j] : 0.f, bias ? bias[c0 + 2 * j + 1] : 0.f);
+#pragma unroll
+    for (int t = 0; t < kTaps; ++t)
+      wr[t][j] = make_float2(to_f(w[(c0 + 2 * j) * kTaps + t]), to_f(w[(c0 + 2 * j + 1) * kTaps + t]));
+  }
+  constexpr bool kExact = sizeof(T) == 4;   // fp32 storage: flush the fp32 statistics partials into fp64 every run
+  float2 s1[4], s2[4];
+  double d1[kExact ? 8 : 1], d2[kExact ? 8 : 1];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s1[j] = s2[j] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (kExact ? 8 : 1); ++e) d1[e] = d2[e] = 0.0;
+  for (int run = tid / cv; run < nruns; run += rstep) {
+    const int rw = run % rpr;
+    const int rr = run / rpr;
+    const int h = rr % g.yh, img = rr / g.yh;
+    const int w0 = rw * RUN;
+    float xv[3][WIN];
+    load_window<T, S>(g, x, ldx, img, h, w0, xv);
+    T* yrow = y + ((img * g.yh + h) * g.yw + w0) * ldy + c0;
+#pragma unroll
+    for (int i = 0; i < RUN; ++i) {
+      float2 o2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 a = b[j];
+#pragma unroll
+        for (int rh = 0; rh < 3; ++rh)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) a = ffma2(make_float2(xv[rh][i * S + q], xv[rh][i * S + q]), wr[rh * 3 + q][j], a);
+        o2[j] = a;
+      }
+      if (w0 + i < g.yw) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (e & 1) ? o2[e / 2].y : o2[e / 2].x;
+        IO<T, 8>::store(yrow + i * ldy, o);
+        if (stats) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {   // statistics of the values as stored
+            const float2 f = make_float2(to_f(from_f<T>(o2[j].x)), to_f(from_f<T>(o2[j].y)));
+            s1[j].x += f.x; s1[j].y += f.y;
+            s2[j] = ffma2(f, f, s2[j]);
+          }
+        }
+      }
+    }
+    if (kExact && stats) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        d1[kExact ? e : 0] += (double)((e & 1) ? s1[e / 2].y : s1[e / 2].x);
+        d2[kExact ? e : 0] += (double)((e & 1) ? s2[e / 2].y : s2[e / 2].x);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s1[j] = s2[j] = make_float2(0.f, 0.f);
+    }
+  }
+  if (stats) {
+    double a[16];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      a[e] = (double)((e & 1) ? s1[e / 2].y : s1[e / 2].x) + (kExact ? d1[kExact ? e : 0] : 0.0);
+      a[8 + e] = (double)((e & 1) ? s2[e / 2].y : s2[e / 2].x) + (kExact ? d2[kExact ? e : 0] : 0.0);
+    }
+    group_reduce<double, 16>(a, cv, sm);
+    for (int j = threadIdx.x; j < cv * 16; j += kThreads) {
+      const int gq = j / 16, i = j - gq * 16;
+      atomicAdd(&stats[(i / 8) * g.C + gq * 8 + (i % 8)], group_total(sm, cv, 16, j));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // bprop: x[q] = bias + sum_t sum_c y[(q + pad - t)/s][c] * w[c][t]            (cx == 1; cv = C/V lanes per pixel)
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, int V, int S>
@@ -515,6 +630,17 @@ int c1f_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, con
   if (cv > 32 && (kThreads % cv) != 0) return 1;
   const int64_t P = (int64_t)q.n * q.yh * q.yw;
   if (!fits32(P, ldy) || !fits32((int64_t)q.n * q.xh * q.xw, ldx) || P * cv >= ((int64_t)1 << 30)) return 1;
+  if (V == 8 && q.s == 1 && cv <= 32 && (32 % cv) == 0) {   // run-based kernel (measured: a win for stride 1 only)
+    const int run = q.s == 1 ? 8 : 4;
+    const int64_t nruns = (int64_t)q.n * q.yh * ((q.yw + run - 1) / run);
+    const int gridr = grid_for(nruns, cv, 2, 4);
+    MPGAN_DISPATCH_DTYPE(dtype, T, {
+      if (q.s == 1) launch_k(fprop_run_kernel<T, 1>, gridr, kThreads, 0, s, q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y, (int)ldy, stats);
+      else launch_k(fprop_run_kernel<T, 2>, gridr, kThreads, 0, s, q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y, (int)ldy, stats);
+      MPGAN_CHECK_LAUNCH("c1f_fprop_run");
+      return 0;
+    });
+  }
   const int grid = grid_for(P, cv, 8, 8);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     C1F_LAUNCH(fprop_kernel, V, q.s, grid, 0, s, q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y,
@@ -565,8 +691,8 @@ int c1f_wgrad(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, con
   if (cv > 8 || (32 % cv) != 0) return 1;
   const int64_t P = (int64_t)q.n * q.yh * q.yw;
   if (!fits32(P, ldy) || !fits32((int64_t)q.n * q.xh * q.xw, ldx) || P * cv >= ((int64_t)1 << 30)) return 1;
-  const int grid = grid_for(P, cv, 32, 4);
   const size_t smem = (size_t)(kThreads / 32) * cv * kTaps * V * sizeof(float);
+  const int grid = grid_for(P, cv, 32, 4);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     C1F_LAUNCH(wgrad_kernel, V, q.s, grid, smem, s, q, (const T*)x, (int)ldx, (const T*)y, (int)ldy, dw);
     MPGAN_CHECK_LAUNCH("c1f_wgrad");
