@@ -80,9 +80,16 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
+def synthetic_batch(batch, dims, spatial, seed=1):
+    """SURVEY.md section 8d synthetic inputs: uniform [-1, 1], T1 then T2 from one seeded CPU generator."""
+    g = torch.Generator().manual_seed(seed)
+    shape = (batch, 1) + (spatial,) * dims
+    return {"t1w": torch.rand(shape, generator=g) * 2 - 1, "t2w": torch.rand(shape, generator=g) * 2 - 1}
+
+
 def cpu_reference_run(steps, warmup):
     """The reference path on the host cores: oracle two-optimizer step, batch 1, 256x256, fp32."""
-    from oracle.gan import GANOracle, lightning_step, synthetic_batch
+    from oracle.gan import GANOracle, lightning_step
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
@@ -153,7 +160,6 @@ def main():
     import torch.distributed as dist
     import mpgan
     from mpgan import _lib, ddp
-    from oracle.gan import synthetic_batch  # synthetic-input generator only (SURVEY.md section 8d seeds)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank, local = 0, 0
@@ -268,8 +274,19 @@ def main():
                                               f"({ms:.0f} ms/step)"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Leave without tearing the NCCL communicator down: destroy_process_group() blocks while a CUDA graph that
+        # captured collectives of that communicator is alive (observed: a 2-GPU run printed its line and then hung).
+        # The watchdog bounds the exit even if a peer died.
+        sys.stdout.flush()
+        watchdog = threading.Timer(60.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        graph = None
+        model._graph = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -78,13 +78,17 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxAcc);
   float* s_stats = reinterpret_cast<float*>(aux + kHaloAux);   // [8 epilogue warps][2*N]
   uint32_t* s_tr = reinterpret_cast<uint32_t*>(s_stats + 8 * 2 * N);   // [8 epilogue warps][32][kTrW] bf16x2
+  float* s_bias = reinterpret_cast<float*>(s_tr + 8 * 32 * kTrW);      // [N]
+  // N <= 32: the two epilogue warp groups take alternate tiles (4 arrivals free an accumulator);
+  // N >= 64: they take alternate 32-column chunks of every tile (8 arrivals)
+  constexpr uint32_t kEmptyArrivals = N <= 32 ? 4u : 8u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && elect_one()) prefetch_tmap(&tmA);
   if (threadIdx.x == 32) {
     for (int i = 0; i < kMaxBuf; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < kMaxAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < kMaxAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEmptyArrivals); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -105,6 +109,7 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
       off ^= ((off >> 7) & swz_mask) << 4;
       cp_async16(smem_u32(w_sm + blk + off), P.w + (size_t)g * 8);
     }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_bias[i] = P.bias ? __ldg(&P.bias[i]) : 0.f;
     cp_async_wait_all();
     fence_proxy_async();   // these generic-proxy writes are read by tcgen05.mma (async proxy)
   }
@@ -174,7 +179,73 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
     const int lh = row >> 3, lw = row & 7;
     uint32_t* tr = s_tr + ew * 32 * kTrW;
     float* sl = s_stats + ew * 2 * N;
-    constexpr int CH = N >= 64 ? 32 : 16;
+    constexpr int CH = N >= 32 ? 32 : 16;
+    if constexpr (N <= 64) {
+      // Small layers: minimal per-tile chain -- one TMEM load, the accumulator is handed back to the MMA warp as soon
+      // as the values are in registers, and the BatchNorm statistics are plain per-thread register accumulators
+      // (thread = tile row, fixed tile order => reproducible) that are transposed and reduced ONCE, after the last tile.
+      constexpr int NCH = N / CH;                 // 1 (N = 16, 32) or 2 (N = 64)
+      const int c0 = NCH == 2 ? half * CH : 0;
+      float s1[CH], s2[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        if (NCH == 1 && (it & 1) != half) continue;
+        const int img = tile / tiles_per_img;
+        const int trm = tile - img * tiles_per_img;
+        const int thi = trm / P.tiles_w, twi = trm - thi * P.tiles_w;
+        const int oh = thi * HT_H + lh, ow = twi * HT_W + lw;
+        const bool valid = oh < P.oh && ow < P.ow;
+        bf16* orow = P.out + (long long)img * P.out_sn + (long long)oh * P.out_sh + (long long)ow * P.out_sw + c0;
+        const int acc = it % NACC;
+        const uint32_t par = (uint32_t)(it / NACC) & 1u;
+        mbar_wait(&tfull[acc], par);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N + c0);
+        uint32_t r[CH];
+        if (CH == 32) tmem_ld_32x32(t_addr, r);
+        else tmem_ld_32x16(t_addr, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        const float m = valid ? 1.f : 0.f;
+        uint32_t packed[CH / 2];
+#pragma unroll
+        for (int j = 0; j < CH / 4; ++j) {
+          const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j);
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r[4 * j]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w);
+          packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+          packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < CH / 8; ++j)
+            *reinterpret_cast<uint4*>(orow + j * 8) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+        if (P.stats) {  // statistics of the values as stored
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) {
+            const float fa = __uint_as_float(packed[j] << 16) * m, fb = __uint_as_float(packed[j] & 0xffff0000u) * m;
+            s1[2 * j] += fa; s1[2 * j + 1] += fb;
+            s2[2 * j] = fmaf(fa, fa, s2[2 * j]); s2[2 * j + 1] = fmaf(fb, fb, s2[2 * j + 1]);
+          }
+        }
+      }
+      if (P.stats) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = j < CH ? s1[j] : 0.f;
+        const float t1 = warp_transpose_reduce32(v, lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = j < CH ? s2[j] : 0.f;
+        const float t2 = warp_transpose_reduce32(v, lane);
+        if (lane < CH) { sl[c0 + lane] = t1; sl[N + c0 + lane] = t2; }
+      }
+    } else {
     int it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int img = tile / tiles_per_img;
@@ -198,7 +269,7 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
 #pragma unroll
         for (int j = 0; j < CH / 2; ++j) {
           float f0 = __uint_as_float(r[2 * j]), f1 = __uint_as_float(r[2 * j + 1]);
-          if (P.bias) { f0 += __ldg(&P.bias[c0 + 2 * j]); f1 += __ldg(&P.bias[c0 + 2 * j + 1]); }
+          f0 += s_bias[c0 + 2 * j]; f1 += s_bias[c0 + 2 * j + 1];
           __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
           packed[j] = *reinterpret_cast<uint32_t*>(&h);
         }
@@ -237,6 +308,7 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
     }
   }
   __syncwarp();
@@ -281,7 +353,7 @@ static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, in
   const int KC = C < 64 ? C : 64;
   const size_t w_bytes = ((size_t)9 * C * N * 2 + 1023) & ~(size_t)1023;
   const size_t a_bytes = ((size_t)HPIX * KC * 2 + 1023) & ~(size_t)1023;   // one <= 64-channel plane
-  const size_t aux = kHaloAux + (size_t)8 * 2 * N * 4 + (size_t)8 * 32 * kTrW * 4;   // barriers, stats slots, transpose scratch
+  const size_t aux = kHaloAux + (size_t)8 * 2 * N * 4 + (size_t)8 * 32 * kTrW * 4 + (size_t)N * 4;   // barriers, stats slots, transpose scratch, bias
   const size_t budget = 227 * 1024 - 1024;
   if (w_bytes + 2 * a_bytes + aux > budget) return 1;
   int nbuf = (int)((budget - w_bytes - aux) / a_bytes);

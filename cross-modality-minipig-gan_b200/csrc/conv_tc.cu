@@ -67,18 +67,33 @@ template <> struct SwizzleOf<64> { static constexpr uint32_t layout = 2, sbo = 1
 template <> struct SwizzleOf<32> { static constexpr uint32_t layout = 4, sbo = 512; };
 template <> struct SwizzleOf<16> { static constexpr uint32_t layout = 6, sbo = 256; };
 
+// Epilogue organisation.  BN <= 64 (generator layers: few MMAs per tile, so the per-tile latency chain of the
+// epilogue is the bottleneck): 8 epilogue warps in two groups -- alternate tiles (BN <= 32) or alternate 32-column
+// chunks (BN = 64) --, up to 8 TMEM accumulators in flight, BatchNorm statistics in per-thread registers.
+// BN >= 128 (discriminator layers, MMA bound): 4 epilogue warps, double-buffered accumulator.
+template <int BN> struct EpiCfg {
+  static constexpr bool REG = BN <= 64;
+  static constexpr int EW = REG ? 8 : 4;                       // epilogue warps
+  static constexpr int THREADS = 128 + 32 * EW;
+  static constexpr int NACC = REG ? (512 / BN > 8 ? 8 : 512 / BN) : 2;
+  static constexpr int CH = BN >= 32 ? 32 : 16;                // columns per tcgen05.ld
+  static constexpr int NCH = BN / CH;
+  static constexpr uint32_t ARRIVALS = REG ? (NCH == 1 ? 4u : 8u) : 4u;
+};
+
 template <int BN, int KC> struct TapCfg {
   static constexpr int A_BYTES = 128 * KC * 2;
   static constexpr int B_TX = BN * KC * 2;
   static constexpr int B_BYTES = B_TX < 1024 ? 1024 : B_TX;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_BYTES = 1024;  // full/empty[<=32] + tfull/tempty[2] + tmem slot
-  static constexpr int AUX_BYTES = BAR_BYTES + 4 * 2 * 512 * 4;  // barriers + per-epilogue-warp stats[2*n_total<=1024 floats]
+  static constexpr int BAR_BYTES = 1024;  // full/empty[<=32] + tfull/tempty[<=8] + tmem slot
+  static constexpr int STAT_BYTES = EpiCfg<BN>::EW * 2 * 512 * 4;   // per-epilogue-warp stats[2*n_total<=1024 floats]
+  static constexpr int AUX_BYTES = BAR_BYTES + STAT_BYTES + 512 * 4;  // barriers + stats slots + bias[n_total<=512]
   static constexpr int MAX_STAGES = (kSmemLimit - 1024 - AUX_BYTES) / STAGE_BYTES;
   // small-channel layers are TMA-latency bound: keep up to 32 stages (>= 3 tiles of a 3x3 layer) in flight
   static constexpr int STAGES = MAX_STAGES > 32 ? 32 : MAX_STAGES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + AUX_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int TMEM_COLS = EpiCfg<BN>::NACC * BN < 32 ? 32 : EpiCfg<BN>::NACC * BN;
   static_assert(STAGES >= 2, "pipeline too shallow");
 };
 
@@ -105,20 +120,23 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
 }
 
 template <int BN, int KC>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(EpiCfg<BN>::THREADS, 1)
 tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB) {
   using Cfg = TapCfg<BN, KC>;
+  using Epi = EpiCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NACC = Epi::NACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tempty = tfull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 8);
   float* s_stats = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+  float* s_bias = s_stats + Epi::EW * 2 * 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const CUtensorMap* mapsA[4] = {&tmA0, &tmA1, &tmA2, &tmA3};
@@ -129,17 +147,18 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], Epi::ARRIVALS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < 4 * 2 * P.n_total; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < Epi::EW * 2 * P.n_total; i += blockDim.x) s_stats[i] = 0.f;
+  pdl_wait();      // PDL: barrier init / TMEM allocation / descriptor prefetch above overlap the previous kernel
+  pdl_launch();
+  for (int i = threadIdx.x; i < P.n_total; i += blockDim.x) s_bias[i] = P.bias ? __ldg(&P.bias[i]) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();      // PDL: barrier init / TMEM allocation / descriptor prefetch above overlap the previous kernel
-  pdl_launch();
 
   const int tn_log2 = 7 - P.tw_log2 - P.th_log2;
   const int per_cls = P.tiles_n * P.tiles_h * P.tiles_w * P.n_tiles;
@@ -180,8 +199,8 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int cls = tile / per_cls;
-        const int buf = it & 1;
-        const uint32_t par = (uint32_t)(it >> 1) & 1u;
+        const int buf = it % NACC;
+        const uint32_t par = (uint32_t)(it / NACC) & 1u;
         mbar_wait(&tempty[buf], par ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
@@ -204,10 +223,90 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {  // ================= epilogue =================
-    const int q = warp - 4;
+    const int ew = warp - 4;
+    const int q = ew & 3;           // TMEM lane quarter (== warp % 4)
+    const int half = ew >> 2;       // second warp group (BN <= 64 only)
     const int row = q * 32 + lane;
     const int tw_mask = (1 << P.tw_log2) - 1, th_mask = (1 << P.th_log2) - 1;
     const int lw = row & tw_mask, lh = (row >> P.tw_log2) & th_mask, ln = row >> (P.tw_log2 + P.th_log2);
+    constexpr int CH = Epi::CH;
+    float* sl = s_stats + ew * 2 * P.n_total;
+    if constexpr (Epi::REG) {
+      constexpr int NCH = Epi::NCH;               // 1 (BN = 16, 32) or 2 (BN = 64)
+      const int c0 = NCH == 2 ? half * CH : 0;
+      float s1[CH], s2[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      int stat_base = -1;                         // channel block the register statistics belong to
+      auto flush = [&]() {                        // once per kernel unless the layer has several BN-column blocks
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = j < CH ? s1[j] : 0.f;
+        const float t1 = warp_transpose_reduce32(v, lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = j < CH ? s2[j] : 0.f;
+        const float t2 = warp_transpose_reduce32(v, lane);
+        if (lane < CH) { sl[stat_base + c0 + lane] += t1; sl[P.n_total + stat_base + c0 + lane] += t2; }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      };
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        if (NCH == 1 && (it & 1) != half) continue;
+        int t = tile;
+        const int nt = t % P.n_tiles; t /= P.n_tiles;
+        const int twi = t % P.tiles_w; t /= P.tiles_w;
+        const int thi = t % P.tiles_h; t /= P.tiles_h;
+        const int tni = t % P.tiles_n; t /= P.tiles_n;
+        const int cls = t;
+        const int ow = (twi << P.tw_log2) + lw, oh = (thi << P.th_log2) + lh, img = (tni << tn_log2) + ln;
+        const bool valid = img < P.nimg && oh < P.cls_oh[cls] && ow < P.cls_ow[cls];
+        const int nbase = nt * BN;
+        bf16* orow = P.out + P.cls_out_off[cls] + (long long)img * P.out_sn + (long long)oh * P.out_sh +
+                     (long long)ow * P.out_sw + nbase + c0;
+        if (P.stats && nbase != stat_base) {
+          if (stat_base >= 0) flush();
+          stat_base = nbase;
+        }
+        const int buf = it % NACC;
+        const uint32_t par = (uint32_t)(it / NACC) & 1u;
+        mbar_wait(&tfull[buf], par);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
+        uint32_t r[CH];
+        if (CH == 32) tmem_ld_32x32(t_addr, r);
+        else tmem_ld_32x16(t_addr, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);   // values are in registers: the accumulator is free again
+        const float m = valid ? 1.f : 0.f;
+        uint32_t packed[CH / 2];
+#pragma unroll
+        for (int j = 0; j < CH / 4; ++j) {
+          const float4 bv = *reinterpret_cast<const float4*>(s_bias + nbase + c0 + 4 * j);
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r[4 * j]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
+          packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+          packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < CH / 8; ++j)
+            *reinterpret_cast<uint4*>(orow + j * 8) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+        if (P.stats) {  // statistics of the values as stored
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) {
+            const float fa = __uint_as_float(packed[j] << 16) * m, fb = __uint_as_float(packed[j] & 0xffff0000u) * m;
+            s1[2 * j] += fa; s1[2 * j + 1] += fb;
+            s2[2 * j] = fmaf(fa, fa, s2[2 * j]); s2[2 * j + 1] = fmaf(fb, fb, s2[2 * j + 1]);
+          }
+        }
+      }
+      if (P.stats && stat_base >= 0) flush();
+    } else {
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int t = tile;
@@ -221,12 +320,11 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
       const int nbase = nt * BN;
       bf16* orow = P.out + P.cls_out_off[cls] + (long long)img * P.out_sn + (long long)oh * P.out_sh +
                    (long long)ow * P.out_sw + nbase;
-      const int buf = it & 1;
-      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      const int buf = it % NACC;
+      const uint32_t par = (uint32_t)(it / NACC) & 1u;
       mbar_wait(&tfull[buf], par);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         uint32_t r[32];
@@ -235,11 +333,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          float f = __uint_as_float(r[j]);
-          if (P.bias) f += __ldg(&P.bias[nbase + c0 + j]);
-          v[j] = f;
-        }
+        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + s_bias[nbase + c0 + j];
         uint32_t packed[CH / 2];
 #pragma unroll
         for (int j = 0; j < CH / 2; ++j) {
@@ -267,7 +361,6 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
           float s1 = warp_transpose_reduce32(v, lane);
           float s2 = warp_transpose_reduce32(sq, lane);
           if (lane < CH) {  // slot owned by (this warp, this lane): fixed accumulation order, run-to-run reproducible
-            float* sl = s_stats + q * 2 * P.n_total;
             sl[nbase + c0 + lane] += s1;
             sl[P.n_total + nbase + c0 + lane] += s2;
           }
@@ -277,14 +370,16 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
+    }
   }
   __syncwarp();
   tc_fence_before();
   __syncthreads();
   if (P.stats) {
     for (int i = threadIdx.x; i < 2 * P.n_total; i += blockDim.x) {
-      const double s = ((double)s_stats[i] + (double)s_stats[2 * P.n_total + i]) +
-                       ((double)s_stats[4 * P.n_total + i] + (double)s_stats[6 * P.n_total + i]);
+      double s = 0.0;
+#pragma unroll
+      for (int e = 0; e < Epi::EW; ++e) s += (double)s_stats[e * 2 * P.n_total + i];
       if (s != 0.0) atomicAdd(&P.stats[i], s);
     }
   }
@@ -572,7 +667,7 @@ static int launch_tapgemm_t(const TapGemmParams& P, const CUtensorMap* mA, const
   }
   const long long total = (long long)P.ncls * P.tiles_n * P.tiles_h * P.tiles_w * P.n_tiles;
   int grid = (int)(total < num_sms() ? total : num_sms());
-  launch_k(tapgemm_kernel<BN, KC>, grid, 256, Cfg::SMEM_BYTES, s, P, mA[0], mA[1], mA[2], mA[3], mB);
+  launch_k(tapgemm_kernel<BN, KC>, grid, EpiCfg<BN>::THREADS, Cfg::SMEM_BYTES, s, P, mA[0], mA[1], mA[2], mA[3], mB);
   MPGAN_CHECK_LAUNCH("tapgemm_kernel");
   return 0;
 }
