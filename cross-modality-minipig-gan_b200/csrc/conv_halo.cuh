@@ -51,7 +51,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int N>
+template <int N, int KC>   // KC = min(C, 64): channels per plane (one swizzle span)
 __global__ void __launch_bounds__(kHaloThreads, 1)
 halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUtensorMap tmA) {
   // accumulator ring: as many 128 x N fp32 tiles as fit in 512 TMEM columns (<= 8): small layers are bound by the
@@ -61,13 +61,12 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int C = P.C;
-  const int KC = C < 64 ? C : 64;                        // channels per plane (one swizzle span)
   const int nkc = C / KC;
-  const int rowb = KC * 2;                               // bytes per pixel row of a plane: 128 / 64 / 32
-  const int cpr = rowb >> 4;                             // 16-byte chunks per row
-  const uint32_t swz_mask = (uint32_t)(cpr - 1);         // Swizzle<log2(cpr),4,3>: chunk ^= (offset >> 7) & mask
+  constexpr int rowb = KC * 2;                           // bytes per pixel row of a plane: 128 / 64 / 32
+  constexpr int cpr = rowb >> 4;                         // 16-byte chunks per row
+  constexpr uint32_t swz_mask = (uint32_t)(cpr - 1);     // Swizzle<log2(cpr),4,3>: chunk ^= (offset >> 7) & mask
   const int w_bytes = 9 * C * N * 2;
-  const int a_bytes = (HPIX * rowb + 1023) & ~1023;      // one plane, padded to the swizzle period
+  constexpr int a_bytes = (HPIX * rowb + 1023) & ~1023;  // one plane, padded to the swizzle period
   uint8_t* w_sm = smem;
   uint8_t* a_sm = smem + ((w_bytes + 1023) & ~1023);
   uint8_t* aux = a_sm + P.nbuf * a_bytes;
@@ -138,37 +137,44 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     if (elect_one()) {  // ================= MMA issuer =================
-      const uint32_t w_addr = smem_u32(w_sm);
-      const uint32_t layout = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);   // SW128 / SW64 / SW32
-      const uint32_t sbo_a = HW * rowb, sbo_b = 8 * rowb;
-      const int ksteps = KC >> 4;
-      int it = 0, pi = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it % NACC;
-        const uint32_t tpar = (uint32_t)(it / NACC) & 1u;
+      // ONE thread issues every MMA of the CTA, so for small N (a 128 x 16 x 16 MMA occupies the tensor pipe for
+      // ~8 cycles) its scalar instruction stream is the critical path: descriptors are a precomputed 64-bit base plus
+      // compile-time offsets (fully unrolled taps / k-steps), ring indices advance without divisions.
+      constexpr uint32_t layout = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);   // SW128 / SW64 / SW32
+      constexpr uint32_t sbo_a = HW * rowb, sbo_b = 8 * rowb;
+      constexpr int ksteps = KC >> 4;
+      constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(a_sm), 16, sbo_a, layout);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(w_sm), 16, sbo_b, layout);
+      uint32_t boff[9];                                  // weight block of tap t (taps flipped for the data gradient)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) boff[tap] = (uint32_t)(((P.flip ? 8 - tap : tap) * nkc * N * rowb) >> 4);
+      int acc = 0, buf = 0;
+      uint32_t tpar = 0, apar = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], tpar ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
-        for (int kc = 0; kc < nkc; ++kc, ++pi) {
-          const int buf = pi % P.nbuf;
-          const uint32_t apar = (uint32_t)(pi / P.nbuf) & 1u;
+        for (int kc = 0; kc < nkc; ++kc) {
           mbar_wait(&a_full[buf], apar);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_sm + buf * a_bytes);
+          const uint64_t ad = adesc0 + (uint64_t)(uint32_t)(buf * (a_bytes >> 4));
+          const uint64_t bd = bdesc0 + (uint64_t)(uint32_t)((kc * N * rowb) >> 4);
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int rh = tap / 3, rw = tap - rh * 3;
-            const int wt = P.flip ? 8 - tap : tap;
-            const uint32_t a_tap = a_addr + (uint32_t)(rh * HW + rw) * rowb;
-            const uint32_t b_tap = w_addr + (uint32_t)((wt * nkc + kc) * N) * rowb;
+#pragma unroll
             for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t adesc = make_smem_desc(a_tap + ks * 32, 16, sbo_a, layout);
-              const uint64_t bdesc = make_smem_desc(b_tap + ks * 32, 16, sbo_b, layout);
-              umma_bf16(d_tmem, adesc, bdesc, P.idesc, (kc | tap | ks) != 0 ? 1u : 0u);
+              const uint64_t adesc = ad + (uint64_t)((((tap / 3) * HW + (tap % 3)) * rowb + ks * 32) >> 4);
+              const uint64_t bdesc = bd + (uint64_t)(boff[tap] + (uint32_t)((ks * 32) >> 4));
+              if (tap == 0 && ks == 0) umma_bf16(d_tmem, adesc, bdesc, idesc, kc != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
             }
           }
           umma_commit(&a_empty[buf]);
+          if (++buf == P.nbuf) { buf = 0; apar ^= 1; }
         }
         umma_commit(&tfull[acc]);
+        if (++acc == NACC) { acc = 0; tpar ^= 1; }
       }
     }
   } else if (warp >= 4) {  // ================= epilogue (8 warps) =================
@@ -328,16 +334,16 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
   }
 }
 
-template <int N>
+template <int N, int KC>
 static int launch_halo(const HaloParams& P, const CUtensorMap& mA, size_t smem, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(halo3x3_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(halo3x3_kernel<N, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     MPGAN_REQUIRE(e == cudaSuccess, MPGAN_ERR_CUDA, "cudaFuncSetAttribute(halo3x3): %s", cudaGetErrorString(e));
     attr_done = true;
   }
   const int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  launch_k(halo3x3_kernel<N>, grid, kHaloThreads, smem, s, P, mA);
+  launch_k(halo3x3_kernel<N, KC>, grid, kHaloThreads, smem, s, P, mA);
   MPGAN_CHECK_LAUNCH("halo3x3_kernel");
   return 0;
 }
@@ -379,12 +385,19 @@ static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, in
     if (rc) return rc;
   }
   const size_t smem = w_bytes + nbuf * a_bytes + aux + 1024;
-  switch (N) {
-    case 16: return launch_halo<16>(P, mA, smem, s);
-    case 32: return launch_halo<32>(P, mA, smem, s);
-    case 64: return launch_halo<64>(P, mA, smem, s);
-    default: return launch_halo<128>(P, mA, smem, s);
+#define HALO_KC(NN)                                                     \
+  switch (KC) {                                                         \
+    case 16: return launch_halo<NN, 16>(P, mA, smem, s);                \
+    case 32: return launch_halo<NN, 32>(P, mA, smem, s);                \
+    default: return launch_halo<NN, 64>(P, mA, smem, s);                \
   }
+  switch (N) {
+    case 16: HALO_KC(16)
+    case 32: HALO_KC(32)
+    case 64: HALO_KC(64)
+    default: HALO_KC(128)
+  }
+#undef HALO_KC
 }
 
 }  // namespace tc

@@ -21,6 +21,7 @@
 //    (pixels are the K dimension), accumulators for a group of taps live in TMEM, split over pixel ranges and
 //    reduced with fp32 atomics into the flat gradient buffer.
 #include <cudaTypedefs.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 
@@ -46,6 +47,7 @@ struct TapGemmParams {
   int tw_log2, th_log2;
   int nimg;
   int n_total, n_tiles;
+  int lane_parallel;   // taps of a tile are loaded by different lanes (needs max taps per class * nkc <= STAGES)
   long long out_sn, out_sh, out_sw;
   bf16* out;
   const float* bias;
@@ -139,7 +141,6 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
   float* s_bias = s_stats + Epi::EW * 2 * 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const CUtensorMap* mapsA[4] = {&tmA0, &tmA1, &tmA2, &tmA3};
 
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmA0);
@@ -165,7 +166,8 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
   const int total_tiles = per_cls * P.ncls;
 
   if (warp == 0) {
-    if (elect_one()) {  // ================= TMA producer =================
+    if (!P.lane_parallel) {
+    if (elect_one()) {  // ================= TMA producer (one thread) =================
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -177,7 +179,8 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         const int cls = t;
         const int w0 = twi << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
         for (int tap = P.cls_tap_begin[cls]; tap < P.cls_tap_begin[cls + 1]; ++tap) {
-          const CUtensorMap* mA = mapsA[P.tap_map[tap]];
+          const int mi = P.tap_map[tap];
+          const CUtensorMap* mA = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
           const int cw = w0 + P.tap_dw[tap], chh = h0 + P.tap_dh[tap], slab = P.tap_slab[tap];
           for (int kc = 0; kc < P.nkc; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -190,6 +193,50 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
           }
         }
       }
+    }
+    } else {
+    // ================= TMA producer: lane l loads tap l of every tile =================
+    // A single issuing thread needs ~40 dependent scalar instructions per (tap, chunk) -- for the generator's layers
+    // (9 taps of 128 x 16..64 channels per tile) that, not bandwidth, was the tile rate.  The taps of a tile use
+    // consecutive ring stages, so each lane owns one tap, waits for its own stage and issues its own two TMA loads.
+    int cur_cls = -1, ntaps = 0, dh = 0, dw = 0, slab = 0;
+    const CUtensorMap* mA = &tmA0;
+    uint32_t cnt = 0;   // ring position of the tile's first stage (identical in all lanes)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int nt = t % P.n_tiles; t /= P.n_tiles;
+      const int twi = t % P.tiles_w; t /= P.tiles_w;
+      const int thi = t % P.tiles_h; t /= P.tiles_h;
+      const int tni = t % P.tiles_n; t /= P.tiles_n;
+      const int cls = t;
+      if (cls != cur_cls) {
+        cur_cls = cls;
+        const int tb = P.cls_tap_begin[cls];
+        ntaps = P.cls_tap_begin[cls + 1] - tb;
+        if (lane < ntaps) {
+          const int tap = tb + lane;
+          const int mi = P.tap_map[tap];
+          mA = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
+          dh = P.tap_dh[tap]; dw = P.tap_dw[tap]; slab = P.tap_slab[tap];
+        }
+      }
+      if (lane < ntaps) {
+        const int cw = (twi << P.tw_log2) + dw, chh = (thi << P.th_log2) + dh, n0 = tni << tn_log2;
+        for (int kc = 0; kc < P.nkc; ++kc) {
+          const uint32_t a = cnt + (uint32_t)(lane * P.nkc + kc);
+          const uint32_t stage = a % (uint32_t)STAGES;
+          const uint32_t phase = (a / (uint32_t)STAGES) & 1u;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_TX);
+          tma_load_4d(sA, mA, &full[stage], kc * KC, cw, chh, n0);
+          tma_load_3d(sB, &tmB, &full[stage], kc * KC, slab, nt * BN);
+        }
+      }
+      cnt += (uint32_t)(ntaps * P.nkc);
+      __syncwarp();   // no lane runs a tile ahead: with taps*chunks <= STAGES the stage parity stays unambiguous
+    }
     }
   } else if (warp == 1) {
     if (elect_one()) {  // ================= MMA issuer =================
@@ -401,6 +448,10 @@ template <> struct WgB<64>  { static constexpr int BYTES = 64 * 128, BOXES = 1, 
 template <> struct WgB<128> { static constexpr int BYTES = 2 * 8192, BOXES = 2, BOXC = 64, LAYOUT = 2, SBO = 1024, KSTEP = 2048, LBO = 8192, TPS = 2; };
 template <> struct WgB<256> { static constexpr int BYTES = 4 * 8192, BOXES = 4, BOXC = 64, LAYOUT = 2, SBO = 1024, KSTEP = 2048, LBO = 8192, TPS = 1; };
 
+// producer warps of wgrad_kernel: every warp but the MMA issuer for the small-channel layers (issue bound), one for
+// the discriminator's 128/256-channel layers (bandwidth bound: more pollers only cost issue slots there)
+template <int NX> struct WgProd { static constexpr int N = NX <= 64 ? 7 : 1; };
+
 template <int NX> struct WgCfg {
   using B = WgB<NX>;
   static constexpr int A_BYTES = 2 * 64 * 128;         // two 64-channel column groups x 64 pixels x 128 B
@@ -420,6 +471,7 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
   using Cfg = WgCfg<NX>;
   using B = WgB<NX>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int kWgProducers = WgProd<NX>::N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -428,14 +480,13 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const CUtensorMap* mapsX[4] = {&tmX0, &tmX1, &tmX2, &tmX3};
 
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmY);
     prefetch_tmap(&tmX0);
   }
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], kWgProducers); mbar_init(&empty[i], 1); }
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
@@ -457,6 +508,7 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
   const int tn_log2 = 6 - P.tw_log2 - P.th_log2;
   const int my_tiles = split < ptiles ? (ptiles - split + P.splits - 1) / P.splits : 0;
 
+  if constexpr (kWgProducers == 1) {
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
@@ -477,7 +529,8 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
           tma_load_4d(sA + 8192, &tmY, &full[stage], mb * 128 + 64, w0, h0, n0);
           for (int q = 0; q < nt; ++q) {
             const int tap = tap0 + tl0 + q;
-            const CUtensorMap* mX = mapsX[P.tap_map[tap]];
+            const int mi = P.tap_map[tap];
+            const CUtensorMap* mX = mi == 0 ? &tmX0 : (mi == 1 ? &tmX1 : (mi == 2 ? &tmX2 : &tmX3));
 #pragma unroll
             for (int i = 0; i < B::BOXES; ++i)
               tma_load_4d(sB + q * B::BYTES + i * 8192, mX, &full[stage], i * 64, w0 + P.tap_dw[tap],
@@ -487,7 +540,53 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
         }
       }
     }
-  } else if (warp == 1) {
+  }
+  } else {
+  if (warp != 1) {
+    // TMA producers: SEVEN warps (every warp but the MMA issuer; the epilogue warps have nothing else to do until
+    // the last tile).  One issuing thread needs ~130 cycles per TMA instruction, and a stage of the 16/32-channel
+    // layers is 11 of them (dY tile in two boxes + nine tap tiles of X) for only 4 MMAs -- the loads of a stage are
+    // dealt round-robin to the producers, each posting its own byte count on the stage's barrier.
+    const int pw = warp == 0 ? 0 : warp - 1;          // producer index 0..6
+    if (pw < kWgProducers && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = split; pt < ptiles; pt += P.splits) {
+        int t = pt;
+        const int twi = t % P.tiles_w; t /= P.tiles_w;
+        const int thi = t % P.tiles_h; t /= P.tiles_h;
+        const int tni = t;
+        const int w0 = twi << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
+        for (int tl0 = 0; tl0 < ntap; tl0 += B::TPS) {
+          const int nt = min(B::TPS, ntap - tl0);
+          const int items = 2 + nt * B::BOXES;          // item 0,1: dY boxes; 2 + q*BOXES + i: box i of tap q
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint32_t bytes = 0;
+          for (int it = pw; it < items; it += kWgProducers) bytes += it < 2 ? 8192u : (uint32_t)(B::BYTES / B::BOXES);
+          if (bytes) mbar_expect_tx(&full[stage], bytes);
+          else mbar_arrive(&full[stage]);
+          for (int it = pw; it < items; it += kWgProducers) {
+            if (it < 2) {
+              tma_load_4d(sA + it * 8192, &tmY, &full[stage], mb * 128 + it * 64, w0, h0, n0);
+            } else {
+              const int q = (it - 2) / B::BOXES, i = (it - 2) % B::BOXES;
+              const int tap = tap0 + tl0 + q;
+              const int mi = P.tap_map[tap];
+              const CUtensorMap* mX = mi == 0 ? &tmX0 : (mi == 1 ? &tmX1 : (mi == 2 ? &tmX2 : &tmX3));
+              tma_load_4d(sB + q * B::BYTES + i * 8192, mX, &full[stage], i * 64, w0 + P.tap_dw[tap],
+                          h0 + P.tap_dh[tap], n0);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  }
+  if (warp == 1) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -667,7 +766,11 @@ static int launch_tapgemm_t(const TapGemmParams& P, const CUtensorMap* mA, const
   }
   const long long total = (long long)P.ncls * P.tiles_n * P.tiles_h * P.tiles_w * P.n_tiles;
   int grid = (int)(total < num_sms() ? total : num_sms());
-  launch_k(tapgemm_kernel<BN, KC>, grid, EpiCfg<BN>::THREADS, Cfg::SMEM_BYTES, s, P, mA[0], mA[1], mA[2], mA[3], mB);
+  int max_taps = 0;
+  for (int c = 0; c < P.ncls; ++c) max_taps = std::max(max_taps, P.cls_tap_begin[c + 1] - P.cls_tap_begin[c]);
+  TapGemmParams Q = P;
+  Q.lane_parallel = (max_taps * P.nkc <= Cfg::STAGES && max_taps <= 32) ? 1 : 0;
+  launch_k(tapgemm_kernel<BN, KC>, grid, EpiCfg<BN>::THREADS, Cfg::SMEM_BYTES, s, Q, mA[0], mA[1], mA[2], mA[3], mB);
   MPGAN_CHECK_LAUNCH("tapgemm_kernel");
   return 0;
 }
