@@ -58,8 +58,11 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
   // MMA -> epilogue -> MMA round trip, not by throughput, so the ring must be deep
   constexpr int NACC = 512 / N > kMaxAcc ? kMaxAcc : 512 / N;
   constexpr int TMEM_COLS = NACC * N < 32 ? 32 : NACC * N;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // No static shared memory in this kernel, so the dynamic window starts at the CTA's (1024-byte aligned) base; using
+  // the symbol directly (instead of a manually aligned pointer) lets the compiler emit LDS/STS rather than generic
+  // loads and stores for every shared-memory access of the epilogue.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int C = P.C;
   const int nkc = C / KC;
   constexpr int rowb = KC * 2;                           // bytes per pixel row of a plane: 128 / 64 / 32

@@ -130,8 +130,11 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
   using Epi = EpiCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NACC = Epi::NACC;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // No static shared memory in this kernel, so the dynamic window starts at the CTA's (1024-byte aligned) base; using
+  // the symbol directly (instead of a manually aligned pointer) lets the compiler emit LDS/STS rather than generic
+  // loads and stores for every shared-memory access of the epilogue.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -458,9 +461,14 @@ template <int NX> struct WgCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B::TPS * B::BYTES;
   static constexpr int AUX_BYTES = 256;
   static constexpr int MAX_STAGES = (kSmemLimit - 1024 - AUX_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  // Small-channel (generator) layers: half of TMEM and <= ~100 KB of shared memory per CTA, so that a weight-gradient
+  // CTA can share an SM with a CTA of the (independent) data-gradient / BatchNorm chain running on the other stream.
+  static constexpr bool SMALL = NX <= 64;
+  static constexpr int TMEM_COLS = SMALL ? 256 : 512;
+  static constexpr int STAGE_CAP = SMALL ? (100 * 1024 / STAGE_BYTES < 2 ? 2 : 100 * 1024 / STAGE_BYTES) : 8;
+  static constexpr int STAGES = MAX_STAGES > STAGE_CAP ? STAGE_CAP : MAX_STAGES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + AUX_BYTES;
-  static constexpr int MAX_TPG = 512 / NX;              // taps whose accumulators fit in TMEM
+  static constexpr int MAX_TPG = TMEM_COLS / NX;        // taps whose accumulators fit in the TMEM allocation
 };
 
 template <int NX>
@@ -472,8 +480,11 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
   using B = WgB<NX>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int kWgProducers = WgProd<NX>::N;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // No static shared memory in this kernel, so the dynamic window starts at the CTA's (1024-byte aligned) base; using
+  // the symbol directly (instead of a manually aligned pointer) lets the compiler emit LDS/STS rather than generic
+  // loads and stores for every shared-memory access of the epilogue.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -490,7 +501,7 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -647,7 +658,7 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -938,7 +949,7 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
       ++ntap;
     }
   P.ntaps = ntap;
-  const int max_tpg = 512 / g.cx;
+  const int max_tpg = (g.cx <= 64 ? 256 : 512) / g.cx;
   P.ngroups = (ntap + max_tpg - 1) / max_tpg;
   P.taps_per_group = (ntap + P.ngroups - 1) / P.ngroups;   // balanced groups
   P.m_blocks = (g.cy + 127) / 128;

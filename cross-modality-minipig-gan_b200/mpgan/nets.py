@@ -42,6 +42,8 @@ class Plan:
         self.fork = os.environ.get("MPGAN_NO_FORK", "0") != "1"
         self._arena = None
         self._arena_used = 0
+        self.keepalive = []        # tensors read by weight-gradient kernels still in flight on the "wgrad" stream
+        self.wgrad_forked = False
 
     ARENA = 1 << 15  # fp64 slots: every BatchNorm statistic / backward sum of one pass, zeroed by ONE memset
 
@@ -73,19 +75,30 @@ def conv_apply(rec, x, out=None, stats=None):
 _SIDE = {}
 
 
-def side_stream(device):
-    """One auxiliary stream per device: independent kernels of a layer (weight gradient vs data gradient) are
-    issued on two streams; under CUDA-graph capture the fork/join becomes two parallel graph branches."""
-    key = torch.device(device).index
+def side_stream(device, which="branch"):
+    """Auxiliary streams per device.  "branch": the residual branch of a ResidualUnit (forked and joined inside the
+    unit).  "wgrad": every weight-gradient kernel of a backward pass -- they are off the critical path (nothing in
+    the backward chain reads a weight gradient), so they are forked layer by layer and joined ONCE, at the end of
+    the pass (``join_wgrad``).  Under CUDA-graph capture the streams become parallel graph branches."""
+    key = (torch.device(device).index, which)
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=device)
     return _SIDE[key]
 
 
+def join_wgrad(plan, device):
+    """End of a backward pass: the optimizer (or the caller) may read the weight gradients after this."""
+    if plan.wgrad_forked:
+        torch.cuda.current_stream().wait_stream(side_stream(device, "wgrad"))
+        plan.wgrad_forked = False
+    plan.keepalive.clear()
+
+
 def conv_backward(rec, x, dy, plan, need_dx, bias_done=False):
     """x: the layer's input, dy: gradient of its output (contiguous or sliced).  Returns dx or None.
     bias_done: the bias gradient was already accumulated by the fused BatchNorm backward.
-    The weight gradient and the data gradient only share inputs, so they run concurrently (fork/join)."""
+    The weight gradient only shares inputs with the data gradient: it is issued on the "wgrad" stream and not
+    waited for until the end of the pass; (x, dy) are kept alive until then so the allocator cannot recycle them."""
     spec = rec.spec
 
     def wgrad():
@@ -103,20 +116,17 @@ def conv_backward(rec, x, dy, plan, need_dx, bias_done=False):
 
     if not plan.need_wgrad:
         return dgrad() if need_dx else None
-    if not need_dx:
-        wgrad()
-        return None
     if not plan.fork:
         wgrad()
-        return dgrad()
+        return dgrad() if need_dx else None
     cur = torch.cuda.current_stream()
-    side = side_stream(dy.device)
+    side = side_stream(dy.device, "wgrad")
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         wgrad()
-    dx = dgrad()
-    cur.wait_stream(side)   # join before anything downstream can recycle dy / x
-    return dx
+    plan.keepalive.append((x, dy))
+    plan.wgrad_forked = True
+    return dgrad() if need_dx else None
 
 
 def bn_act_forward(c, bn, act, alpha, leaky, res, out, plan, stats, fused_stats):
@@ -487,6 +497,7 @@ class CasNetGenerator(_PlanNet):
         unets = [m for m in self.model if isinstance(m, UNet)]
         for i in range(len(unets) - 1, -1, -1):
             dh = unets[i]._bwd(dh, plan, need_dx=(need_dx or i > 0))
+        join_wgrad(plan, dyc.device)
         if not need_dx:
             return None
         d_in = dh if dh.dtype == torch.float32 else ops.add_copy(dh, None, _new(dh, dh.shape, torch.float32))
@@ -645,6 +656,7 @@ class _ConvBnLeakyStack(_PlanNet):
             if (3 * i) in ag:
                 dc = dc + ag[3 * i].permute(to_cl).to(dc.dtype)
             dh = conv_backward(rt.rec[convs[i]], h_in, dc, plan, need_dx=(need_dx or i > 0), bias_done=fused_bias)
+        join_wgrad(plan, dp.device)
         if not need_dx:
             return None
         d_in = dh if dh.dtype == torch.float32 else ops.add_copy(dh, None, _new(dh, dh.shape, torch.float32))
