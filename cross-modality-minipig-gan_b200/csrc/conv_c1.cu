@@ -6,6 +6,8 @@
 //   * wgrad_x1:   weight gradient when the X side has ONE channel: dw[cy][tap] += sum_p y[p][cy] * x[gather(p,tap)].
 // Replaces the corresponding cuDNN calls behind nn.Conv2d / nn.ConvTranspose2d at
 // /root/reference/code/GAN/GAN_final.py:167-169 (D first conv) and the MONAI UNet's first / last layers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mpgan {
@@ -184,6 +186,9 @@ int c1f_bprop(const MpganConvGeom* g, int dtype, const void* y, int64_t ldy, con
               int64_t ldx, double* stats, cudaStream_t s);
 int c1f_wgrad(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* y, int64_t ldy, float* dw,
               cudaStream_t s);
+// conv_c1mma.cuh (conv_tc.cu): tcgen05 path for bf16 cx == 1 forward convolutions; returns 1 when not covered
+int c1mma_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* w, const float* bias, void* y,
+                int64_t ldy, double* stats, cudaStream_t s);
 }  // namespace mpgan
 
 using namespace mpgan;
@@ -226,6 +231,9 @@ extern "C" int mpgan_c1_conv_fprop(const MpganConvGeom* g, int dtype, const void
   C1Geom p;
   int rc = make_c1(g, &p);
   if (rc) return rc;
+  static const bool use_mma = !(getenv("MPGAN_NO_C1MMA") && getenv("MPGAN_NO_C1MMA")[0] == '1');
+  rc = use_mma ? c1mma_fprop(g, dtype, x, ldx, w, bias, y, ldy, stats, (cudaStream_t)stream) : 1;   // bf16, cy in {16,32,64}
+  if (rc != 1) return rc;
   rc = c1f_fprop(g, dtype, x, ldx, w, bias, y, ldy, stats, (cudaStream_t)stream);   // rank-2 3x3, cx == 1
   if (rc != 1) return rc;
   if (g->cy == 1 && (size_t)p.taps * g->cx * 4 <= 48 * 1024) {

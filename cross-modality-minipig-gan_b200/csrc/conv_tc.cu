@@ -684,7 +684,7 @@ static CUtensorMapSwizzle swizzle_for_bytes(int inner_bytes) {
 
 // bf16 tensor map, `rank` dims (innermost first); strides in elements for dims 1..rank-1
 static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                      const uint32_t* box) {
+                      const uint32_t* box, bool no_swizzle = false) {
   auto enc = get_encode();
   MPGAN_REQUIRE(enc != nullptr, MPGAN_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
   cuuint64_t gdim[5], gstr[4];
@@ -696,7 +696,8 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
     MPGAN_REQUIRE(gstr[i] % 16 == 0, MPGAN_ERR_SHAPE, "tensor stride %d (=%llu B) not a multiple of 16 B", i,
                   (unsigned long long)gstr[i]);
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes((int)box[0] * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_for_bytes((int)box[0] * 2),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MPGAN_REQUIRE(r == CUDA_SUCCESS, MPGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
@@ -811,6 +812,8 @@ static int pick_bn(int n) {
 }  // namespace mpgan
 // stride-1 3x3 layers with resident weights and one halo load per tile (halo3x3_run returns 1 = not covered)
 #include "conv_halo.cuh"
+// one-input-channel forward convolutions (im2col tile built in shared memory, one MMA per tile)
+#include "conv_c1mma.cuh"
 namespace mpgan {
 namespace tc {
 

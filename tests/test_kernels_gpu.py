@@ -42,6 +42,9 @@ CONV_CASES = [
     (2, 2, 1, 32, 30, 3, 2, 1),
     (2, 2, 1, 16, 20, 3, 2, 1),
     (2, 2, 1, 64, 19, 3, 1, 0),
+    (2, 2, 1, 64, 40, 3, 1, 0),     # width % 8 == 0: the tcgen05 im2col kernel (conv_c1mma.cuh) takes bf16 fprop
+    (2, 2, 1, 16, 48, 3, 2, 1),
+    (2, 3, 1, 32, 24, 3, 1, 1),
     (2, 3, 16, 16, 17, 3, 1, 1),
     (2, 2, 32, 1, 16, 3, 1, 1),
     (2, 2, 24, 40, 13, 4, 2, 0),
