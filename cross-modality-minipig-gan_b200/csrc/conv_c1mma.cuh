@@ -148,7 +148,7 @@ c1mma_fprop_kernel(const __grid_constant__ C1mmaParams P, const __grid_constant_
             v[k][0] | (v[k][1] << 16), v[k][2] | (v[k][3] << 16), v[k][4] | (v[k][5] << 16), v[k][6] | (v[k][7] << 16));
         *reinterpret_cast<uint4*>(rowp + ((1u ^ sw) << 4)) = make_uint4(v[k][8], 0u, 0u, 0u);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tcgen05.mma reads
+      if (!(P.dbg & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tcgen05.mma reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[stage]);
     }
@@ -179,9 +179,9 @@ c1mma_fprop_kernel(const __grid_constant__ C1mmaParams P, const __grid_constant_
     const int lh = row >> 3, lw = row & 7;
     float* sl = s_stats + ew * 2 * N;
     const int c0 = NCH == 2 ? half * CH : 0;
-    float s1[CH], s2[CH];
+    unsigned long long s1[CH / 2], s2[CH / 2];   // packed fp32 pairs
 #pragma unroll
-    for (int j = 0; j < CH; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    for (int j = 0; j < CH / 2; ++j) { s1[j] = 0ull; s2[j] = 0ull; }
     int it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       if (NCH == 1 && (it & 1) != half) continue;
@@ -203,38 +203,15 @@ c1mma_fprop_kernel(const __grid_constant__ C1mmaParams P, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      const float mk = valid ? 1.f : 0.f;
-      uint32_t packed[CH / 2];
-#pragma unroll
-      for (int j = 0; j < CH / 4; ++j) {
-        const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j);
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r[4 * j]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w);
-        packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
-        packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
-      }
-      if (valid && !(P.dbg & 1)) {
-#pragma unroll
-        for (int j = 0; j < CH / 8; ++j)
-          *reinterpret_cast<uint4*>(orow + j * 8) =
-              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-      }
-      if (P.stats) {  // statistics of the values as stored
-#pragma unroll
-        for (int j = 0; j < CH / 2; ++j) {
-          const float fa = __uint_as_float(packed[j] << 16) * mk, fb = __uint_as_float(packed[j] & 0xffff0000u) * mk;
-          s1[2 * j] += fa; s1[2 * j + 1] += fb;
-          s2[2 * j] = fmaf(fa, fa, s2[2 * j]); s2[2 * j + 1] = fmaf(fb, fb, s2[2 * j + 1]);
-        }
-      }
+      if (!(P.dbg & 8)) epi_chunk_store<CH>(r, s_bias + c0, orow, valid && !(P.dbg & 1), P.stats != nullptr, s1, s2);
     }
     if (P.stats) {
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = j < CH ? s1[j] : 0.f;
+      for (int j = 0; j < 32; ++j) v[j] = j < CH ? ((j & 1) ? unpack_f32x2(s1[j / 2]).y : unpack_f32x2(s1[j / 2]).x) : 0.f;
       const float t1 = warp_transpose_reduce32(v, lane);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = j < CH ? s2[j] : 0.f;
+      for (int j = 0; j < 32; ++j) v[j] = j < CH ? ((j & 1) ? unpack_f32x2(s2[j / 2]).y : unpack_f32x2(s2[j / 2]).x) : 0.f;
       const float t2 = warp_transpose_reduce32(v, lane);
       if (lane < CH) { sl[c0 + lane] = t1; sl[N + c0 + lane] = t2; }
     }

@@ -195,9 +195,9 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
       // (thread = tile row, fixed tile order => reproducible) that are transposed and reduced ONCE, after the last tile.
       constexpr int NCH = N / CH;                 // 1 (N = 16, 32) or 2 (N = 64)
       const int c0 = NCH == 2 ? half * CH : 0;
-      float s1[CH], s2[CH];
+      unsigned long long s1[CH / 2], s2[CH / 2];   // packed fp32 pairs
 #pragma unroll
-      for (int j = 0; j < CH; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      for (int j = 0; j < CH / 2; ++j) { s1[j] = 0ull; s2[j] = 0ull; }
       int it = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
         if (NCH == 1 && (it & 1) != half) continue;
@@ -219,38 +219,15 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
-        const float m = valid ? 1.f : 0.f;
-        uint32_t packed[CH / 2];
-#pragma unroll
-        for (int j = 0; j < CH / 4; ++j) {
-          const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j);
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r[4 * j]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w);
-          packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
-          packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
-        }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < CH / 8; ++j)
-            *reinterpret_cast<uint4*>(orow + j * 8) =
-                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        }
-        if (P.stats) {  // statistics of the values as stored
-#pragma unroll
-          for (int j = 0; j < CH / 2; ++j) {
-            const float fa = __uint_as_float(packed[j] << 16) * m, fb = __uint_as_float(packed[j] & 0xffff0000u) * m;
-            s1[2 * j] += fa; s1[2 * j + 1] += fb;
-            s2[2 * j] = fmaf(fa, fa, s2[2 * j]); s2[2 * j + 1] = fmaf(fb, fb, s2[2 * j + 1]);
-          }
-        }
+        epi_chunk_store<CH>(r, s_bias + c0, orow, valid, P.stats != nullptr, s1, s2);
       }
       if (P.stats) {
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = j < CH ? s1[j] : 0.f;
+        for (int j = 0; j < 32; ++j) v[j] = j < CH ? ((j & 1) ? unpack_f32x2(s1[j / 2]).y : unpack_f32x2(s1[j / 2]).x) : 0.f;
         const float t1 = warp_transpose_reduce32(v, lane);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = j < CH ? s2[j] : 0.f;
+        for (int j = 0; j < 32; ++j) v[j] = j < CH ? ((j & 1) ? unpack_f32x2(s2[j / 2]).y : unpack_f32x2(s2[j / 2]).x) : 0.f;
         const float t2 = warp_transpose_reduce32(v, lane);
         if (lane < CH) { sl[c0 + lane] = t1; sl[N + c0 + lane] = t2; }
       }

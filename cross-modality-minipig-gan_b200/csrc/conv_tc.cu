@@ -47,6 +47,7 @@ struct TapGemmParams {
   int tw_log2, th_log2;
   int nimg;
   int n_total, n_tiles;
+  int mt;              // 128-pixel tiles per weight stage (1, or 2 for large BN = 128 layers)
   int lane_parallel;   // taps of a tile are loaded by different lanes (needs max taps per class * nkc <= STAGES)
   long long out_sn, out_sh, out_sw;
   bf16* out;
@@ -83,8 +84,13 @@ template <int BN> struct EpiCfg {
   static constexpr uint32_t ARRIVALS = REG ? (NCH == 1 ? 4u : 8u) : 4u;
 };
 
-template <int BN, int KC> struct TapCfg {
-  static constexpr int A_BYTES = 128 * KC * 2;
+// MT = 128-pixel tiles that share one weight stage ("supertile", consecutive along w).  A 128-column MMA reads as
+// many weight bytes as activation bytes, so with MT = 1 the BN = 128 layers (D layer 3 data gradient) were bound by the
+// L2 -> shared-memory stream (125 B/clk/SM); MT = 2 reuses every weight stage twice (94 B/clk, like the BN = 256 layers).
+template <int BN, int KC, int MT_> struct TapCfg {
+  static constexpr int MT = MT_;
+  static constexpr int A_TILE = 128 * KC * 2;
+  static constexpr int A_BYTES = MT * A_TILE;
   static constexpr int B_TX = BN * KC * 2;
   static constexpr int B_BYTES = B_TX < 1024 ? 1024 : B_TX;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -95,7 +101,8 @@ template <int BN, int KC> struct TapCfg {
   // small-channel layers are TMA-latency bound: keep up to 32 stages (>= 3 tiles of a 3x3 layer) in flight
   static constexpr int STAGES = MAX_STAGES > 32 ? 32 : MAX_STAGES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + AUX_BYTES;
-  static constexpr int TMEM_COLS = EpiCfg<BN>::NACC * BN < 32 ? 32 : EpiCfg<BN>::NACC * BN;
+  static constexpr int TMEM_COLS = EpiCfg<BN>::NACC * MT * BN < 32 ? 32 : EpiCfg<BN>::NACC * MT * BN;
+  static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
   static_assert(STAGES >= 2, "pipeline too shallow");
 };
 
@@ -121,15 +128,16 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
   return v[0];
 }
 
-template <int BN, int KC>
+template <int BN, int KC, int MT_>
 __global__ void __launch_bounds__(EpiCfg<BN>::THREADS, 1)
 tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB) {
-  using Cfg = TapCfg<BN, KC>;
+  using Cfg = TapCfg<BN, KC, MT_>;
   using Epi = EpiCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NACC = Epi::NACC;
+  constexpr int MT = Cfg::MT;
   // No static shared memory in this kernel, so the dynamic window starts at the CTA's (1024-byte aligned) base; using
   // the symbol directly (instead of a manually aligned pointer) lets the compiler emit LDS/STS rather than generic
   // loads and stores for every shared-memory access of the epilogue.
@@ -180,7 +188,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         const int thi = t % P.tiles_h; t /= P.tiles_h;
         const int tni = t % P.tiles_n; t /= P.tiles_n;
         const int cls = t;
-        const int w0 = twi << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
+        const int w0 = (twi * MT) << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
         for (int tap = P.cls_tap_begin[cls]; tap < P.cls_tap_begin[cls + 1]; ++tap) {
           const int mi = P.tap_map[tap];
           const CUtensorMap* mA = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
@@ -190,7 +198,9 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
             uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sB = sA + Cfg::A_BYTES;
             mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_TX);
-            tma_load_4d(sA, mA, &full[stage], kc * KC, cw, chh, n0);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub)
+              tma_load_4d(sA + sub * Cfg::A_TILE, mA, &full[stage], kc * KC, cw + (sub << P.tw_log2), chh, n0);
             tma_load_3d(sB, &tmB, &full[stage], kc * KC, slab, nt * BN);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -224,7 +234,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         }
       }
       if (lane < ntaps) {
-        const int cw = (twi << P.tw_log2) + dw, chh = (thi << P.th_log2) + dh, n0 = tni << tn_log2;
+        const int cw = ((twi * MT) << P.tw_log2) + dw, chh = (thi << P.th_log2) + dh, n0 = tni << tn_log2;
         for (int kc = 0; kc < P.nkc; ++kc) {
           const uint32_t a = cnt + (uint32_t)(lane * P.nkc + kc);
           const uint32_t stage = a % (uint32_t)STAGES;
@@ -233,7 +243,9 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
           mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_TX);
-          tma_load_4d(sA, mA, &full[stage], kc * KC, cw, chh, n0);
+#pragma unroll
+          for (int sub = 0; sub < MT; ++sub)
+            tma_load_4d(sA + sub * Cfg::A_TILE, mA, &full[stage], kc * KC, cw + (sub << P.tw_log2), chh, n0);
           tma_load_3d(sB, &tmB, &full[stage], kc * KC, slab, nt * BN);
         }
       }
@@ -253,7 +265,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         const uint32_t par = (uint32_t)(it / NACC) & 1u;
         mbar_wait(&tempty[buf], par ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * MT * BN);
         const int kiters = (P.cls_tap_begin[cls + 1] - P.cls_tap_begin[cls]) * P.nkc;
         for (int ki = 0; ki < kiters; ++ki) {
           mbar_wait(&full[stage], phase);
@@ -262,9 +274,13 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) {
-            const uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, SwizzleOf<KC>::sbo, SwizzleOf<KC>::layout);
             const uint64_t bdesc = make_smem_desc(b_addr + k * 32, 16, SwizzleOf<KC>::sbo, SwizzleOf<KC>::layout);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (ki | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub) {
+              const uint64_t adesc = make_smem_desc(a_addr + sub * Cfg::A_TILE + k * 32, 16, SwizzleOf<KC>::sbo,
+                                                    SwizzleOf<KC>::layout);
+              umma_bf16(d_tmem + (uint32_t)(sub * BN), adesc, bdesc, idesc, (ki | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -284,21 +300,21 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
     if constexpr (Epi::REG) {
       constexpr int NCH = Epi::NCH;               // 1 (BN = 16, 32) or 2 (BN = 64)
       const int c0 = NCH == 2 ? half * CH : 0;
-      float s1[CH], s2[CH];
+      unsigned long long s1[CH / 2], s2[CH / 2];   // packed fp32 pairs
 #pragma unroll
-      for (int j = 0; j < CH; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      for (int j = 0; j < CH / 2; ++j) { s1[j] = 0ull; s2[j] = 0ull; }
       int stat_base = -1;                         // channel block the register statistics belong to
       auto flush = [&]() {                        // once per kernel unless the layer has several BN-column blocks
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = j < CH ? s1[j] : 0.f;
+        for (int j = 0; j < 32; ++j) v[j] = j < CH ? ((j & 1) ? unpack_f32x2(s1[j / 2]).y : unpack_f32x2(s1[j / 2]).x) : 0.f;
         const float t1 = warp_transpose_reduce32(v, lane);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = j < CH ? s2[j] : 0.f;
+        for (int j = 0; j < 32; ++j) v[j] = j < CH ? ((j & 1) ? unpack_f32x2(s2[j / 2]).y : unpack_f32x2(s2[j / 2]).x) : 0.f;
         const float t2 = warp_transpose_reduce32(v, lane);
         if (lane < CH) { sl[stat_base + c0 + lane] += t1; sl[P.n_total + stat_base + c0 + lane] += t2; }
 #pragma unroll
-        for (int j = 0; j < CH; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+        for (int j = 0; j < CH / 2; ++j) { s1[j] = 0ull; s2[j] = 0ull; }
       };
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -330,30 +346,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);   // values are in registers: the accumulator is free again
-        const float m = valid ? 1.f : 0.f;
-        uint32_t packed[CH / 2];
-#pragma unroll
-        for (int j = 0; j < CH / 4; ++j) {
-          const float4 bv = *reinterpret_cast<const float4*>(s_bias + nbase + c0 + 4 * j);
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r[4 * j]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
-          packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
-          packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
-        }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < CH / 8; ++j)
-            *reinterpret_cast<uint4*>(orow + j * 8) =
-                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        }
-        if (P.stats) {  // statistics of the values as stored
-#pragma unroll
-          for (int j = 0; j < CH / 2; ++j) {
-            const float fa = __uint_as_float(packed[j] << 16) * m, fb = __uint_as_float(packed[j] & 0xffff0000u) * m;
-            s1[2 * j] += fa; s1[2 * j + 1] += fb;
-            s2[2 * j] = fmaf(fa, fa, s2[2 * j]); s2[2 * j + 1] = fmaf(fb, fb, s2[2 * j + 1]);
-          }
-        }
+        epi_chunk_store<CH>(r, s_bias + nbase + c0, orow, valid, P.stats != nullptr, s1, s2);
       }
       if (P.stats && stat_base >= 0) flush();
     } else {
@@ -365,16 +358,18 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
       const int thi = t % P.tiles_h; t /= P.tiles_h;
       const int tni = t % P.tiles_n; t /= P.tiles_n;
       const int cls = t;
-      const int ow = (twi << P.tw_log2) + lw, oh = (thi << P.th_log2) + lh, img = (tni << tn_log2) + ln;
-      const bool valid = img < P.nimg && oh < P.cls_oh[cls] && ow < P.cls_ow[cls];
       const int nbase = nt * BN;
-      bf16* orow = P.out + P.cls_out_off[cls] + (long long)img * P.out_sn + (long long)oh * P.out_sh +
-                   (long long)ow * P.out_sw + nbase;
       const int buf = it % NACC;
       const uint32_t par = (uint32_t)(it / NACC) & 1u;
       mbar_wait(&tfull[buf], par);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+      const int ow = ((twi * MT + sub) << P.tw_log2) + lw, oh = (thi << P.th_log2) + lh, img = (tni << tn_log2) + ln;
+      const bool valid = img < P.nimg && oh < P.cls_oh[cls] && ow < P.cls_ow[cls];
+      bf16* orow = P.out + P.cls_out_off[cls] + (long long)img * P.out_sn + (long long)oh * P.out_sh +
+                   (long long)ow * P.out_sw + nbase;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * MT + sub) * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         uint32_t r[32];
@@ -415,6 +410,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
             sl[P.n_total + nbase + c0 + lane] += s2;
           }
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -766,12 +762,12 @@ static int make_act_maps(CUtensorMap* maps, const void* base, int nimg, int h, i
   return 0;
 }
 
-template <int BN, int KC>
+template <int BN, int KC, int MT>
 static int launch_tapgemm_t(const TapGemmParams& P, const CUtensorMap* mA, const CUtensorMap& mB, cudaStream_t s) {
-  using Cfg = TapCfg<BN, KC>;
+  using Cfg = TapCfg<BN, KC, MT>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, KC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     MPGAN_REQUIRE(e == cudaSuccess, MPGAN_ERR_CUDA, "cudaFuncSetAttribute(tapgemm): %s", cudaGetErrorString(e));
     attr_done = true;
@@ -782,7 +778,7 @@ static int launch_tapgemm_t(const TapGemmParams& P, const CUtensorMap* mA, const
   for (int c = 0; c < P.ncls; ++c) max_taps = std::max(max_taps, P.cls_tap_begin[c + 1] - P.cls_tap_begin[c]);
   TapGemmParams Q = P;
   Q.lane_parallel = (max_taps * P.nkc <= Cfg::STAGES && max_taps <= 32) ? 1 : 0;
-  launch_k(tapgemm_kernel<BN, KC>, grid, EpiCfg<BN>::THREADS, Cfg::SMEM_BYTES, s, Q, mA[0], mA[1], mA[2], mA[3], mB);
+  launch_k(tapgemm_kernel<BN, KC, MT>, grid, EpiCfg<BN>::THREADS, Cfg::SMEM_BYTES, s, Q, mA[0], mA[1], mA[2], mA[3], mB);
   MPGAN_CHECK_LAUNCH("tapgemm_kernel");
   return 0;
 }
@@ -791,11 +787,15 @@ template <int KC>
 static int launch_tapgemm_kc(int bn, const TapGemmParams& P, const CUtensorMap* mA, const CUtensorMap& mB,
                              cudaStream_t s) {
   switch (bn) {
-    case 16: return launch_tapgemm_t<16, KC>(P, mA, mB, s);
-    case 32: return launch_tapgemm_t<32, KC>(P, mA, mB, s);
-    case 64: return launch_tapgemm_t<64, KC>(P, mA, mB, s);
-    case 128: return launch_tapgemm_t<128, KC>(P, mA, mB, s);
-    case 256: return launch_tapgemm_t<256, KC>(P, mA, mB, s);
+    case 16: return launch_tapgemm_t<16, KC, 1>(P, mA, mB, s);
+    case 32: return launch_tapgemm_t<32, KC, 1>(P, mA, mB, s);
+    case 64: return launch_tapgemm_t<64, KC, 1>(P, mA, mB, s);
+    case 128:
+      if constexpr (KC == 64) {
+        if (P.mt == 2) return launch_tapgemm_t<128, KC, 2>(P, mA, mB, s);
+      }
+      return launch_tapgemm_t<128, KC, 1>(P, mA, mB, s);
+    case 256: return launch_tapgemm_t<256, KC, 1>(P, mA, mB, s);
   }
   set_error("bad BN %d", bn);
   return MPGAN_ERR_UNSUPPORTED;
@@ -900,6 +900,9 @@ static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, con
   choose_tile(low, loh, g.n, 128, &P.tw_log2, &P.th_log2);
   const int tw = 1 << P.tw_log2, th = 1 << P.th_log2, tn = 128 / (tw * th);
   P.tiles_w = (low + tw - 1) / tw; P.tiles_h = (loh + th - 1) / th; P.tiles_n = (g.n + tn - 1) / tn;
+  // two tiles per weight stage only when the layer still has several supertiles per SM (D layer 3 data gradient)
+  P.mt = (BN == 128 && KC == 64 && (long long)P.ncls * P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles >= 8LL * num_sms()) ? 2 : 1;
+  P.tiles_w = (P.tiles_w + P.mt - 1) / P.mt;
 
   CUtensorMap mA[4], mB;
   uint32_t boxA[4] = {(uint32_t)KC, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};

@@ -136,5 +136,61 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+
+// ---- small-N epilogue arithmetic (shared by the halo, tap-GEMM and one-channel kernels) ----
+// Blackwell issues fp32 FMAs at full rate in the packed form (two lanes of a 64-bit register pair).
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
+  float2 f;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v));
+  return f;
+}
+
+// One CH-column chunk of one accumulator row: + bias -> bf16 -> 16-byte stores at `orow`, and (optionally) the
+// BatchNorm statistics of the values AS STORED, accumulated in per-thread packed registers s1 / s2 (CH/2 pairs each).
+template <int CH>
+__device__ __forceinline__ void epi_chunk_store(const uint32_t (&r)[CH], const float* s_bias_c0, bf16* orow, bool valid,
+                                                bool do_stats, unsigned long long (&s1)[CH / 2],
+                                                unsigned long long (&s2)[CH / 2]) {
+  const unsigned long long ones = pack_f32x2(1.f, 1.f);
+  uint32_t packed[CH / 2];
+#pragma unroll
+  for (int j = 0; j < CH / 4; ++j) {
+    const float4 b = *reinterpret_cast<const float4*>(s_bias_c0 + 4 * j);
+    const float2 v0 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), ones,
+                                             pack_f32x2(b.x, b.y)));
+    const float2 v1 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), ones,
+                                             pack_f32x2(b.z, b.w)));
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(v1.x, v1.y);
+    packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+    packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+  }
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < CH / 8; ++j)
+      *reinterpret_cast<uint4*>(orow + j * 8) =
+          make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    if (do_stats) {
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) {
+        const unsigned long long f =
+            pack_f32x2(__uint_as_float(packed[j] << 16), __uint_as_float(packed[j] & 0xffff0000u));
+        s1[j] = fma_f32x2(f, ones, s1[j]);
+        s2[j] = fma_f32x2(f, f, s2[j]);
+      }
+    }
+  }
+}
+
 }  // namespace tc
 }  // namespace mpgan
