@@ -62,6 +62,7 @@ struct WgradParams {
   int taps_per_group, ngroups, m_blocks, splits;
   int tiles_w, tiles_h, tiles_n, tw_log2, th_log2;
   int cx, cy;
+  int nprod;           // TMA producer warps (1..7)
   float* dw;
 };
 
@@ -451,7 +452,7 @@ template <> struct WgB<256> { static constexpr int BYTES = 4 * 8192, BOXES = 4, 
 // the discriminator's 128/256-channel layers (bandwidth bound: more pollers only cost issue slots there)
 template <int NX> struct WgProd { static constexpr int N = NX <= 64 ? 7 : 1; };
 
-template <int NX> struct WgCfg {
+template <int NX, bool SMALL_> struct WgCfg {
   using B = WgB<NX>;
   static constexpr int A_BYTES = 2 * 64 * 128;         // two 64-channel column groups x 64 pixels x 128 B
   static constexpr int STAGE_BYTES = A_BYTES + B::TPS * B::BYTES;
@@ -459,7 +460,7 @@ template <int NX> struct WgCfg {
   static constexpr int MAX_STAGES = (kSmemLimit - 1024 - AUX_BYTES) / STAGE_BYTES;
   // Small-channel (generator) layers: half of TMEM and <= ~100 KB of shared memory per CTA, so that a weight-gradient
   // CTA can share an SM with a CTA of the (independent) data-gradient / BatchNorm chain running on the other stream.
-  static constexpr bool SMALL = NX <= 64;
+  static constexpr bool SMALL = SMALL_;
   static constexpr int TMEM_COLS = SMALL ? 256 : 512;
   static constexpr int STAGE_CAP = SMALL ? (100 * 1024 / STAGE_BYTES < 2 ? 2 : 100 * 1024 / STAGE_BYTES) : 8;
   static constexpr int STAGES = MAX_STAGES > STAGE_CAP ? STAGE_CAP : MAX_STAGES;
@@ -467,15 +468,15 @@ template <int NX> struct WgCfg {
   static constexpr int MAX_TPG = TMEM_COLS / NX;        // taps whose accumulators fit in the TMEM allocation
 };
 
-template <int NX>
+template <int NX, bool SMALL>
 __global__ void __launch_bounds__(256, 1)
 wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUtensorMap tmY,
              const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
              const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmX3) {
-  using Cfg = WgCfg<NX>;
+  using Cfg = WgCfg<NX, SMALL>;
   using B = WgB<NX>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int kWgProducers = WgProd<NX>::N;
+  const int kWgProducers = P.nprod;   // producer warps (runtime: barrier arrival count)
   // No static shared memory in this kernel, so the dynamic window starts at the CTA's (1024-byte aligned) base; using
   // the symbol directly (instead of a manually aligned pointer) lets the compiler emit LDS/STS rather than generic
   // loads and stores for every shared-memory access of the epilogue.
@@ -515,7 +516,7 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
   const int tn_log2 = 6 - P.tw_log2 - P.th_log2;
   const int my_tiles = split < ptiles ? (ptiles - split + P.splits - 1) / P.splits : 0;
 
-  if constexpr (kWgProducers == 1) {
+  if (kWgProducers == 1) {
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
@@ -922,17 +923,17 @@ static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, con
   }
 }
 
-template <int NX>
+template <int NX, bool SMALL>
 static int launch_wgrad_t(const WgradParams& P, const CUtensorMap& mY, const CUtensorMap* mX, cudaStream_t s) {
-  using Cfg = WgCfg<NX>;
+  using Cfg = WgCfg<NX, SMALL>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<NX, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     MPGAN_REQUIRE(e == cudaSuccess, MPGAN_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
     attr_done = true;
   }
   int grid = P.m_blocks * P.ngroups * P.splits;
-  launch_k(wgrad_kernel<NX>, grid, 256, Cfg::SMEM_BYTES, s, P, mY, mX[0], mX[1], mX[2], mX[3]);
+  launch_k(wgrad_kernel<NX, SMALL>, grid, 256, Cfg::SMEM_BYTES, s, P, mY, mX[0], mX[1], mX[2], mX[3]);
   MPGAN_CHECK_LAUNCH("wgrad_kernel");
   return 0;
 }
@@ -944,6 +945,12 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
   WgradParams P;
   memset(&P, 0, sizeof(P));
   P.cx = g.cx; P.cy = g.cy; P.dw = dw;
+  {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("MPGAN_WG_NPROD"); forced = e ? atoi(e) : 0; }
+    P.nprod = g.cx <= 64 ? 7 : 1;
+    if (forced >= 1 && forced <= 7) P.nprod = forced;
+  }
   int ntap = 0;
   for (int rh = 0; rh < g.kh; ++rh)
     for (int rw = 0; rw < g.kw; ++rw) {
@@ -955,7 +962,10 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
       ++ntap;
     }
   P.ntaps = ntap;
-  const int max_tpg = (g.cx <= 64 ? 256 : 512) / g.cx;
+  // "small" = generator-sized layer (<= 1M output pixels): half of TMEM / ~100 KB of shared memory per CTA so that a
+  // CTA of the concurrent data-gradient chain fits on the same SM; large layers (D) take the whole SM
+  const bool small = g.cx <= 64 && (long long)g.n * g.yh * g.yw <= (1LL << 20);
+  const int max_tpg = (small ? 256 : 512) / g.cx;
   P.ngroups = (ntap + max_tpg - 1) / max_tpg;
   P.taps_per_group = (ntap + P.ngroups - 1) / P.ngroups;   // balanced groups
   P.m_blocks = (g.cy + 127) / 128;
@@ -964,7 +974,9 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
   P.tiles_w = (g.yw + tw - 1) / tw; P.tiles_h = (g.yh + th - 1) / th; P.tiles_n = (g.n + tn - 1) / tn;
   const int ptiles = P.tiles_w * P.tiles_h * P.tiles_n;
   const int items = P.m_blocks * P.ngroups;
-  int splits = (num_sms() + items - 1) / items;
+  // one CTA per SM for the large-channel configurations (~200 KB of shared memory each): the grid must not exceed the
+  // SM count or the few extra CTAs run as a second wave and double the kernel time (152 CTAs did, on 148 SMs)
+  int splits = !small ? num_sms() / items : (num_sms() + items - 1) / items;
   if (splits > ptiles) splits = ptiles;
   if (splits < 1) splits = 1;
   P.splits = splits;
@@ -981,11 +993,11 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
   int rc = make_act_maps(mX, x, g.n, g.xh, g.xw, g.cx, ldx, g.s, boxX);
   if (rc) return rc;
   switch (g.cx) {
-    case 16: return launch_wgrad_t<16>(P, mY, mX, s);
-    case 32: return launch_wgrad_t<32>(P, mY, mX, s);
-    case 64: return launch_wgrad_t<64>(P, mY, mX, s);
-    case 128: return launch_wgrad_t<128>(P, mY, mX, s);
-    default: return launch_wgrad_t<256>(P, mY, mX, s);
+    case 16: return small ? launch_wgrad_t<16, true>(P, mY, mX, s) : launch_wgrad_t<16, false>(P, mY, mX, s);
+    case 32: return small ? launch_wgrad_t<32, true>(P, mY, mX, s) : launch_wgrad_t<32, false>(P, mY, mX, s);
+    case 64: return small ? launch_wgrad_t<64, true>(P, mY, mX, s) : launch_wgrad_t<64, false>(P, mY, mX, s);
+    case 128: return launch_wgrad_t<128, false>(P, mY, mX, s);
+    default: return launch_wgrad_t<256, false>(P, mY, mX, s);
   }
 }
 
