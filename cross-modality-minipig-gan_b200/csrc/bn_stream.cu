@@ -359,7 +359,16 @@ static size_t stream_smem(int C, int nin, int* stages) {
 template <int MODE>
 static int launch_stream(bns::StreamParams& p, cudaStream_t s) {
   int stages;
-  const size_t smem = stream_smem(p.C, p.nin, &stages);
+  size_t smem = stream_smem(p.C, p.nin, &stages);
+  {
+    // generator-sized tensors (a few 16 KB chunks per CTA): two stages are enough, and the small footprint lets a CTA
+    // of the concurrent weight-gradient stream share the SM
+    const int64_t per_cta = ceil_div(ceil_div(p.total * 2, (int64_t)bns::kChunkBytes), (int64_t)num_sms());
+    if (per_cta <= 16 && stages > 2) {
+      smem -= (size_t)(stages - 2) * p.nin * bns::kChunkBytes;
+      stages = 2;
+    }
+  }
   p.stages = stages;
   static bool attr_done = false;
   if (!attr_done) {

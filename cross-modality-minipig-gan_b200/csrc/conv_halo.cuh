@@ -52,11 +52,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int N, int KC>   // KC = min(C, 64): channels per plane (one swizzle span)
-__global__ void __launch_bounds__(kHaloThreads, 1)
+__global__ void __launch_bounds__(kHaloThreads, 1) __maxnreg__(N <= 64 ? 128 : 168)
 halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUtensorMap tmA) {
   // accumulator ring: as many 128 x N fp32 tiles as fit in 512 TMEM columns (<= 8): small layers are bound by the
   // MMA -> epilogue -> MMA round trip, not by throughput, so the ring must be deep
-  constexpr int NACC = 512 / N > kMaxAcc ? kMaxAcc : 512 / N;
+  // N <= 64 (generator layers): at most half of TMEM, <= 128 registers per thread and (host side) a capped plane ring,
+  // so that a CTA of the concurrent weight-gradient stream fits on the same SM
+  constexpr int NACC = N <= 64 ? (256 / N > kMaxAcc ? kMaxAcc : 256 / N) : 512 / N;
   constexpr int TMEM_COLS = NACC * N < 32 ? 32 : NACC * N;
   // No static shared memory in this kernel, so the dynamic window starts at the CTA's (1024-byte aligned) base; using
   // the symbol directly (instead of a manually aligned pointer) lets the compiler emit LDS/STS rather than generic
@@ -344,6 +346,12 @@ static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, in
   if (w_bytes + 2 * a_bytes + aux > budget) return 1;
   int nbuf = (int)((budget - w_bytes - aux) / a_bytes);
   if (nbuf > kMaxBuf) nbuf = kMaxBuf;
+  const int total_tiles_ = n * ((ow + HT_W - 1) / HT_W) * ((oh + HT_H - 1) / HT_H);
+  if (N <= 64 && total_tiles_ <= 32 * num_sms()) {   // generator-sized layer: leave room for a second CTA on the SM
+    const int cap = (int)(((size_t)100 * 1024 > w_bytes + aux ? (size_t)100 * 1024 - w_bytes - aux : 0) / a_bytes);
+    const int floor_ = C > 64 ? 2 : 3;
+    if (nbuf > (cap > floor_ ? cap : floor_)) nbuf = cap > floor_ ? cap : floor_;
+  }
   HaloParams P;
   memset(&P, 0, sizeof(P));
   P.nimg = n; P.oh = oh; P.ow = ow; P.C = C; P.N = N;
