@@ -164,6 +164,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank, local = 0, 0
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MPGAN_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout (one JSON line)
         rank, world, local = ddp.init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

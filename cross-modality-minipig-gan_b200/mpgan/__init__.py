@@ -10,5 +10,6 @@ from . import _lib, ops  # noqa: F401
 from .gan import GAN  # noqa: F401
 from .nets import CasNetGenerator, Discriminator, PatchDiscriminator, UNet, DEFAULT_PRECISION  # noqa: F401
 from .runtime import FlatAdam, Runtime  # noqa: F401
+from . import inference, transforms  # noqa: F401,E402
 
 __all__ = ["GAN", "CasNetGenerator", "Discriminator", "PatchDiscriminator", "UNet", "FlatAdam", "Runtime"]

@@ -73,6 +73,8 @@ class GAN(nn.Module):
         self.variant = variant
         if variant == "perceptual":  # test_runs/GAN.py:238-250: a single lr (2e-4) for both optimisers
             g_lr = d_lr = 0.0002 if lr is None else lr
+        self._ctor_args = dict(channels=channels, width=width, height=height, depth=depth, variant=variant, lr=lr,
+                               precision=precision, n_unet_blocks=n_unet_blocks, num_samples=num_samples, roi=roi)
         self.hparams = _Hparams(latent_dim=latent_dim, g_lr=g_lr, d_lr=d_lr, b1=b1, b2=b2, batch_size=batch_size,
                                 one_sided_label_value=one_sided_label_value)
         data_shape = (channels, width, height) if depth is None else (channels, width, height, depth)
@@ -98,6 +100,54 @@ class GAN(nn.Module):
         self._opt = None
         self._graph = None
         self.comm = None  # set by mpgan.ddp.attach()
+
+    # ---------------------------------------------------------------- Lightning checkpoint wire format (8f, N3)
+    _CTOR_KEYS = ("channels", "width", "height", "depth", "latent_dim", "d_lr", "g_lr", "b1", "b2", "batch_size",
+                  "one_sided_label_value", "variant", "lr", "precision", "n_unet_blocks", "num_samples", "roi")
+
+    def save_checkpoint(self, path, epoch=0, global_step=0):
+        """Write a pytorch-lightning 1.2.1 style ``.ckpt`` (a ``torch.save``d dict with ``state_dict`` under the
+        reference's parameter names -- the module tree is the reference's -- and ``hyper_parameters``), the file
+        ``ModelCheckpoint`` produces at GAN_final.py:448-472 and ``load_from_checkpoint`` reads at
+        inferrence.py:97-106.  Logical (NC[D]HW / OI[D]HW) tensors, so the reference can load it back."""
+        hp = dict(self.hparams)
+        hp.update(self._ctor_args)
+        ckpt = {"epoch": int(epoch), "global_step": int(global_step), "pytorch-lightning_version": "1.2.1",
+                "state_dict": {k: v.detach().cpu().clone() for k, v in self.state_dict().items()},
+                "hyper_parameters": hp}
+        torch.save(ckpt, path)
+        return path
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, hparams_file=None, strict=True, **kwargs):
+        """``LightningModule.load_from_checkpoint`` as the reference calls it (inferrence.py:97-106): constructor
+        arguments come from the checkpoint's ``hyper_parameters``, then ``hparams_file`` (yaml), then ``kwargs``;
+        unknown keys (``img_shape`` ...) are ignored like the reference's ``**kwargs``."""
+        ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+        args = dict(ckpt.get("hyper_parameters", {}) or {})
+        if hparams_file is not None:
+            import yaml
+            with open(hparams_file) as f:
+                args.update(yaml.safe_load(f) or {})
+        args.update(kwargs)
+        ctor = {k: args[k] for k in cls._CTOR_KEYS if k in args}
+        for need in ("channels", "width", "height"):
+            if need not in ctor:
+                raise RuntimeError(f"checkpoint carries no '{need}': pass it to load_from_checkpoint like the reference does")
+        model = cls(**ctor)
+        state = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
+        result = model.load_state_dict(state, strict=strict)
+        for net in (model.generator, model.discriminator):
+            if net._runtime is not None:
+                net._runtime.mark_dirty()
+        model.load_result = result
+        return model
+
+    def freeze(self):
+        """LightningModule.freeze (inferrence.py:109): eval mode, no parameter gradients."""
+        for p in self.parameters():
+            p.requires_grad_(False)
+        return self.eval()
 
     # ---------------------------------------------------------------- reference surface
     def forward(self, x):
