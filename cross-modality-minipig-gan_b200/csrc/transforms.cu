@@ -114,6 +114,39 @@ __global__ void __launch_bounds__(kThreads) hist_lo_kernel(const float* __restri
   }
 }
 
+// ranks 0 and n-1 (the 0 / 100 percentiles of the post-processing transform) are a plain min / max reduction
+__global__ void __launch_bounds__(kThreads) minmax_key_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ mm) {
+  pdl_wait();
+  pdl_launch();
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = x4[i];
+    const uint32_t a = key_of(v.x), b = key_of(v.y), c = key_of(v.z), d = key_of(v.w);
+    lo = min(lo, min(min(a, b), min(c, d)));
+    hi = max(hi, max(max(a, b), max(c, d)));
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t a = key_of(x[i]);
+    lo = min(lo, a); hi = max(hi, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
+}
+
+__global__ void write_minmax_kernel(const uint32_t* __restrict__ mm, const int64_t* __restrict__ ranks, int nr,
+                                    float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
+  if ((int)threadIdx.x < nr) out[threadIdx.x] = value_of(ranks[threadIdx.x] == 0 ? mm[0] : mm[1]);
+}
+
 __global__ void write_values_kernel(const uint32_t* __restrict__ sel, int nr, float* __restrict__ out) {
   pdl_wait();
   pdl_launch();
@@ -182,6 +215,25 @@ using namespace mpgan;
 
 extern "C" size_t mpgan_order_stats_workspace(int32_t nranks) {
   return (size_t)65536 * 4 + (size_t)nranks * 65536 * 4 + 64 * 4;   // hi histogram, lo histograms, selection records
+}
+
+extern "C" int mpgan_minmax(const float* x, int64_t n, const int64_t* ranks_dev, int32_t nranks, float* out,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  MPGAN_REQUIRE(x && ranks_dev && out && workspace, MPGAN_ERR_SHAPE, "minmax: null pointer");
+  MPGAN_REQUIRE(n > 0, MPGAN_ERR_SHAPE, "minmax: empty volume");
+  MPGAN_REQUIRE(nranks >= 1 && nranks <= 4, MPGAN_ERR_UNSUPPORTED, "minmax: 1..4 ranks per call");
+  MPGAN_REQUIRE(workspace_bytes >= 8, MPGAN_ERR_SHAPE, "minmax: workspace too small");
+  MPGAN_REQUIRE(((uintptr_t)x & 15) == 0, MPGAN_ERR_SHAPE, "minmax: volume not 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  uint32_t* mm = (uint32_t*)workspace;
+  cudaError_t e = cudaMemsetAsync(mm, 0xff, 4, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(mm + 1, 0, 4, s);
+  MPGAN_REQUIRE(e == cudaSuccess, MPGAN_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  launch_k(xf::minmax_key_kernel, xf::grid_for(n, 32), xf::kThreads, 0, s, x, n, mm);
+  MPGAN_CHECK_LAUNCH("minmax_key_kernel");
+  launch_k(xf::write_minmax_kernel, 1, 32, 0, s, (const uint32_t*)mm, ranks_dev, (int)nranks, out);
+  MPGAN_CHECK_LAUNCH("write_minmax_kernel");
+  return 0;
 }
 
 extern "C" int mpgan_order_stats(const float* x, int64_t n, const int64_t* ranks_dev, int32_t nranks, float* out,

@@ -68,6 +68,7 @@ _SIGS = {
     "mpgan_patch_scatter_add": (c_int, [c_int, _P, c_int32, c_int32, _P, c_int32, _P, c_int32, c_int32, _P, _P]),
     "mpgan_order_stats_workspace": (c_size_t, [c_int32]),
     "mpgan_order_stats": (c_int, [_P, c_int64, _P, c_int32, _P, _P, c_size_t, _P]),
+    "mpgan_minmax": (c_int, [_P, c_int64, _P, c_int32, _P, _P, c_size_t, _P]),
     "mpgan_rescale_intensity": (c_int, [_P, c_int64, c_float, c_float, c_float, c_float, c_int, c_float, c_float, c_int,
                                         c_int, _P, _P]),
     "mpgan_err_sums": (c_int, [_P, _P, c_int64, _P, _P]),

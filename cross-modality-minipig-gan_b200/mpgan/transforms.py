@@ -25,8 +25,9 @@ def percentile_ranks(n, q):
     """np.percentile's linear interpolation: position q/100*(n-1) between two neighbouring order statistics."""
     pos = (q / 100.0) * (n - 1)
     lo = int(math.floor(pos))
-    hi = min(lo + 1, n - 1)
-    return lo, hi, pos - lo
+    frac = pos - lo
+    hi = lo if frac == 0 else min(lo + 1, n - 1)   # exact percentiles (0, 100, ...) need one order statistic only
+    return lo, hi, frac
 
 
 def order_statistics(x, ranks):
@@ -44,8 +45,12 @@ def order_statistics(x, ranks):
         o_dev = torch.empty(len(grp), dtype=torch.float32, device=x.device)
         nbytes = int(lib.mpgan_order_stats_workspace(len(grp)))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        check(lib.mpgan_order_stats(ptr(x), x.numel(), ptr(r_dev), len(grp), ptr(o_dev), ptr(ws), nbytes, _stream()),
-              "mpgan_order_stats")
+        if all(r in (0, x.numel() - 1) for r in grp):   # 0 / 100 percentiles: one min/max pass
+            check(lib.mpgan_minmax(ptr(x), x.numel(), ptr(r_dev), len(grp), ptr(o_dev), ptr(ws), nbytes, _stream()),
+                  "mpgan_minmax")
+        else:
+            check(lib.mpgan_order_stats(ptr(x), x.numel(), ptr(r_dev), len(grp), ptr(o_dev), ptr(ws), nbytes, _stream()),
+                  "mpgan_order_stats")
         out += o_dev.tolist()
     return out
 

@@ -191,6 +191,7 @@ int mpgan_patch_scatter_add(int dtype, const void* dpatch, int32_t batch, int32_
  * MeanAbsoluteError / MeanSquaredError (inferrence.py:170-176, metrics.py:213-218).
  * order_stats: out[r] = the ranks[r]-th smallest value (0-based, exact) of the fp32 volume x[0..n); ranks is a DEVICE
  *   array of nranks <= 4 int64; workspace of mpgan_order_stats_workspace(nranks) bytes (caller-owned, overwritten).
+ * minmax: the same contract restricted to ranks in {0, n-1} (the 0 / 100 percentiles): one min/max reduction pass.
  * rescale_intensity: y = ((x - a_min) / (a_max - a_min)) * (b_max - b_min) + b_min  (x - a_min + b_min when
  *   a_max == a_min), each step rounded to fp32; optional clip to [clip_lo, clip_hi]; optional round-half-even;
  *   out_dtype 0 = fp32, 2 = fp16.
@@ -198,6 +199,8 @@ int mpgan_patch_scatter_add(int dtype, const void* dpatch, int32_t batch, int32_
 size_t mpgan_order_stats_workspace(int32_t nranks);
 int mpgan_order_stats(const float* x, int64_t n, const int64_t* ranks, int32_t nranks, float* out, void* workspace,
                       size_t workspace_bytes, void* stream);
+int mpgan_minmax(const float* x, int64_t n, const int64_t* ranks, int32_t nranks, float* out, void* workspace,
+                 size_t workspace_bytes, void* stream);
 int mpgan_rescale_intensity(const float* x, int64_t n, float a_min, float a_max, float b_min, float b_max, int clip,
                             float clip_lo, float clip_hi, int round_half_even, int out_dtype, void* y, void* stream);
 int mpgan_err_sums(const float* a, const float* b, int64_t n, double* out2, void* stream);

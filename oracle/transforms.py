@@ -29,8 +29,9 @@ def percentile_ranks(n, q):
     """(lower rank, upper rank, fraction) of np.percentile(..., q) with linear interpolation."""
     pos = (q / 100.0) * (n - 1)
     lo = int(np.floor(pos))
-    hi = min(lo + 1, n - 1)
-    return lo, hi, pos - lo
+    frac = pos - lo
+    hi = lo if frac == 0 else min(lo + 1, n - 1)   # exact percentiles (0, 100, ...) need one order statistic only
+    return lo, hi, frac
 
 
 def percentile_f32(img, q):
