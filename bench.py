@@ -265,7 +265,10 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel<256,64> (D conv 128->256 k4 s2, batch 32)",
                          "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                         "peak_kind": f"{pk_kind} burst bf16", "kernel_ms": kms, "traffic": None},
+                         "peak_kind": f"{pk_kind} burst bf16", "kernel_ms": kms,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this
+                         # kernel on this shape (profiles/ncu_r1_s3_tapgemm256.md); algorithmic bytes are 776.2e6
+                         "traffic": 744.0e6, "traffic_unit": "B/launch", "algorithmic_bytes": 776.2e6},
             "losses": {"g_adv": final_logs[0], "g_recon": final_logs[1], "d_loss": final_logs[2] + final_logs[3]},
         }
         if world == 1 and not args.no_cpu_baseline:
