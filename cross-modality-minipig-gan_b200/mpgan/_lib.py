@@ -66,6 +66,8 @@ _SIGS = {
     "mpgan_weight_transpose": (c_int, [c_int, _P, c_int, _P, c_int32, c_int32, c_int32, _P]),
     "mpgan_patch_gather": (c_int, [c_int, _P, c_int32, c_int32, _P, c_int32, _P, c_int32, c_int32, _P, _P]),
     "mpgan_patch_scatter_add": (c_int, [c_int, _P, c_int32, c_int32, _P, c_int32, _P, c_int32, c_int32, _P, _P]),
+    "mpgan_im2col_c1": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "mpgan_fold_dw16": (c_int, [_P, c_int32, _P, _P]),
     "mpgan_order_stats_workspace": (c_size_t, [c_int32]),
     "mpgan_order_stats": (c_int, [_P, c_int64, _P, c_int32, _P, _P, c_size_t, _P]),
     "mpgan_minmax": (c_int, [_P, c_int64, _P, c_int32, _P, _P, c_size_t, _P]),

@@ -4,6 +4,7 @@ Activation tensors are channels-last ``(N, *spatial, C)`` with unit channel stri
 strides (a channel slice of a wider concat buffer is fine).
 """
 import ctypes
+import os
 
 import torch
 
@@ -146,14 +147,36 @@ def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True,
     return out, False
 
 
-def conv_wgrad(spec, x, y, dw, use_tc=True, use_c1=True):
+_C1COL = os.environ.get("MPGAN_NO_C1COL", "0") != "1"
+_SPEC_1X1 = {}
+
+
+def _spec_1x1(cx, cy):
+    if (cx, cy) not in _SPEC_1X1:
+        _SPEC_1X1[(cx, cy)] = ConvSpec(2, cx, cy, 1, 1, 0)
+    return _SPEC_1X1[(cx, cy)]
+
+
+def conv_wgrad(spec, x, y, dw, use_tc=True, use_c1=True, force_c1col=False):
     """dw[cy][taps][cx] (fp32, accumulates) from the X-grid tensor and the Y-grid tensor."""
     lib = _lib.require_device()
     check_act(x), check_act(y)
     n, xs, ys = x.shape[0], tuple(x.shape[1:-1]), tuple(y.shape[1:-1])
     g = spec.geom(n, xs, ys)
     assert dw.dtype == torch.float32
-    if use_tc and x.dtype == torch.bfloat16 and tc_supported(g, 2):
+    if (use_tc and use_c1 and x.dtype == torch.bfloat16 and spec.rank == 2 and spec.cx == 1 and spec.k == (3, 3)
+            and spec.cy % 16 == 0 and spec.cy <= 256 and ld(x) == 1 and x.is_contiguous() and _C1COL
+            and (force_c1col or n * ys[0] * ys[1] > (1 << 20))):   # measured: a win for D layer 1, not for G's 0.5M-pixel layers
+        # one input channel: im2col (9 taps -> 16 "channels") + the tcgen05 weight gradient of the equivalent 1x1 layer
+        xcol = torch.empty((n,) + ys + (16,), dtype=torch.bfloat16, device=x.device)
+        check(lib.mpgan_im2col_c1(ptr(x), n, xs[0], xs[1], ys[0], ys[1], spec.stride[0], spec.pad[0], ptr(xcol),
+                                  _stream()), "im2col_c1")
+        dw16 = torch.zeros((spec.cy, 16), dtype=torch.float32, device=x.device)
+        g1 = _spec_1x1(16, spec.cy).geom(n, ys, ys)
+        check(lib.mpgan_tc_conv_wgrad(ctypes.byref(g1), ptr(xcol), 16, ptr(y), ld(y), ptr(dw16), None, 0, _stream()),
+              "tc_conv_wgrad(im2col)")
+        check(lib.mpgan_fold_dw16(ptr(dw16), spec.cy, ptr(dw), _stream()), "fold_dw16")
+    elif use_tc and x.dtype == torch.bfloat16 and tc_supported(g, 2):
         check(lib.mpgan_tc_conv_wgrad(ctypes.byref(g), ptr(x), ld(x), ptr(y), ld(y), ptr(dw), None, 0, _stream()),
               "tc_conv_wgrad")
     elif use_c1 and lib.mpgan_c1_supported(ctypes.byref(g), 2):

@@ -185,6 +185,14 @@ int mpgan_patch_scatter_add(int dtype, const void* dpatch, int32_t batch, int32_
                             int32_t c, const int32_t* origins, int32_t num_samples, int32_t roi, void* dvol,
                             void* stream);
 
+/* ---- one-input-channel 3x3 weight gradient through the tensor cores (conv_c1col.cu) ----
+ * im2col_c1: x (n, ih, iw) contiguous bf16, one channel -> xcol (n, oh, ow, 16) bf16: the 9 taps of every output pixel
+ *   (zero padded borders) followed by 7 zeros.  The weight gradient is then mpgan_tc_conv_wgrad of the 1x1 layer
+ *   xcol(16) -> dY(cy) into a zeroed fp32 dw16[cy][16], and fold_dw16 adds dw16[c][t<9] into dw[c][9]. */
+int mpgan_im2col_c1(const void* x_bf16, int32_t n, int32_t ih, int32_t iw, int32_t oh, int32_t ow, int32_t stride,
+                    int32_t pad, void* xcol_bf16, void* stream);
+int mpgan_fold_dw16(const float* dw16, int32_t cy, float* dw, void* stream);
+
 /* ---- intensity transforms / volume metrics around the generator ----
  * MONAI ScaleIntensityRangePercentilesd (reference: GAN_final.py:386-394 lower=1 upper=99 -> [-1,1];
  * inferrence.py:152-160,190-198 lower=0 upper=100 -> [0,255] followed by np.round) and torchmetrics

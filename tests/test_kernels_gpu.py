@@ -94,6 +94,22 @@ def test_conv_generic_fwd_dgrad_wgrad(case, dtype, use_c1):
     assert rel_l2(db, dy.sum(dim=[0] + list(range(2, rank + 2)))) <= 1e-4
 
 
+@pytest.mark.parametrize("n,cout,size,s,p", [(2, 64, 40, 1, 0), (3, 16, 48, 2, 1), (2, 32, 30, 2, 1), (1, 64, 19, 1, 0)])
+def test_c1_wgrad_through_tensor_cores(n, cout, size, s, p):
+    """One-input-channel weight gradient = im2col + tcgen05 1x1 weight gradient + fold (conv_c1col.cu); accumulates."""
+    x = rnd(n, 1, size, size, seed=1).bfloat16().float()
+    w = (rnd(cout, 1, 3, 3, seed=2) * 0.2).requires_grad_(True)
+    y = F.conv2d(x, w, None, stride=s, padding=p)
+    dy = rnd(*y.shape, seed=4).bfloat16().float()
+    y.backward(dy)
+    spec = ops.ConvSpec(2, 1, cout, 3, s, p)
+    dw = torch.ones(cout, 9, 1, device=DEV)                    # pre-existing content must be accumulated onto
+    calls0 = ops._lib.ABI_CALLS
+    ops.conv_wgrad(spec, cl(x, torch.bfloat16), cl(dy, torch.bfloat16), dw, force_c1col=True)
+    assert ops._lib.ABI_CALLS - calls0 == 3                    # im2col, tcgen05 wgrad, fold: the composite path ran
+    assert rel_l2(dw - 1.0, oti(w.grad)) <= 6e-3
+
+
 def test_conv_transpose_is_bprop():
     """ConvTranspose2d(k3,s2,p1,op1) forward == bprop of the underlying conv with the same OTI weight."""
     ct = torch.nn.ConvTranspose2d(24, 8, 3, stride=2, padding=1, output_padding=1).to(DEV)
