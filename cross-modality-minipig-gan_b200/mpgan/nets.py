@@ -44,6 +44,7 @@ class Plan:
         self._arena_used = 0
         self.keepalive = []        # tensors read by weight-gradient kernels still in flight on the "wgrad" stream
         self.wgrad_forked = False
+        self.wgrad_count = 0
 
     ARENA = 1 << 15  # fp64 slots: every BatchNorm statistic / backward sum of one pass, zeroed by ONE memset
 
@@ -73,6 +74,7 @@ def conv_apply(rec, x, out=None, stats=None):
 
 
 _SIDE = {}
+N_WGRAD_STREAMS = int(os.environ.get("MPGAN_WGRAD_STREAMS", "1"))   # measured: 2-4 streams give nothing
 
 
 def side_stream(device, which="branch"):
@@ -89,7 +91,8 @@ def side_stream(device, which="branch"):
 def join_wgrad(plan, device):
     """End of a backward pass: the optimizer (or the caller) may read the weight gradients after this."""
     if plan.wgrad_forked:
-        torch.cuda.current_stream().wait_stream(side_stream(device, "wgrad"))
+        for i in range(N_WGRAD_STREAMS):
+            torch.cuda.current_stream().wait_stream(side_stream(device, f"wgrad{i}"))
         plan.wgrad_forked = False
     plan.keepalive.clear()
 
@@ -120,7 +123,8 @@ def conv_backward(rec, x, dy, plan, need_dx, bias_done=False):
         wgrad()
         return dgrad() if need_dx else None
     cur = torch.cuda.current_stream()
-    side = side_stream(dy.device, "wgrad")
+    side = side_stream(dy.device, f"wgrad{plan.wgrad_count % N_WGRAD_STREAMS}")   # round robin: wgrads are independent
+    plan.wgrad_count += 1
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         wgrad()
@@ -374,7 +378,11 @@ class UNet(nn.Module):
         cd = down.out_channels
         dh = up[1]._bwd(dy, plan)
         dcat = up[0]._bwd(dh, plan)
+        # the sub-block's gradient is the upper channel slice of dcat: one packing copy (7 us) lets its BatchNorm
+        # backward run on the contiguous streaming kernels (2 x 8 us) instead of the strided ones (2 x 20 us)
         dsub = dcat[..., cd:]
+        if dsub.dtype == torch.bfloat16 and os.environ.get("MPGAN_NO_PACK_DSUB", "0") != "1":
+            dsub = ops.add_copy(dsub, None, _new(dsub, dsub.shape))
         if isinstance(sub, ResidualUnit):
             dxd_sub = sub._bwd(dsub, plan)
         else:
