@@ -42,6 +42,8 @@ struct HaloParams {
   long long out_sn, out_sh, out_sw;
   const float* bias;
   double* stats;
+  const bf16* res;     // optional tensor added to the result before rounding (same grid as out)
+  long long res_sn, res_sh, res_sw;
   uint32_t idesc;
 };
 
@@ -221,7 +223,9 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
-        epi_chunk_store<CH>(r, s_bias + c0, orow, valid, P.stats != nullptr, s1, s2);
+        const bf16* rrow = P.res ? P.res + (long long)img * P.res_sn + (long long)oh * P.res_sh + (long long)ow * P.res_sw + c0
+                                 : nullptr;
+        epi_chunk_store<CH>(r, s_bias + c0, orow, valid, P.stats != nullptr, s1, s2, rrow);
       }
       if (P.stats) {
         float v[32];
@@ -258,6 +262,11 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         for (int j = 0; j < CH / 2; ++j) {
           float f0 = __uint_as_float(r[2 * j]), f1 = __uint_as_float(r[2 * j + 1]);
           f0 += s_bias[c0 + 2 * j]; f1 += s_bias[c0 + 2 * j + 1];
+          if (P.res && valid) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(P.res + (long long)img * P.res_sn + (long long)oh * P.res_sh +
+                                                                   (long long)ow * P.res_sw + c0 + 2 * j);
+            f0 += __uint_as_float(u << 16); f1 += __uint_as_float(u & 0xffff0000u);
+          }
           __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
           packed[j] = *reinterpret_cast<uint32_t*>(&h);
         }
@@ -334,10 +343,11 @@ static int launch_halo(const HaloParams& P, const CUtensorMap& mA, size_t smem, 
 // gradient (w = transposed shadow [N=cx][9][C=cy], taps flipped).  Returns 1 when the layer is not covered.
 static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, int N, int pad, const void* in,
                        int64_t ldi, const void* w, const float* bias, void* out, int64_t ldo, double* stats,
-                       cudaStream_t s) {
+                       const void* res, int64_t ldres, cudaStream_t s) {
   if (!(C == 16 || C == 32 || C == 64 || C == 128)) return 1;
   if (!(N == 16 || N == 32 || N == 64 || N == 128)) return 1;
   if (ldi % 8 != 0 || ldo % 8 != 0 || ((uintptr_t)in & 15) || ((uintptr_t)out & 15) || ((uintptr_t)w & 15)) return 1;
+  if (res && (ldres % 8 != 0 || ((uintptr_t)res & 15))) return 1;
   const int KC = C < 64 ? C : 64;
   const size_t w_bytes = ((size_t)9 * C * N * 2 + 1023) & ~(size_t)1023;
   const size_t a_bytes = ((size_t)HPIX * KC * 2 + 1023) & ~(size_t)1023;   // one <= 64-channel plane
@@ -363,6 +373,8 @@ static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, in
   P.w = (const bf16*)w; P.out = (bf16*)out;
   P.out_sn = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo; P.out_sw = ldo;
   P.bias = bias; P.stats = stats;
+  P.res = (const bf16*)res;
+  P.res_sn = (long long)oh * ow * ldres; P.res_sh = (long long)ow * ldres; P.res_sw = ldres;
   P.idesc = make_idesc_bf16(128, N, 0, 0);
   CUtensorMap mA;
   {

@@ -53,6 +53,9 @@ struct TapGemmParams {
   bf16* out;
   const float* bias;
   double* stats;
+  const bf16* res;     // optional tensor added to the result before rounding (same grid / classes as out)
+  long long res_sn, res_sh, res_sw;
+  long long cls_res_off[MAXCLS];
 };
 
 struct WgradParams {
@@ -347,7 +350,10 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);   // values are in registers: the accumulator is free again
-        epi_chunk_store<CH>(r, s_bias + nbase + c0, orow, valid, P.stats != nullptr, s1, s2);
+        const bf16* rrow = P.res ? P.res + P.cls_res_off[cls] + (long long)img * P.res_sn + (long long)oh * P.res_sh +
+                                       (long long)ow * P.res_sw + nbase + c0
+                                 : nullptr;
+        epi_chunk_store<CH>(r, s_bias + nbase + c0, orow, valid, P.stats != nullptr, s1, s2, rrow);
       }
       if (P.stats && stat_base >= 0) flush();
     } else {
@@ -380,6 +386,20 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + s_bias[nbase + c0 + j];
+        if (P.res && valid) {
+          const bf16* rrow = P.res + P.cls_res_off[cls] + (long long)img * P.res_sn + (long long)oh * P.res_sh +
+                             (long long)ow * P.res_sw + nbase + c0;
+#pragma unroll
+          for (int j = 0; j < CH / 8; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(rrow + j * 8);
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[8 * j + 2 * e] += __uint_as_float(u[e] << 16);
+              v[8 * j + 2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u);
+            }
+          }
+        }
         uint32_t packed[CH / 2];
 #pragma unroll
         for (int j = 0; j < CH / 2; ++j) {
@@ -826,14 +846,14 @@ static bool halo_enabled() {
 
 // common driver for fprop (dir 0) and bprop (dir 1)
 static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, const void* w, const float* bias, void* out,
-                       int64_t ldo, double* stats, cudaStream_t s) {
+                       int64_t ldo, double* stats, cudaStream_t s, const void* res = nullptr, int64_t ldres = 0) {
   const int C = dir == 0 ? g.cx : g.cy;  // reduced channels
   const int N = dir == 0 ? g.cy : g.cx;  // produced channels
   const int ih = dir == 0 ? g.xh : g.yh, iw = dir == 0 ? g.xw : g.yw;
   const int oh = dir == 0 ? g.yh : g.xh, ow = dir == 0 ? g.yw : g.xw;
   const int T = g.kh * g.kw;
   if (g.s == 1 && g.kh == 3 && g.kw == 3 && g.ph == g.pw && g.ph <= 1 && halo_enabled()) {
-    int rc = halo3x3_run(dir, g.n, ih, iw, oh, ow, C, N, g.ph, in, ldi, w, bias, out, ldo, stats, s);
+    int rc = halo3x3_run(dir, g.n, ih, iw, oh, ow, C, N, g.ph, in, ldi, w, bias, out, ldo, stats, res, ldres, s);
     if (rc != 1) return rc;
   }
   const int KC = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
@@ -851,6 +871,8 @@ static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, con
   P.out = (bf16*)out;
   P.bias = bias;
   P.stats = stats;
+  P.res = (const bf16*)res;
+  MPGAN_REQUIRE(!res || (ldres % 8 == 0 && ((uintptr_t)res & 15) == 0), MPGAN_ERR_SHAPE, "residual tensor misaligned");
   MPGAN_REQUIRE(N <= 512, MPGAN_ERR_UNSUPPORTED, "N > 512");
 
   int ntap = 0;
@@ -869,8 +891,9 @@ static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, con
         ++ntap;
       }
     P.cls_tap_begin[1] = ntap;
-    P.cls_oh[0] = oh; P.cls_ow[0] = ow; P.cls_out_off[0] = 0;
+    P.cls_oh[0] = oh; P.cls_ow[0] = ow; P.cls_out_off[0] = 0; P.cls_res_off[0] = 0;
     P.out_sn = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo; P.out_sw = ldo;
+    P.res_sn = (long long)oh * ow * ldres; P.res_sh = (long long)ow * ldres; P.res_sw = ldres;
     loh = oh; low = ow;
   } else {  // gather Y: ypos = (xpos + pad - r)/s
     P.ncls = g.s * g.s;
@@ -892,9 +915,11 @@ static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, con
         P.cls_oh[cls] = (oh - cph + g.s - 1) / g.s;
         P.cls_ow[cls] = (ow - cpw + g.s - 1) / g.s;
         P.cls_out_off[cls] = ((long long)cph * ow + cpw) * ldo;
+        P.cls_res_off[cls] = ((long long)cph * ow + cpw) * ldres;
       }
     P.cls_tap_begin[P.ncls] = ntap;
     P.out_sn = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo * g.s; P.out_sw = ldo * g.s;
+    P.res_sn = (long long)oh * ow * ldres; P.res_sh = (long long)ow * ldres * g.s; P.res_sw = ldres * g.s;
     loh = (oh + g.s - 1) / g.s; low = (ow + g.s - 1) / g.s;
   }
   (void)T;
@@ -1031,6 +1056,15 @@ extern "C" int mpgan_tc_conv_bprop(const MpganConvGeom* g, const void* y, int64_
   int rc = to_geom2(g, &g2);
   if (rc) return rc;
   return run_tapgemm(g2, 1, y, ldy, w_b, bias, x, ldx, stats, (cudaStream_t)stream);
+}
+
+extern "C" int mpgan_tc_conv_bprop_res(const MpganConvGeom* g, const void* y, int64_t ldy, const void* w_b,
+                                       const float* bias, void* x, int64_t ldx, const void* res, int64_t ldres,
+                                       double* stats, void* stream) {
+  Geom2 g2;
+  int rc = to_geom2(g, &g2);
+  if (rc) return rc;
+  return run_tapgemm(g2, 1, y, ldy, w_b, bias, x, ldx, stats, (cudaStream_t)stream, res, ldres);
 }
 
 extern "C" size_t mpgan_tc_conv_wgrad_workspace(const MpganConvGeom* g) {

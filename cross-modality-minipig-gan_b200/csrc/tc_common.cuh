@@ -157,15 +157,29 @@ __device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
 
 // One CH-column chunk of one accumulator row: + bias -> bf16 -> 16-byte stores at `orow`, and (optionally) the
 // BatchNorm statistics of the values AS STORED, accumulated in per-thread packed registers s1 / s2 (CH/2 pairs each).
+// `rrow` (optional): a bf16 row of the same shape added before rounding (fused residual / gradient accumulation).
 template <int CH>
 __device__ __forceinline__ void epi_chunk_store(const uint32_t (&r)[CH], const float* s_bias_c0, bf16* orow, bool valid,
                                                 bool do_stats, unsigned long long (&s1)[CH / 2],
-                                                unsigned long long (&s2)[CH / 2]) {
+                                                unsigned long long (&s2)[CH / 2], const bf16* rrow = nullptr) {
   const unsigned long long ones = pack_f32x2(1.f, 1.f);
   uint32_t packed[CH / 2];
+  uint32_t rq[CH / 2];
+  const bool has_res = rrow != nullptr && valid;
+  if (has_res) {
+#pragma unroll
+    for (int j = 0; j < CH / 8; ++j) {
+      const uint4 q = *reinterpret_cast<const uint4*>(rrow + j * 8);
+      rq[4 * j] = q.x; rq[4 * j + 1] = q.y; rq[4 * j + 2] = q.z; rq[4 * j + 3] = q.w;
+    }
+  }
 #pragma unroll
   for (int j = 0; j < CH / 4; ++j) {
-    const float4 b = *reinterpret_cast<const float4*>(s_bias_c0 + 4 * j);
+    float4 b = *reinterpret_cast<const float4*>(s_bias_c0 + 4 * j);
+    if (has_res) {
+      b.x += __uint_as_float(rq[2 * j] << 16); b.y += __uint_as_float(rq[2 * j] & 0xffff0000u);
+      b.z += __uint_as_float(rq[2 * j + 1] << 16); b.w += __uint_as_float(rq[2 * j + 1] & 0xffff0000u);
+    }
     const float2 v0 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), ones,
                                              pack_f32x2(b.x, b.y)));
     const float2 v1 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), ones,

@@ -97,9 +97,10 @@ def join_wgrad(plan, device):
     plan.keepalive.clear()
 
 
-def conv_backward(rec, x, dy, plan, need_dx, bias_done=False):
+def conv_backward(rec, x, dy, plan, need_dx, bias_done=False, res=None):
     """x: the layer's input, dy: gradient of its output (contiguous or sliced).  Returns dx or None.
     bias_done: the bias gradient was already accumulated by the fused BatchNorm backward.
+    res: a tensor of dx's shape added to it (gradient of a parallel branch) -- fused into the convolution's epilogue.
     The weight gradient only shares inputs with the data gradient: it is issued on the "wgrad" stream and not
     waited for until the end of the pass; (x, dy) are kept alive until then so the allocator cannot recycle them."""
     spec = rec.spec
@@ -114,8 +115,9 @@ def conv_backward(rec, x, dy, plan, need_dx, bias_done=False):
 
     def dgrad():
         if spec.transposed:
-            return ops.conv_fprop(spec, dy, rec.w, None)[0]
-        return ops.conv_bprop(spec, dy, rec.w, rec.wt, None, xs=tuple(x.shape[1:-1]))[0]
+            dx = ops.conv_fprop(spec, dy, rec.w, None)[0]
+            return ops.add_copy(dx, res, dx) if res is not None else dx
+        return ops.conv_bprop(spec, dy, rec.w, rec.wt, None, xs=tuple(x.shape[1:-1]), res=res)[0]
 
     if not plan.need_wgrad:
         return dgrad() if need_dx else None
@@ -211,14 +213,14 @@ class Convolution(nn.Sequential):
             plan.tape.append((x, c, saved, plan.training))
         return y
 
-    def _bwd(self, dy, plan, need_dx=True):
+    def _bwd(self, dy, plan, need_dx=True, res=None):
         rec = plan.rt.rec[self.conv]
         if self.conv_only:
             (x,) = plan.tape.pop()
-            return conv_backward(rec, x, dy, plan, need_dx)
+            return conv_backward(rec, x, dy, plan, need_dx, res=res)
         x, c, saved, trained = plan.tape.pop()
         dc = bn_act_backward(dy, c, saved, self.norm, ACT_PRELU, self.act.weight, 0.0, plan, trained, conv_db=rec.db)
-        return conv_backward(rec, x, dc, plan, need_dx, bias_done=True)
+        return conv_backward(rec, x, dc, plan, need_dx, bias_done=True, res=res)
 
 
 class ResidualUnit(nn.Module):
@@ -277,7 +279,9 @@ class ResidualUnit(nn.Module):
             plan.tape.append((x,))
         return y
 
-    def _bwd(self, dy, plan, need_dx=True):
+    def _bwd(self, dy, plan, need_dx=True, res=None):
+        """res: gradient of a branch parallel to the whole unit, added to the returned dx.  The branch sums
+        (dx = main-path dgrad + residual-branch dgrad [+ res]) ride in the epilogues of the data-gradient kernels."""
         (x,) = plan.tape.pop()
         has_res_conv = not isinstance(self.residual, nn.Identity)
         units = list(self.conv)
@@ -287,20 +291,22 @@ class ResidualUnit(nn.Module):
                 cur, side = torch.cuda.current_stream(), side_stream(dy.device)
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
-                    dr = conv_backward(plan.rt.rec[self.residual], x, dy, plan, need_dx)
+                    dr = conv_backward(plan.rt.rec[self.residual], x, dy, plan, need_dx, res=res)
                 forked = True
             else:
-                dr = conv_backward(plan.rt.rec[self.residual], x, dy, plan, need_dx)
+                dr = conv_backward(plan.rt.rec[self.residual], x, dy, plan, need_dx, res=res)
+        elif res is not None and need_dx:
+            dr = ops.add_copy(dy, res, _new(dy, dy.shape))
         else:
             dr = dy
         dh = dy
         for i in range(len(units) - 1, -1, -1):
-            dh = units[i]._bwd(dh, plan, need_dx=(need_dx or i > 0))
-        if forked:
-            cur.wait_stream(side)
+            if i == 0 and forked:
+                cur.wait_stream(side)   # the first unit's data gradient accumulates onto the residual branch's
+            dh = units[i]._bwd(dh, plan, need_dx=(need_dx or i > 0), res=dr if (i == 0 and need_dx) else None)
         if not need_dx:
             return None
-        return ops.add_copy(dh, dr, _new(dh, dh.shape))
+        return dh
 
 
 class SkipConnection(nn.Module):
@@ -372,7 +378,7 @@ class UNet(nn.Module):
         return up[1]._fwd(h, plan, out=out)
 
     @staticmethod
-    def _block_bwd(block, dy, plan, need_dx=True):
+    def _block_bwd(block, dy, plan, need_dx=True, res=None):
         down, skip, up = block[0], block[1], block[2]
         sub = skip.submodule
         cd = down.out_channels
@@ -383,12 +389,14 @@ class UNet(nn.Module):
         dsub = dcat[..., cd:]
         if dsub.dtype == torch.bfloat16 and os.environ.get("MPGAN_NO_PACK_DSUB", "0") != "1":
             dsub = ops.add_copy(dsub, None, _new(dsub, dsub.shape))
+        # d(down output) = skip slice of dcat + the sub-block's input gradient: the slice is handed down as `res` and
+        # added in the epilogue of the sub-block's last data-gradient kernel
+        dskip = dcat[..., :cd]
         if isinstance(sub, ResidualUnit):
-            dxd_sub = sub._bwd(dsub, plan)
+            dxd = sub._bwd(dsub, plan, res=dskip)
         else:
-            dxd_sub = UNet._block_bwd(sub, dsub, plan)
-        dxd = ops.add_copy(dcat[..., :cd], dxd_sub, _new(dxd_sub, dxd_sub.shape))
-        return down._bwd(dxd, plan, need_dx=need_dx)
+            dxd = UNet._block_bwd(sub, dsub, plan, res=dskip)
+        return down._bwd(dxd, plan, need_dx=need_dx, res=res)
 
     def _fwd(self, x, plan, out=None):
         return UNet._block_fwd(self.model, x, plan, out=out)

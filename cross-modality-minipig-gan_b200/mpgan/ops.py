@@ -123,8 +123,10 @@ def conv_fprop(spec, x, w, bias, out=None, stats=None, use_tc=True, use_c1=True)
     return out, False
 
 
-def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True, use_c1=True):
-    """Y-grid tensor -> X-grid tensor (ConvTranspose forward; Conv data gradient)."""
+def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True, use_c1=True, res=None):
+    """Y-grid tensor -> X-grid tensor (ConvTranspose forward; Conv data gradient).  ``res``: an X-grid tensor added
+    to the result (gradient accumulation of a residual / skip branch) -- fused into the tcgen05 epilogue, otherwise
+    one add kernel after the convolution."""
     lib = _lib.require_device()
     check_act(y, "conv input")
     n, ys = y.shape[0], tuple(y.shape[1:-1])
@@ -135,15 +137,25 @@ def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True,
     check_act(out, "conv output")
     g = spec.geom(n, xs, ys)
     if use_tc and wt is not None and y.dtype == torch.bfloat16 and tc_supported(g, 1):
+        if res is not None and res.dtype == torch.bfloat16 and ld(res) % 8 == 0 and res.data_ptr() % 16 == 0:
+            check(lib.mpgan_tc_conv_bprop_res(ctypes.byref(g), ptr(y), ld(y), ptr(wt), ptr(bias), ptr(out), ld(out),
+                                              ptr(res), ld(res), ptr(stats), _stream()), "tc_conv_bprop_res")
+            return out, stats is not None
         check(lib.mpgan_tc_conv_bprop(ctypes.byref(g), ptr(y), ld(y), ptr(wt), ptr(bias), ptr(out), ld(out), ptr(stats),
                                       _stream()), "tc_conv_bprop")
+        if res is not None:
+            add_copy(out, res, out)
         return out, stats is not None
     if use_c1 and lib.mpgan_c1_supported(ctypes.byref(g), 1):
         check(lib.mpgan_c1_conv_bprop(ctypes.byref(g), dt(y), ptr(y), ld(y), ptr(w), ptr(bias), ptr(out), ld(out),
                                       ptr(stats), _stream()), "c1_conv_bprop")
+        if res is not None:
+            add_copy(out, res, out)
         return out, stats is not None
     check(lib.mpgan_conv_bprop(ctypes.byref(g), dt(y), ptr(y), ld(y), ptr(w), ptr(bias), ptr(out), ld(out), _stream()),
           "conv_bprop")
+    if res is not None:
+        add_copy(out, res, out)
     return out, False
 
 

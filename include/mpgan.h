@@ -72,6 +72,10 @@ int mpgan_tc_conv_fprop(const MpganConvGeom* g, const void* x, int64_t ldx, cons
                         void* y, int64_t ldy, double* stats, void* stream);
 int mpgan_tc_conv_bprop(const MpganConvGeom* g, const void* y, int64_t ldy, const void* w_b, const float* bias,
                         void* x, int64_t ldx, double* stats, void* stream);
+/* same, with a bf16 tensor `res` (pixel stride ldres, the X grid) added to the result before rounding: fuses the
+ * gradient accumulation of residual / skip branches (dx = dgrad(dy) + res) into the convolution's epilogue */
+int mpgan_tc_conv_bprop_res(const MpganConvGeom* g, const void* y, int64_t ldy, const void* w_b, const float* bias,
+                            void* x, int64_t ldx, const void* res, int64_t ldres, double* stats, void* stream);
 /* workspace_bytes from mpgan_tc_conv_wgrad_workspace(); dw accumulates (fp32 [cy][taps][cx]). */
 size_t mpgan_tc_conv_wgrad_workspace(const MpganConvGeom* g);
 int mpgan_tc_conv_wgrad(const MpganConvGeom* g, const void* x, int64_t ldx, const void* y, int64_t ldy, float* dw,
