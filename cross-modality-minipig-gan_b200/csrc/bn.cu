@@ -567,6 +567,96 @@ extern "C" int mpgan_bn_train_apply(int dtype, const void* x, int64_t ldx, int64
                                                         leaky_slope, res, ldres, y, ldy, vec, (cudaStream_t)stream));
 }
 
+namespace mpgan {
+
+// ------------------------------------------------------------------------------------------------------------
+// Tail of every UNet of the generator (MONAI UNet top level, is_top: ConvT(32->1) -> BatchNorm(1) -> PReLU ->
+// ResidualUnit(1->1, conv only, identity residual)):   h = prelu(bn(c));  y = conv3x3(h) + bias + h
+// on a ONE-channel full-resolution image.  Three launches (BatchNorm apply, one-channel convolution, residual add)
+// of 10-17 us each on a 4 MB tensor become one stencil kernel: the BatchNorm coefficients come from the fp64 statistics
+// that the ConvTranspose epilogue reduced, each thread transforms its 3 x 6 window of c on the fly (h is rounded to
+// bf16 exactly as the unfused path stores it) and produces 4 output pixels; h itself is written only when the
+// backward pass needs it.  Block 0 updates the running statistics and the saved mean / invstd / scale / shift.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+c1_tail_fwd_kernel(const bf16* __restrict__ c, int n, int H, int W, const BnTrain f, const float* __restrict__ alpha,
+                   const bf16* __restrict__ w9, const float* __restrict__ bias, bf16* __restrict__ h_out,
+                   bf16* __restrict__ y_out) {
+  pdl_wait();
+  pdl_launch();
+  const int64_t P = (int64_t)n * H * W;
+  float sc, sh;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && f.nbt) *f.nbt += 1;
+  bn_train_coeffs(f, 0, 1, P, blockIdx.x == 0 && threadIdx.x == 0, sc, sh);
+  const float slope = *alpha;
+  float wt[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wt[t] = to_f(w9[t]);
+  const float b = bias ? bias[0] : 0.f;
+  const int wq = (W + 3) / 4;                       // 4-pixel runs per row
+  const int64_t runs = (int64_t)n * H * wq;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < runs; r += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(r % wq);
+    const int64_t row = r / wq;
+    const int hh = (int)(row % H), img = (int)(row / H);
+    const int w0 = q * 4;
+    const bf16* ci = c + (int64_t)img * H * W;
+    float hv[3][6];
+#pragma unroll
+    for (int rh = 0; rh < 3; ++rh) {
+      const int y = hh - 1 + rh;
+      const bool oky = (unsigned)y < (unsigned)H;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int x = w0 - 1 + j;
+        float v = 0.f;
+        if (oky && (unsigned)x < (unsigned)W) {
+          const float z = fmaf(to_f(ci[(int64_t)y * W + x]), sc, sh);
+          v = to_f(from_f<bf16>(z > 0.f ? z : slope * z));     // h as the unfused path stores it
+        }
+        hv[rh][j] = v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (w0 + i >= W) break;
+      float a = b;
+#pragma unroll
+      for (int rh = 0; rh < 3; ++rh)
+#pragma unroll
+        for (int rw = 0; rw < 3; ++rw) a = fmaf(hv[rh][i + rw], wt[rh * 3 + rw], a);
+      const float hc = hv[1][i + 1];
+      const int64_t o = ((int64_t)img * H + hh) * W + w0 + i;
+      if (h_out) h_out[o] = from_f<bf16>(hc);
+      y_out[o] = from_f<bf16>(to_f(from_f<bf16>(a)) + hc);     // conv result rounded, then the residual add (two kernels before)
+    }
+  }
+}
+
+}  // namespace mpgan
+
+extern "C" int mpgan_c1_tail_fwd(const void* c_bf16, int32_t n, int32_t h, int32_t w, const double* stats,
+                                 const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                                 float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd,
+                                 float* scale, float* shift, const float* alpha, const void* w9_bf16, const float* bias,
+                                 void* h_out_bf16, void* y_out_bf16, void* stream) {
+  MPGAN_REQUIRE(c_bf16 && stats && scale && shift && alpha && w9_bf16 && y_out_bf16, MPGAN_ERR_SHAPE,
+                "c1_tail_fwd: null pointer");
+  MPGAN_REQUIRE(n > 0 && h > 0 && w > 0, MPGAN_ERR_SHAPE, "c1_tail_fwd: empty tensor");
+  BnTrain f;
+  f.stats = stats; f.gamma = gamma; f.beta = beta; f.eps = eps; f.momentum = momentum;
+  f.running_mean = running_mean; f.running_var = running_var; f.nbt = num_batches_tracked;
+  f.mean_out = mean; f.invstd_out = invstd; f.scale_out = scale; f.shift_out = shift;
+  const int64_t runs = (int64_t)n * h * ((w + 3) / 4);
+  int64_t blocks = ceil_div(runs, (int64_t)kThreads);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  launch_k(c1_tail_fwd_kernel, (int)blocks, kThreads, 0, (cudaStream_t)stream, (const bf16*)c_bf16, (int)n, (int)h, (int)w, f,
+           alpha, (const bf16*)w9_bf16, bias, (bf16*)h_out_bf16, (bf16*)y_out_bf16);
+  MPGAN_CHECK_LAUNCH("c1_tail_fwd_kernel");
+  return 0;
+}
+
 extern "C" int mpgan_bn_act_bwd_reduce(int dtype, const void* dy, int64_t lddy, const void* x, int64_t ldx,
                                        int64_t pixels, int32_t c, const float* mean, const float* invstd,
                                        const float* scale, const float* shift, int act, const float* alpha,

@@ -374,8 +374,34 @@ class UNet(nn.Module):
             sub._fwd(xd, plan, out=cat[..., cd:])
         else:
             UNet._block_fwd(sub, xd, plan, out=cat[..., cd:])
+        fused = UNet._tail_fwd(up, cat, plan, out)
+        if fused is not None:
+            return fused
         h = up[0]._fwd(cat, plan)
         return up[1]._fwd(h, plan, out=out)
+
+    @staticmethod
+    def _tail_fwd(up, cat, plan, out):
+        """Top level of a 2-D bf16 UNet in training mode: ConvT(->1) + BatchNorm(1) + PReLU + ResidualUnit(1->1, conv
+        only) run as the ConvTranspose (with fused statistics) plus ONE stencil kernel; the tape is the one the
+        unfused layers would have recorded.  Returns None when the pattern does not apply."""
+        conv0, ru = up[0], up[1]
+        if (out is not None or not plan.training or plan.dtype != torch.bfloat16 or conv0.out_channels != 1
+                or conv0.conv_only or cat.dim() != 4 or len(ru.conv) != 1 or not ru.conv[0].conv_only
+                or not isinstance(ru.residual, nn.Identity) or os.environ.get("MPGAN_NO_TAIL_FUSION", "0") == "1"):
+            return None
+        rec0, rec1 = plan.rt.rec[conv0.conv], plan.rt.rec[ru.conv[0].conv]
+        stats = plan.zeros64(2, cat.device)
+        c, fused_stats = conv_apply(rec0, cat, stats=stats)
+        if not fused_stats:
+            ops.bn_stats(c, stats)
+        saved = torch.empty((4, 1), dtype=torch.float32, device=c.device)
+        h, y = ops.c1_tail_fwd(c, stats, conv0.norm, saved, conv0.act.weight, rec1.w, rec1.bias, plan.save)
+        if plan.save:
+            plan.tape.append((cat, c, (saved[0], saved[1], saved[2], saved[3]), plan.training))   # Convolution (ConvT)
+            plan.tape.append((h,))                                                              # conv-only Convolution
+            plan.tape.append((h,))                                                              # ResidualUnit
+        return y
 
     @staticmethod
     def _block_bwd(block, dy, plan, need_dx=True, res=None):

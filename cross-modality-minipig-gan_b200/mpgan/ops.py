@@ -244,6 +244,21 @@ def bn_train_apply(x, stats, bn, saved, act, alpha, leaky, res, out):
     return out
 
 
+def c1_tail_fwd(c, stats, bn, saved, alpha, w9, bias, want_h):
+    """Fused UNet tail on a one-channel bf16 image (n, h, w, 1): returns (hmap or None, y)."""
+    lib = _lib.require_device()
+    assert c.dtype == torch.bfloat16 and c.is_contiguous() and c.shape[-1] == 1 and c.dim() == 4
+    n, h, w = c.shape[0], c.shape[1], c.shape[2]
+    hmap = torch.empty_like(c) if want_h else None
+    y = torch.empty_like(c)
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    check(lib.mpgan_c1_tail_fwd(ptr(c), n, h, w, ptr(stats), ptr(bn.weight), ptr(bn.bias), bn.eps, mom,
+                                ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked), ptr(saved[0]),
+                                ptr(saved[1]), ptr(saved[2]), ptr(saved[3]), ptr(alpha), ptr(w9), ptr(bias), ptr(hmap),
+                                ptr(y), _stream()), "c1_tail_fwd")
+    return hmap, y
+
+
 def bn_act_bwd(dy, x, mean, invstd, scale, shift, act, alpha, leaky, sums, dgamma, dbeta, dalpha, dx, dbias=None):
     lib = _lib.require_device()
     check_act(dy), check_act(x), check_act(dx)

@@ -189,6 +189,17 @@ int mpgan_patch_scatter_add(int dtype, const void* dpatch, int32_t batch, int32_
                             int32_t c, const int32_t* origins, int32_t num_samples, int32_t roi, void* dvol,
                             void* stream);
 
+/* ---- fused tail of a generator UNet (MONAI UNet top level: ConvT(..->1) -> BatchNorm(1) -> PReLU -> ResidualUnit(1->1,
+ * conv only), call site GAN_final.py:106-114) on a one-channel (n, h, w) bf16 image, training mode:
+ *   hmap = prelu(batchnorm(c));  y = conv3x3(hmap, w9, pad 1) + bias + hmap
+ * stats: the fp64 {sum, sum of squares} of c; running statistics / saved mean, invstd, scale, shift are updated as by
+ * mpgan_bn_train_apply.  h_out may be NULL (no backward pass will follow). */
+int mpgan_c1_tail_fwd(const void* c_bf16, int32_t n, int32_t h, int32_t w, const double* stats, const float* gamma,
+                      const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                      int64_t* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
+                      const float* alpha, const void* w9_bf16, const float* bias, void* h_out_bf16, void* y_out_bf16,
+                      void* stream);
+
 /* ---- one-input-channel 3x3 weight gradient through the tensor cores (conv_c1col.cu) ----
  * im2col_c1: x (n, ih, iw) contiguous bf16, one channel -> xcol (n, oh, ow, 16) bf16: the 9 taps of every output pixel
  *   (zero padded borders) followed by 7 zeros.  The weight gradient is then mpgan_tc_conv_wgrad of the 1x1 layer
