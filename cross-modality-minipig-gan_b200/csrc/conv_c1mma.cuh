@@ -26,6 +26,7 @@ struct C1mmaParams {
   int xrow;                 // bytes per row of an input window in shared memory (box width * 2)
   uint32_t xbytes;          // bytes of one window (TMA transaction size)
   int xoff;                 // column of the window's first needed pixel (the TMA start is kept 16-byte aligned)
+  int wide;                 // output rows 32-byte aligned: 256-bit stores
   int dbg;                  // timing experiments (MPGAN_C1_DBG): 1 = no global stores, 2 = no window reads
   const bf16* w;            // [N][9]
   bf16* out;
@@ -203,7 +204,7 @@ c1mma_fprop_kernel(const __grid_constant__ C1mmaParams P, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (!(P.dbg & 8)) epi_chunk_store<CH>(r, s_bias + c0, orow, valid && !(P.dbg & 1), P.stats != nullptr, s1, s2);
+      if (!(P.dbg & 8)) epi_chunk_store<CH>(r, s_bias + c0, orow, valid && !(P.dbg & 1), P.stats != nullptr, s1, s2, nullptr, P.wide != 0);
     }
     if (P.stats) {
       float v[32];
@@ -286,6 +287,7 @@ int c1mma_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, c
   P.out = (bf16*)y;
   P.out_sn = (long long)P.oh * P.ow * ldy; P.out_sh = (long long)P.ow * ldy; P.out_sw = ldy;
   P.bias = bias; P.stats = stats;
+  P.wide = (ldy % 16 == 0 && ((uintptr_t)y & 31) == 0) ? 1 : 0;
   { const char* e = getenv("MPGAN_C1_DBG"); P.dbg = e ? atoi(e) : 0; }
   switch (N) {
     case 16: return launch_c1mma<16>(P, mX, s);

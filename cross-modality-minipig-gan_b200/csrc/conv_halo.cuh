@@ -44,6 +44,7 @@ struct HaloParams {
   double* stats;
   const bf16* res;     // optional tensor added to the result before rounding (same grid as out)
   long long res_sn, res_sh, res_sw;
+  int wide;            // output rows are 32-byte aligned: 256-bit stores
   uint32_t idesc;
 };
 
@@ -225,7 +226,7 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive(&tempty[acc]);
         const bf16* rrow = P.res ? P.res + (long long)img * P.res_sn + (long long)oh * P.res_sh + (long long)ow * P.res_sw + c0
                                  : nullptr;
-        epi_chunk_store<CH>(r, s_bias + c0, orow, valid, P.stats != nullptr, s1, s2, rrow);
+        epi_chunk_store<CH>(r, s_bias + c0, orow, valid, P.stats != nullptr, s1, s2, rrow, P.wide != 0);
       }
       if (P.stats) {
         float v[32];
@@ -271,10 +272,17 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
           packed[j] = *reinterpret_cast<uint32_t*>(&h);
         }
         if (valid) {
+          if (P.wide) {
 #pragma unroll
-          for (int j = 0; j < CH / 8; ++j)
-            *reinterpret_cast<uint4*>(orow + c0 + j * 8) =
-                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            for (int j = 0; j < CH / 16; ++j)
+              st_global_256(orow + c0 + j * 16, packed[8 * j], packed[8 * j + 1], packed[8 * j + 2], packed[8 * j + 3],
+                            packed[8 * j + 4], packed[8 * j + 5], packed[8 * j + 6], packed[8 * j + 7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j)
+              *reinterpret_cast<uint4*>(orow + c0 + j * 8) =
+                  make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          }
         }
         if (P.stats) {  // statistics of the values as stored: transpose through shared memory
           constexpr int WPR = CH / 2;           // bf16x2 words per row; lane = (row part, column pair)
@@ -373,6 +381,7 @@ static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, in
   P.w = (const bf16*)w; P.out = (bf16*)out;
   P.out_sn = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo; P.out_sw = ldo;
   P.bias = bias; P.stats = stats;
+  P.wide = (ldo % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
   P.res = (const bf16*)res;
   P.res_sn = (long long)oh * ow * ldres; P.res_sh = (long long)ow * ldres; P.res_sw = ldres;
   P.idesc = make_idesc_bf16(128, N, 0, 0);

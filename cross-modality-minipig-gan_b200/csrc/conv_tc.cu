@@ -56,6 +56,7 @@ struct TapGemmParams {
   const bf16* res;     // optional tensor added to the result before rounding (same grid / classes as out)
   long long res_sn, res_sh, res_sw;
   long long cls_res_off[MAXCLS];
+  int wide;            // output rows are 32-byte aligned: 256-bit stores
 };
 
 struct WgradParams {
@@ -353,7 +354,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         const bf16* rrow = P.res ? P.res + P.cls_res_off[cls] + (long long)img * P.res_sn + (long long)oh * P.res_sh +
                                        (long long)ow * P.res_sw + nbase + c0
                                  : nullptr;
-        epi_chunk_store<CH>(r, s_bias + nbase + c0, orow, valid, P.stats != nullptr, s1, s2, rrow);
+        epi_chunk_store<CH>(r, s_bias + nbase + c0, orow, valid, P.stats != nullptr, s1, s2, rrow, P.wide != 0);
       }
       if (P.stats && stat_base >= 0) flush();
     } else {
@@ -412,10 +413,17 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
           }
         }
         if (valid) {
+          if (P.wide) {
 #pragma unroll
-          for (int j = 0; j < CH / 8; ++j)
-            *reinterpret_cast<uint4*>(orow + c0 + j * 8) =
-                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            for (int j = 0; j < CH / 16; ++j)
+              st_global_256(orow + c0 + j * 16, packed[8 * j], packed[8 * j + 1], packed[8 * j + 2], packed[8 * j + 3],
+                            packed[8 * j + 4], packed[8 * j + 5], packed[8 * j + 6], packed[8 * j + 7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j)
+              *reinterpret_cast<uint4*>(orow + c0 + j * 8) =
+                  make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          }
         }
         if (P.stats) {
           float sq[32];
@@ -871,6 +879,7 @@ static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, con
   P.out = (bf16*)out;
   P.bias = bias;
   P.stats = stats;
+  P.wide = (ldo % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
   P.res = (const bf16*)res;
   MPGAN_REQUIRE(!res || (ldres % 8 == 0 && ((uintptr_t)res & 15) == 0), MPGAN_ERR_SHAPE, "residual tensor misaligned");
   MPGAN_REQUIRE(N <= 512, MPGAN_ERR_UNSUPPORTED, "N > 512");

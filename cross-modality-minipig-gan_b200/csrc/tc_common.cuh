@@ -155,13 +155,22 @@ __device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
   return f;
 }
 
+// 32-byte store (sm_100 STG.256): one full sector per thread instead of two half-sector writes
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                              uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+               "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+
 // One CH-column chunk of one accumulator row: + bias -> bf16 -> 16-byte stores at `orow`, and (optionally) the
 // BatchNorm statistics of the values AS STORED, accumulated in per-thread packed registers s1 / s2 (CH/2 pairs each).
 // `rrow` (optional): a bf16 row of the same shape added before rounding (fused residual / gradient accumulation).
 template <int CH>
 __device__ __forceinline__ void epi_chunk_store(const uint32_t (&r)[CH], const float* s_bias_c0, bf16* orow, bool valid,
                                                 bool do_stats, unsigned long long (&s1)[CH / 2],
-                                                unsigned long long (&s2)[CH / 2], const bf16* rrow = nullptr) {
+                                                unsigned long long (&s2)[CH / 2], const bf16* rrow = nullptr,
+                                                bool wide = false) {
   const unsigned long long ones = pack_f32x2(1.f, 1.f);
   uint32_t packed[CH / 2];
   uint32_t rq[CH / 2];
@@ -190,10 +199,17 @@ __device__ __forceinline__ void epi_chunk_store(const uint32_t (&r)[CH], const f
     packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
   }
   if (valid) {
+    if (wide) {   // row address 32-byte aligned
 #pragma unroll
-    for (int j = 0; j < CH / 8; ++j)
-      *reinterpret_cast<uint4*>(orow + j * 8) =
-          make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      for (int j = 0; j < CH / 16; ++j)
+        st_global_256(orow + j * 16, packed[8 * j], packed[8 * j + 1], packed[8 * j + 2], packed[8 * j + 3], packed[8 * j + 4],
+                      packed[8 * j + 5], packed[8 * j + 6], packed[8 * j + 7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH / 8; ++j)
+        *reinterpret_cast<uint4*>(orow + j * 8) =
+            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    }
     if (do_stats) {
 #pragma unroll
       for (int j = 0; j < CH / 2; ++j) {
