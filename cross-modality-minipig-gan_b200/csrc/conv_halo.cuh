@@ -45,6 +45,7 @@ struct HaloParams {
   const bf16* res;     // optional tensor added to the result before rounding (same grid as out)
   long long res_sn, res_sh, res_sw;
   int wide;            // output rows are 32-byte aligned: 256-bit stores
+  int n_store;         // 0 = all N channels; 1 = only channel 0 (one-channel output computed with a zero-padded N = 16)
   uint32_t idesc;
 };
 
@@ -226,6 +227,14 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive(&tempty[acc]);
         const bf16* rrow = P.res ? P.res + (long long)img * P.res_sn + (long long)oh * P.res_sh + (long long)ow * P.res_sw + c0
                                  : nullptr;
+        if (P.n_store == 1) {   // one real output channel (data gradient of a one-input-channel layer)
+          if (valid && c0 == 0) {
+            float v = __uint_as_float(r[0]) + s_bias[0];
+            if (rrow) v += to_f(rrow[0]);
+            orow[0] = from_f<bf16>(v);
+          }
+          continue;
+        }
         epi_chunk_store<CH>(r, s_bias + c0, orow, valid, P.stats != nullptr, s1, s2, rrow, P.wide != 0);
       }
       if (P.stats) {
@@ -351,11 +360,16 @@ static int launch_halo(const HaloParams& P, const CUtensorMap& mA, size_t smem, 
 // gradient (w = transposed shadow [N=cx][9][C=cy], taps flipped).  Returns 1 when the layer is not covered.
 static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, int N, int pad, const void* in,
                        int64_t ldi, const void* w, const float* bias, void* out, int64_t ldo, double* stats,
-                       const void* res, int64_t ldres, cudaStream_t s) {
+                       const void* res, int64_t ldres, cudaStream_t s, int n_store = 0) {
   if (!(C == 16 || C == 32 || C == 64 || C == 128)) return 1;
   if (!(N == 16 || N == 32 || N == 64 || N == 128)) return 1;
-  if (ldi % 8 != 0 || ldo % 8 != 0 || ((uintptr_t)in & 15) || ((uintptr_t)out & 15) || ((uintptr_t)w & 15)) return 1;
-  if (res && (ldres % 8 != 0 || ((uintptr_t)res & 15))) return 1;
+  if (ldi % 8 != 0 || ((uintptr_t)in & 15) || ((uintptr_t)w & 15)) return 1;
+  if (n_store == 0) {
+    if (ldo % 8 != 0 || ((uintptr_t)out & 15)) return 1;
+    if (res && (ldres % 8 != 0 || ((uintptr_t)res & 15))) return 1;
+  } else if (N != 16 || stats) {
+    return 1;
+  }
   const int KC = C < 64 ? C : 64;
   const size_t w_bytes = ((size_t)9 * C * N * 2 + 1023) & ~(size_t)1023;
   const size_t a_bytes = ((size_t)HPIX * KC * 2 + 1023) & ~(size_t)1023;   // one <= 64-channel plane
@@ -381,7 +395,8 @@ static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, in
   P.w = (const bf16*)w; P.out = (bf16*)out;
   P.out_sn = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo; P.out_sw = ldo;
   P.bias = bias; P.stats = stats;
-  P.wide = (ldo % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
+  P.wide = (n_store == 0 && ldo % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
+  P.n_store = n_store;
   P.res = (const bf16*)res;
   P.res_sn = (long long)oh * ow * ldres; P.res_sh = (long long)ow * ldres; P.res_sw = ldres;
   P.idesc = make_idesc_bf16(128, N, 0, 0);

@@ -1076,6 +1076,24 @@ extern "C" int mpgan_tc_conv_bprop_res(const MpganConvGeom* g, const void* y, in
   return run_tapgemm(g2, 1, y, ldy, w_b, bias, x, ldx, stats, (cudaStream_t)stream, res, ldres);
 }
 
+// Data gradient of a ONE-input-channel stride-1 3x3 convolution (D layer 1: dY has 64 channels, dX one): the
+// halo-resident kernel with the transposed weights zero-padded to N = 16 output columns, of which only column 0 is
+// stored.  w_b16: bf16 [16][9][cy] (row 0 = the layer's transposed weights, rows 1..15 zero).
+extern "C" int mpgan_tc_conv_bprop_c1out(const MpganConvGeom* g, const void* y, int64_t ldy, const void* w_b16,
+                                         void* x, int64_t ldx, const void* res, int64_t ldres, void* stream) {
+  MPGAN_REQUIRE(g && g->rank == 2 && g->cx == 1, MPGAN_ERR_UNSUPPORTED, "bprop_c1out: rank-2 layer with one input channel");
+  MPGAN_REQUIRE(g->k[1] == 3 && g->k[2] == 3 && g->stride[1] == 1 && g->stride[2] == 1 && g->pad[1] == g->pad[2] &&
+                    g->pad[1] >= 0 && g->pad[1] <= 1,
+                MPGAN_ERR_UNSUPPORTED, "bprop_c1out: 3x3, stride 1, pad 0 or 1");
+  MPGAN_REQUIRE(g->cy == 16 || g->cy == 32 || g->cy == 64 || g->cy == 128, MPGAN_ERR_UNSUPPORTED,
+                "bprop_c1out: cy in {16, 32, 64, 128}");
+  MPGAN_REQUIRE(y && w_b16 && x && ldx >= 1, MPGAN_ERR_SHAPE, "bprop_c1out: bad arguments");
+  int rc = halo3x3_run(1, g->n, g->ys[1], g->ys[2], g->xs[1], g->xs[2], g->cy, 16, g->pad[1], y, ldy, w_b16, nullptr, x, ldx,
+                       nullptr, res, ldres, (cudaStream_t)stream, 1);
+  MPGAN_REQUIRE(rc != 1, MPGAN_ERR_UNSUPPORTED, "bprop_c1out: layer not covered by the halo kernel (alignment / size)");
+  return rc;
+}
+
 extern "C" size_t mpgan_tc_conv_wgrad_workspace(const MpganConvGeom* g) {
   (void)g;
   return 0;  // split partials are reduced with fp32 atomics straight into dw

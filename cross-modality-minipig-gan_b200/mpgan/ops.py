@@ -123,7 +123,11 @@ def conv_fprop(spec, x, w, bias, out=None, stats=None, use_tc=True, use_c1=True)
     return out, False
 
 
-def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True, use_c1=True, res=None):
+_C1OUT = os.environ.get("MPGAN_NO_C1OUT", "0") != "1"
+
+
+def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True, use_c1=True, res=None,
+               force_c1out=False):
     """Y-grid tensor -> X-grid tensor (ConvTranspose forward; Conv data gradient).  ``res``: an X-grid tensor added
     to the result (gradient accumulation of a residual / skip branch) -- fused into the tcgen05 epilogue, otherwise
     one add kernel after the convolution."""
@@ -136,6 +140,16 @@ def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True,
         out = torch.empty((n,) + tuple(xs) + (spec.cx,), dtype=y.dtype, device=y.device)
     check_act(out, "conv output")
     g = spec.geom(n, xs, ys)
+    if (use_tc and use_c1 and w is not None and w.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and spec.rank == 2 and spec.cx == 1
+            and spec.k == (3, 3) and spec.stride == (1, 1) and spec.cy in (16, 32, 64, 128) and stats is None
+            and bias is None and ld(y) % 8 == 0 and (res is None or res.dtype == torch.bfloat16) and _C1OUT
+            and (force_c1out or n * xs[0] * xs[1] > (1 << 20))):
+        # one input channel, large layer (D layer 1): the halo tcgen05 kernel with the weights zero-padded to 16 columns
+        wt16 = torch.zeros((16, 9, spec.cy), dtype=torch.bfloat16, device=y.device)
+        wt16[0].copy_(w.reshape(spec.cy, 9).t())   # [cy][9][1] -> transposed [9][cy]
+        check(lib.mpgan_tc_conv_bprop_c1out(ctypes.byref(g), ptr(y), ld(y), ptr(wt16), ptr(out), ld(out), ptr(res),
+                                            ld(res) if res is not None else 0, _stream()), "tc_conv_bprop_c1out")
+        return out, False
     if use_tc and wt is not None and y.dtype == torch.bfloat16 and tc_supported(g, 1):
         if res is not None and res.dtype == torch.bfloat16 and ld(res) % 8 == 0 and res.data_ptr() % 16 == 0:
             check(lib.mpgan_tc_conv_bprop_res(ctypes.byref(g), ptr(y), ld(y), ptr(wt), ptr(bias), ptr(out), ld(out),

@@ -74,6 +74,11 @@ int mpgan_tc_conv_bprop(const MpganConvGeom* g, const void* y, int64_t ldy, cons
                         void* x, int64_t ldx, double* stats, void* stream);
 /* same, with a bf16 tensor `res` (pixel stride ldres, the X grid) added to the result before rounding: fuses the
  * gradient accumulation of residual / skip branches (dx = dgrad(dy) + res) into the convolution's epilogue */
+/* data gradient of a one-input-channel stride-1 3x3 layer (cx == 1; dY has cy in {16,32,64,128} channels) through the
+ * halo-resident tcgen05 kernel: w_b16 = bf16 [16][9][cy], row 0 the layer's transposed weights, rows 1..15 zero;
+ * x: (n, xh, xw) one channel, pixel stride ldx; res (optional, same layout, stride ldres) is added. */
+int mpgan_tc_conv_bprop_c1out(const MpganConvGeom* g, const void* y, int64_t ldy, const void* w_b16, void* x,
+                              int64_t ldx, const void* res, int64_t ldres, void* stream);
 int mpgan_tc_conv_bprop_res(const MpganConvGeom* g, const void* y, int64_t ldy, const void* w_b, const float* bias,
                             void* x, int64_t ldx, const void* res, int64_t ldres, double* stats, void* stream);
 /* workspace_bytes from mpgan_tc_conv_wgrad_workspace(); dw accumulates (fp32 [cy][taps][cx]). */

@@ -110,6 +110,24 @@ def test_c1_wgrad_through_tensor_cores(n, cout, size, s, p):
     assert rel_l2(dw - 1.0, oti(w.grad)) <= 6e-3
 
 
+@pytest.mark.parametrize("n,cout,size,p", [(2, 64, 40, 0), (3, 16, 33, 1), (1, 128, 24, 0)])
+def test_c1_dgrad_through_tensor_cores(n, cout, size, p):
+    """Data gradient of a one-input-channel stride-1 layer = halo tcgen05 kernel with weights padded to 16 columns."""
+    x = rnd(n, 1, size, size, seed=1).requires_grad_(True)
+    w = (rnd(cout, 1, 3, 3, seed=2) * 0.2).bfloat16().float()
+    y = F.conv2d(x, w, None, stride=1, padding=p)
+    dy = rnd(*y.shape, seed=4).bfloat16().float()
+    y.backward(dy)
+    spec = ops.ConvSpec(2, 1, cout, 3, 1, p)
+    wo = oti(w, torch.bfloat16).reshape(cout, 9, 1)
+    wt = None   # one-input-channel layers keep no transposed shadow
+    r = rnd(n, size, size, 1, seed=5).bfloat16()
+    dx, _ = ops.conv_bprop(spec, cl(dy, torch.bfloat16), wo, wt, None, xs=(size, size), force_c1out=True)
+    assert rel_l2(uncl(dx), x.grad) <= 6e-3
+    dx2, _ = ops.conv_bprop(spec, cl(dy, torch.bfloat16), wo, wt, None, xs=(size, size), force_c1out=True, res=r)
+    assert rel_l2(dx2.float() - r.float(), dx.float()) <= 6e-3
+
+
 def test_conv_transpose_is_bprop():
     """ConvTranspose2d(k3,s2,p1,op1) forward == bprop of the underlying conv with the same OTI weight."""
     ct = torch.nn.ConvTranspose2d(24, 8, 3, stride=2, padding=1, output_padding=1).to(DEV)
