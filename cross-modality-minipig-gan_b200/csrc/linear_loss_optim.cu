@@ -2,6 +2,8 @@
 // Replaces nn.Linear + nn.Sigmoid (/root/reference/code/GAN/GAN_final.py:199-204), F.binary_cross_entropy and
 // F.l1_loss (GAN_final.py:244-248), torch.optim.Adam (GAN_final.py:298-308) and the RandSpatialCropSamplesd
 // slicing + torch.cat of /root/reference/test_runs/GAN.py:313-337.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mpgan {
@@ -69,6 +71,68 @@ __global__ void linear_dw_kernel(const T* __restrict__ x, const float* __restric
     float acc = 0.f;
     for (int b = 0; b < B; ++b) acc = fmaf(dy[(int64_t)b * J + j], to_f(x[(int64_t)b * K + k]), acc);
     dw[i] += acc;
+  }
+}
+
+// 8-wide bf16 variants (K % 8 == 0, 16-byte aligned rows): one 16-byte access per operand, the batch / output index in
+// blockIdx.y (no 64-bit divisions).  The scalar kernels above cover fp32 and ragged shapes.
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const uint32_t v[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(v[i] << 16); f[2 * i + 1] = __uint_as_float(v[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint32_t v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    v[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(v[0], v[1], v[2], v[3]);
+}
+
+__global__ void __launch_bounds__(256) linear_dx_vec_kernel(const bf16* __restrict__ w, const float* __restrict__ dy,
+                                                            bf16* __restrict__ dx, int64_t K8, int J) {
+  pdl_wait();
+  pdl_launch();
+  const int b = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < K8; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int j = 0; j < J; ++j) {
+      float wv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w + (int64_t)j * K8 * 8) + i), wv);
+      const float g = dy[b * J + j];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(g, wv[e], acc[e]);
+    }
+    reinterpret_cast<uint4*>(dx + (int64_t)b * K8 * 8)[i] = pack8(acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) linear_dw_vec_kernel(const bf16* __restrict__ x, const float* __restrict__ dy,
+                                                            float* __restrict__ dw, int B, int64_t K8, int J) {
+  pdl_wait();
+  pdl_launch();
+  const int j = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < K8; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 4
+    for (int b = 0; b < B; ++b) {
+      float xv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + (int64_t)b * K8 * 8) + i), xv);
+      const float g = dy[(int64_t)b * J + j];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(g, xv[e], acc[e]);
+    }
+    float4* o = reinterpret_cast<float4*>(dw + ((int64_t)j * K8 + i) * 8);
+    float4 a = o[0], c = o[1];
+    a.x += acc[0]; a.y += acc[1]; a.z += acc[2]; a.w += acc[3];
+    c.x += acc[4]; c.y += acc[5]; c.z += acc[6]; c.w += acc[7];
+    o[0] = a; o[1] = c;
   }
 }
 
@@ -259,12 +323,17 @@ extern "C" int mpgan_linear_bwd(int dtype, const void* x, const void* w, const f
   MPGAN_REQUIRE(batch > 0 && k > 0 && j > 0 && dy, MPGAN_ERR_SHAPE, "linear_bwd: bad shape");
   cudaStream_t s = (cudaStream_t)stream;
   MPGAN_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = sizeof(T) == 2 && k % 8 == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)x & 15) == 0 &&
+                     ((uintptr_t)dx & 15) == 0 && ((uintptr_t)dw & 15) == 0 && batch <= 65535 && j <= 65535;
+    const int vgrid = (int)std::min<int64_t>(ceil_div(k / 8, (int64_t)256), (int64_t)num_sms() * 8);
     if (dx) {
-      launch_k(linear_dx_kernel<T>, ew_grid((int64_t)batch * k), 256, 0, s, (const T*)w, dy, (T*)dx, batch, k, j);
+      if (vec) launch_k(linear_dx_vec_kernel, dim3(vgrid, batch), 256, 0, s, (const bf16*)w, dy, (bf16*)dx, k / 8, j);
+      else launch_k(linear_dx_kernel<T>, ew_grid((int64_t)batch * k), 256, 0, s, (const T*)w, dy, (T*)dx, batch, k, j);
       MPGAN_CHECK_LAUNCH("linear_dx");
     }
     if (dw) {
-      launch_k(linear_dw_kernel<T>, ew_grid((int64_t)j * k), 256, 0, s, (const T*)x, dy, dw, batch, k, j);
+      if (vec) launch_k(linear_dw_vec_kernel, dim3(vgrid, j), 256, 0, s, (const bf16*)x, dy, dw, batch, k / 8, j);
+      else launch_k(linear_dw_kernel<T>, ew_grid((int64_t)j * k), 256, 0, s, (const T*)x, dy, dw, batch, k, j);
       MPGAN_CHECK_LAUNCH("linear_dw");
     }
     if (db) {
