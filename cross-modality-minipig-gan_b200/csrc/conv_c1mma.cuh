@@ -27,7 +27,6 @@ struct C1mmaParams {
   uint32_t xbytes;          // bytes of one window (TMA transaction size)
   int xoff;                 // column of the window's first needed pixel (the TMA start is kept 16-byte aligned)
   int wide;                 // output rows 32-byte aligned: 256-bit stores
-  int dbg;                  // timing experiments (MPGAN_C1_DBG): 1 = no global stores, 2 = no window reads
   const bf16* w;            // [N][9]
   bf16* out;
   long long out_sn, out_sh, out_sw;
@@ -124,11 +123,6 @@ c1mma_fprop_kernel(const __grid_constant__ C1mmaParams P, const __grid_constant_
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int m = lane + 32 * k;
-        if (P.dbg & 2) {
-#pragma unroll
-          for (int t = 0; t < 9; ++t) v[k][t] = 0x3f80u;
-          continue;
-        }
         const uint8_t* p0 = xw + ((m >> 3) * S) * P.xrow + ((m & 7) * S + P.xoff) * 2;
 #pragma unroll
         for (int rh = 0; rh < 3; ++rh)
@@ -149,7 +143,7 @@ c1mma_fprop_kernel(const __grid_constant__ C1mmaParams P, const __grid_constant_
             v[k][0] | (v[k][1] << 16), v[k][2] | (v[k][3] << 16), v[k][4] | (v[k][5] << 16), v[k][6] | (v[k][7] << 16));
         *reinterpret_cast<uint4*>(rowp + ((1u ^ sw) << 4)) = make_uint4(v[k][8], 0u, 0u, 0u);
       }
-      if (!(P.dbg & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tcgen05.mma reads
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tcgen05.mma reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[stage]);
     }
@@ -204,7 +198,7 @@ c1mma_fprop_kernel(const __grid_constant__ C1mmaParams P, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (!(P.dbg & 8)) epi_chunk_store<CH>(r, s_bias + c0, orow, valid && !(P.dbg & 1), P.stats != nullptr, s1, s2, nullptr, P.wide != 0);
+      epi_chunk_store<CH>(r, s_bias + c0, orow, valid, P.stats != nullptr, s1, s2, nullptr, P.wide != 0);
     }
     if (P.stats) {
       float v[32];
@@ -288,7 +282,6 @@ int c1mma_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, c
   P.out_sn = (long long)P.oh * P.ow * ldy; P.out_sh = (long long)P.ow * ldy; P.out_sw = ldy;
   P.bias = bias; P.stats = stats;
   P.wide = (ldy % 16 == 0 && ((uintptr_t)y & 31) == 0) ? 1 : 0;
-  { const char* e = getenv("MPGAN_C1_DBG"); P.dbg = e ? atoi(e) : 0; }
   switch (N) {
     case 16: return launch_c1mma<16>(P, mX, s);
     case 32: return launch_c1mma<32>(P, mX, s);

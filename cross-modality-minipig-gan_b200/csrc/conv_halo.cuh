@@ -45,6 +45,7 @@ struct HaloParams {
   const bf16* res;     // optional tensor added to the result before rounding (same grid as out)
   long long res_sn, res_sh, res_sw;
   int wide;            // output rows are 32-byte aligned: 256-bit stores
+  const float* slope;  // optional device scalar: PReLU applied to (acc + bias) before the residual (inference fusion)
   int n_store;         // 0 = all N channels; 1 = only channel 0 (one-channel output computed with a zero-padded N = 16)
   uint32_t idesc;
 };
@@ -235,7 +236,7 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
           }
           continue;
         }
-        epi_chunk_store<CH>(r, s_bias + c0, orow, valid, P.stats != nullptr, s1, s2, rrow, P.wide != 0);
+        epi_chunk_store<CH>(r, s_bias + c0, orow, valid, P.stats != nullptr, s1, s2, rrow, P.wide != 0, P.slope);
       }
       if (P.stats) {
         float v[32];
@@ -272,6 +273,7 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         for (int j = 0; j < CH / 2; ++j) {
           float f0 = __uint_as_float(r[2 * j]), f1 = __uint_as_float(r[2 * j + 1]);
           f0 += s_bias[c0 + 2 * j]; f1 += s_bias[c0 + 2 * j + 1];
+          if (P.slope) { const float a = __ldg(P.slope); f0 = f0 > 0.f ? f0 : a * f0; f1 = f1 > 0.f ? f1 : a * f1; }
           if (P.res && valid) {
             const uint32_t u = *reinterpret_cast<const uint32_t*>(P.res + (long long)img * P.res_sn + (long long)oh * P.res_sh +
                                                                    (long long)ow * P.res_sw + c0 + 2 * j);
@@ -360,7 +362,7 @@ static int launch_halo(const HaloParams& P, const CUtensorMap& mA, size_t smem, 
 // gradient (w = transposed shadow [N=cx][9][C=cy], taps flipped).  Returns 1 when the layer is not covered.
 static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, int N, int pad, const void* in,
                        int64_t ldi, const void* w, const float* bias, void* out, int64_t ldo, double* stats,
-                       const void* res, int64_t ldres, cudaStream_t s, int n_store = 0) {
+                       const void* res, int64_t ldres, cudaStream_t s, int n_store = 0, const float* slope = nullptr) {
   if (!(C == 16 || C == 32 || C == 64 || C == 128)) return 1;
   if (!(N == 16 || N == 32 || N == 64 || N == 128)) return 1;
   if (ldi % 8 != 0 || ((uintptr_t)in & 15) || ((uintptr_t)w & 15)) return 1;
@@ -397,6 +399,7 @@ static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, in
   P.bias = bias; P.stats = stats;
   P.wide = (n_store == 0 && ldo % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
   P.n_store = n_store;
+  P.slope = slope;
   P.res = (const bf16*)res;
   P.res_sn = (long long)oh * ow * ldres; P.res_sh = (long long)ow * ldres; P.res_sw = ldres;
   P.idesc = make_idesc_bf16(128, N, 0, 0);

@@ -57,6 +57,7 @@ struct TapGemmParams {
   long long res_sn, res_sh, res_sw;
   long long cls_res_off[MAXCLS];
   int wide;            // output rows are 32-byte aligned: 256-bit stores
+  const float* slope;  // optional device scalar: PReLU applied to (acc + bias) before the residual (inference fusion)
 };
 
 struct WgradParams {
@@ -354,7 +355,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         const bf16* rrow = P.res ? P.res + P.cls_res_off[cls] + (long long)img * P.res_sn + (long long)oh * P.res_sh +
                                        (long long)ow * P.res_sw + nbase + c0
                                  : nullptr;
-        epi_chunk_store<CH>(r, s_bias + nbase + c0, orow, valid, P.stats != nullptr, s1, s2, rrow, P.wide != 0);
+        epi_chunk_store<CH>(r, s_bias + nbase + c0, orow, valid, P.stats != nullptr, s1, s2, rrow, P.wide != 0, P.slope);
       }
       if (P.stats && stat_base >= 0) flush();
     } else {
@@ -387,6 +388,11 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + s_bias[nbase + c0 + j];
+        if (P.slope) {
+          const float a = __ldg(P.slope);
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : a * v[j];
+        }
         if (P.res && valid) {
           const bf16* rrow = P.res + P.cls_res_off[cls] + (long long)img * P.res_sn + (long long)oh * P.res_sh +
                              (long long)ow * P.res_sw + nbase + c0;
@@ -476,10 +482,6 @@ template <> struct WgB<64>  { static constexpr int BYTES = 64 * 128, BOXES = 1, 
 template <> struct WgB<128> { static constexpr int BYTES = 2 * 8192, BOXES = 2, BOXC = 64, LAYOUT = 2, SBO = 1024, KSTEP = 2048, LBO = 8192, TPS = 2; };
 template <> struct WgB<256> { static constexpr int BYTES = 4 * 8192, BOXES = 4, BOXC = 64, LAYOUT = 2, SBO = 1024, KSTEP = 2048, LBO = 8192, TPS = 1; };
 
-// producer warps of wgrad_kernel: every warp but the MMA issuer for the small-channel layers (issue bound), one for
-// the discriminator's 128/256-channel layers (bandwidth bound: more pollers only cost issue slots there)
-template <int NX> struct WgProd { static constexpr int N = NX <= 64 ? 7 : 1; };
-
 template <int NX, bool SMALL_> struct WgCfg {
   using B = WgB<NX>;
   static constexpr int A_BYTES = 2 * 64 * 128;         // two 64-channel column groups x 64 pixels x 128 B
@@ -504,7 +506,9 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
   using Cfg = WgCfg<NX, SMALL>;
   using B = WgB<NX>;
   constexpr int STAGES = Cfg::STAGES;
-  const int kWgProducers = P.nprod;   // producer warps (runtime: barrier arrival count)
+  // producer warps: every warp but the MMA issuer for the small-channel layers (issue bound), one for the 128/256-channel
+  // layers (measured: more pollers only cost issue slots there); runtime value = barrier arrival count
+  const int kWgProducers = P.nprod;
   // No static shared memory in this kernel, so the dynamic window starts at the CTA's (1024-byte aligned) base; using
   // the symbol directly (instead of a manually aligned pointer) lets the compiler emit LDS/STS rather than generic
   // loads and stores for every shared-memory access of the epilogue.
@@ -854,14 +858,15 @@ static bool halo_enabled() {
 
 // common driver for fprop (dir 0) and bprop (dir 1)
 static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, const void* w, const float* bias, void* out,
-                       int64_t ldo, double* stats, cudaStream_t s, const void* res = nullptr, int64_t ldres = 0) {
+                       int64_t ldo, double* stats, cudaStream_t s, const void* res = nullptr, int64_t ldres = 0,
+                       const float* slope = nullptr) {
   const int C = dir == 0 ? g.cx : g.cy;  // reduced channels
   const int N = dir == 0 ? g.cy : g.cx;  // produced channels
   const int ih = dir == 0 ? g.xh : g.yh, iw = dir == 0 ? g.xw : g.yw;
   const int oh = dir == 0 ? g.yh : g.xh, ow = dir == 0 ? g.yw : g.xw;
   const int T = g.kh * g.kw;
   if (g.s == 1 && g.kh == 3 && g.kw == 3 && g.ph == g.pw && g.ph <= 1 && halo_enabled()) {
-    int rc = halo3x3_run(dir, g.n, ih, iw, oh, ow, C, N, g.ph, in, ldi, w, bias, out, ldo, stats, res, ldres, s);
+    int rc = halo3x3_run(dir, g.n, ih, iw, oh, ow, C, N, g.ph, in, ldi, w, bias, out, ldo, stats, res, ldres, s, 0, slope);
     if (rc != 1) return rc;
   }
   const int KC = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
@@ -880,6 +885,7 @@ static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, con
   P.bias = bias;
   P.stats = stats;
   P.wide = (ldo % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
+  P.slope = slope;
   P.res = (const bf16*)res;
   MPGAN_REQUIRE(!res || (ldres % 8 == 0 && ((uintptr_t)res & 15) == 0), MPGAN_ERR_SHAPE, "residual tensor misaligned");
   MPGAN_REQUIRE(N <= 512, MPGAN_ERR_UNSUPPORTED, "N > 512");
@@ -1074,6 +1080,18 @@ extern "C" int mpgan_tc_conv_bprop_res(const MpganConvGeom* g, const void* y, in
   int rc = to_geom2(g, &g2);
   if (rc) return rc;
   return run_tapgemm(g2, 1, y, ldy, w_b, bias, x, ldx, stats, (cudaStream_t)stream, res, ldres);
+}
+
+// Inference-mode fused layer: y = prelu(conv(x, w_folded) + bias_folded) + res, BatchNorm folded into w / bias by the
+// caller (MONAI Convolution / ResidualUnit in eval mode); direction 0 = convolution, 1 = transposed convolution.
+extern "C" int mpgan_tc_conv_act(const MpganConvGeom* g, int direction, const void* in, int64_t ldi, const void* w,
+                                 const float* bias, const float* slope, const void* res, int64_t ldres, void* out,
+                                 int64_t ldo, void* stream) {
+  Geom2 g2;
+  int rc = to_geom2(g, &g2);
+  if (rc) return rc;
+  MPGAN_REQUIRE(direction == 0 || direction == 1, MPGAN_ERR_SHAPE, "conv_act: direction 0 (conv) or 1 (transposed conv)");
+  return run_tapgemm(g2, direction, in, ldi, w, bias, out, ldo, nullptr, (cudaStream_t)stream, res, ldres, slope);
 }
 
 // Data gradient of a ONE-input-channel stride-1 3x3 convolution (D layer 1: dY has 64 channels, dX one): the

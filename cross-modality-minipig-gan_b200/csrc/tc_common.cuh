@@ -166,11 +166,13 @@ __device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, u
 // One CH-column chunk of one accumulator row: + bias -> bf16 -> 16-byte stores at `orow`, and (optionally) the
 // BatchNorm statistics of the values AS STORED, accumulated in per-thread packed registers s1 / s2 (CH/2 pairs each).
 // `rrow` (optional): a bf16 row of the same shape added before rounding (fused residual / gradient accumulation).
+// `slope` (optional, device scalar): PReLU / LeakyReLU applied to (acc + bias) BEFORE the residual is added -- the
+// inference-mode fusion conv -> folded BatchNorm -> PReLU (+ residual) of MONAI's Convolution / ResidualUnit.
 template <int CH>
 __device__ __forceinline__ void epi_chunk_store(const uint32_t (&r)[CH], const float* s_bias_c0, bf16* orow, bool valid,
                                                 bool do_stats, unsigned long long (&s1)[CH / 2],
                                                 unsigned long long (&s2)[CH / 2], const bf16* rrow = nullptr,
-                                                bool wide = false) {
+                                                bool wide = false, const float* slope = nullptr) {
   const unsigned long long ones = pack_f32x2(1.f, 1.f);
   uint32_t packed[CH / 2];
   uint32_t rq[CH / 2];
@@ -182,17 +184,25 @@ __device__ __forceinline__ void epi_chunk_store(const uint32_t (&r)[CH], const f
       rq[4 * j] = q.x; rq[4 * j + 1] = q.y; rq[4 * j + 2] = q.z; rq[4 * j + 3] = q.w;
     }
   }
+  const bool has_act = slope != nullptr;
+  const float a = has_act ? __ldg(slope) : 1.f;
 #pragma unroll
   for (int j = 0; j < CH / 4; ++j) {
     float4 b = *reinterpret_cast<const float4*>(s_bias_c0 + 4 * j);
+    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_res) {
-      b.x += __uint_as_float(rq[2 * j] << 16); b.y += __uint_as_float(rq[2 * j] & 0xffff0000u);
-      b.z += __uint_as_float(rq[2 * j + 1] << 16); b.w += __uint_as_float(rq[2 * j + 1] & 0xffff0000u);
+      rr.x = __uint_as_float(rq[2 * j] << 16); rr.y = __uint_as_float(rq[2 * j] & 0xffff0000u);
+      rr.z = __uint_as_float(rq[2 * j + 1] << 16); rr.w = __uint_as_float(rq[2 * j + 1] & 0xffff0000u);
+      if (!has_act) { b.x += rr.x; b.y += rr.y; b.z += rr.z; b.w += rr.w; }
     }
-    const float2 v0 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), ones,
-                                             pack_f32x2(b.x, b.y)));
-    const float2 v1 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), ones,
-                                             pack_f32x2(b.z, b.w)));
+    float2 v0 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), ones,
+                                       pack_f32x2(b.x, b.y)));
+    float2 v1 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), ones,
+                                       pack_f32x2(b.z, b.w)));
+    if (has_act) {
+      v0.x = (v0.x > 0.f ? v0.x : a * v0.x) + rr.x; v0.y = (v0.y > 0.f ? v0.y : a * v0.y) + rr.y;
+      v1.x = (v1.x > 0.f ? v1.x : a * v1.x) + rr.z; v1.y = (v1.y > 0.f ? v1.y : a * v1.y) + rr.w;
+    }
     __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y);
     __nv_bfloat162 h1 = __floats2bfloat162_rn(v1.x, v1.y);
     packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);

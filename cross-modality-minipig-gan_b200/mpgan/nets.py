@@ -206,6 +206,13 @@ class Convolution(nn.Sequential):
                 plan.tape.append((x,))
             return y
         ch = self.out_channels
+        if (not plan.training and not plan.save and plan.dtype == torch.bfloat16
+                and os.environ.get("MPGAN_NO_EVAL_FUSION", "0") != "1"):
+            # inference: BatchNorm folded into the weights, PReLU and the residual in the convolution's epilogue
+            wf, bf = plan.rt.folded(self.conv, self.norm)
+            y = ops.conv_act(rec.spec, x, wf, bf, self.act.weight, res=res, out=out)
+            if y is not None:
+                return y
         stats = plan.zeros64(2 * ch, x.device) if plan.training else None
         c, fused = conv_apply(rec, x, stats=stats)
         y, saved = bn_act_forward(c, self.norm, ACT_PRELU, self.act.weight, 0.0, res, out, plan, stats, fused)

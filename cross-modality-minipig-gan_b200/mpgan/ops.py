@@ -123,6 +123,30 @@ def conv_fprop(spec, x, w, bias, out=None, stats=None, use_tc=True, use_c1=True)
     return out, False
 
 
+def conv_act(spec, x, w, bias, slope, res=None, out=None):
+    """Inference-mode fused layer on the tcgen05 path: out = prelu(conv(x, w) + bias) + res with BatchNorm already
+    folded into (w, bias).  Transposed layers take the transposed weights.  Returns None when the layer is not covered
+    (the caller then runs the unfused kernels)."""
+    lib = _lib.require_device()
+    if x.dtype != torch.bfloat16 or spec.rank != 2:
+        return None
+    n, ins = x.shape[0], tuple(x.shape[1:-1])
+    if spec.transposed:
+        xs, ys, direction, cout = spec.x_of_y(ins), ins, 1, spec.cx
+    else:
+        xs, ys, direction, cout = ins, spec.y_of_x(ins), 0, spec.cy
+    g = spec.geom(n, xs, ys)
+    if not tc_supported(g, direction):
+        return None
+    if out is None:
+        out = torch.empty((n,) + tuple(xs if spec.transposed else ys) + (cout,), dtype=x.dtype, device=x.device)
+    if res is not None and (res.dtype != torch.bfloat16 or ld(res) % 8 or res.data_ptr() % 16):
+        return None
+    check(lib.mpgan_tc_conv_act(ctypes.byref(g), direction, ptr(x), ld(x), ptr(w), ptr(bias), ptr(slope), ptr(res),
+                                ld(res) if res is not None else 0, ptr(out), ld(out), _stream()), "tc_conv_act")
+    return out
+
+
 _C1OUT = os.environ.get("MPGAN_NO_C1OUT", "0") != "1"
 
 

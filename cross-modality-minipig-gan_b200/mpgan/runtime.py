@@ -31,6 +31,7 @@ class Runtime:
         self.rec = {}
         self._shadow_version = None
         self.manual_version = 0
+        self._folded = {}
 
     # ------------------------------------------------------------------------------------------------
     def _params(self):
@@ -129,6 +130,30 @@ class Runtime:
             if r.wt is not None:
                 ops.weight_transpose(r.w, r.wt, r.spec.cy, r.spec.taps, r.spec.cx)
         self._shadow_version = ver
+
+    def folded(self, conv, bn):
+        """Inference: BatchNorm (running statistics) folded into the convolution -- bf16 weights in the layout the
+        tcgen05 kernel of that layer reads ([cy][taps][cx], or the transposed [cx][taps][cy] for ConvTranspose) and an
+        fp32 bias.  Recomputed only when the weights or the running statistics change (host-side glue, a handful
+        of tiny torch kernels per layer per weight version)."""
+        r = self.rec[conv]
+        ver = (self.flat._version, self.manual_version, bn.running_mean._version, bn.running_var._version,
+               bn.weight._version, bn.bias._version)
+        hit = self._folded.get(conv)
+        if hit is not None and hit[0] == ver:
+            return hit[1], hit[2]
+        sp = r.spec
+        with torch.no_grad():
+            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
+            w3 = r.w32.view(sp.cy, sp.taps, sp.cx)
+            b0 = conv.bias.detach().float() if conv.bias is not None else torch.zeros_like(scale)
+            if sp.transposed:   # ConvTranspose: output channels are the cx axis; kernel wants [cx][taps][cy]
+                wf = (w3 * scale.view(1, 1, -1)).permute(2, 1, 0).contiguous().to(torch.bfloat16)
+            else:
+                wf = (w3 * scale.view(-1, 1, 1)).contiguous().to(torch.bfloat16)
+            bf = ((b0 - bn.running_mean.float()) * scale + bn.bias.detach().float()).contiguous()
+        self._folded[conv] = (ver, wf, bf)
+        return wf, bf
 
     def zero_grad(self):
         if self.grad is not None:

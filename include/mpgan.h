@@ -74,6 +74,12 @@ int mpgan_tc_conv_bprop(const MpganConvGeom* g, const void* y, int64_t ldy, cons
                         void* x, int64_t ldx, double* stats, void* stream);
 /* same, with a bf16 tensor `res` (pixel stride ldres, the X grid) added to the result before rounding: fuses the
  * gradient accumulation of residual / skip branches (dx = dgrad(dy) + res) into the convolution's epilogue */
+/* inference-mode fused layer (BatchNorm folded into w / bias by the caller):  out = prelu(conv(in, w) + bias) + res
+ * direction 0: convolution X -> Y with w = [cy][taps][cx]; direction 1: transposed convolution Y -> X with the
+ * transposed weights [cx][taps][cy].  slope: device scalar (PReLU weight) or NULL (no activation); res optional. */
+int mpgan_tc_conv_act(const MpganConvGeom* g, int direction, const void* in, int64_t ldi, const void* w,
+                      const float* bias, const float* slope, const void* res, int64_t ldres, void* out, int64_t ldo,
+                      void* stream);
 /* data gradient of a one-input-channel stride-1 3x3 layer (cx == 1; dY has cy in {16,32,64,128} channels) through the
  * halo-resident tcgen05 kernel: w_b16 = bf16 [16][9][cy], row 0 the layer's transposed weights, rows 1..15 zero;
  * x: (n, xh, xw) one channel, pixel stride ldx; res (optional, same layout, stride ldres) is added. */
