@@ -157,6 +157,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner does, whatever
+    # NCCL_DEBUG says) are redirected to stderr for the whole run, the line is written to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch.distributed as dist
     import mpgan
     from mpgan import _lib, ddp
@@ -276,7 +282,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"5 two-optimizer steps of batch 1 at {SIZE}x{SIZE}, fp32 torch CPU "
                                               f"({ms:.0f} ms/step)"}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         # Leave without tearing the NCCL communicator down: destroy_process_group() blocks while a CUDA graph that
         # captured collectives of that communicator is alive (observed: a 2-GPU run printed its line and then hung).
