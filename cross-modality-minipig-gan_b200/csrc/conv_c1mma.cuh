@@ -95,10 +95,10 @@ c1mma_fprop_kernel(const __grid_constant__ C1mmaParams P, const __grid_constant_
     if (elect_one()) {  // ================= TMA producer: the raw (16S+2) x (8S+2) input window of every tile =========
       int xs = 0;
       uint32_t xpar = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int img = tile / tiles_per_img;
-        const int trm = tile - img * tiles_per_img;
-        const int thi = trm / P.tiles_w, twi = trm - thi * P.tiles_w;
+      TileWalk<3> tw;
+      { const int radix[3] = {P.tiles_w, P.tiles_h, 1 << 30}; tw.init((int)blockIdx.x, (int)gridDim.x, radix); }
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, tw.next()) {
+        const int twi = tw.d[0], thi = tw.d[1], img = tw.d[2];
         mbar_wait(&x_empty[xs], xpar ^ 1);
         mbar_expect_tx(&x_full[xs], P.xbytes);
         // the innermost coordinate must stay a multiple of 8 elements (16-byte aligned global address; an odd start
@@ -178,11 +178,11 @@ c1mma_fprop_kernel(const __grid_constant__ C1mmaParams P, const __grid_constant_
 #pragma unroll
     for (int j = 0; j < CH / 2; ++j) { s1[j] = 0ull; s2[j] = 0ull; }
     int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+    TileWalk<3> tw;
+    { const int radix[3] = {P.tiles_w, P.tiles_h, 1 << 30}; tw.init((int)blockIdx.x, (int)gridDim.x, radix); }
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, tw.next()) {
       if (NCH == 1 && (it & 1) != half) continue;
-      const int img = tile / tiles_per_img;
-      const int trm = tile - img * tiles_per_img;
-      const int thi = trm / P.tiles_w, twi = trm - thi * P.tiles_w;
+      const int twi = tw.d[0], thi = tw.d[1], img = tw.d[2];
       const int oh = thi * HT_H + lh, ow = twi * HT_W + lw;
       const bool valid = oh < P.oh && ow < P.ow;
       bf16* orow = P.out + (long long)img * P.out_sn + (long long)oh * P.out_sh + (long long)ow * P.out_sw + c0;

@@ -57,12 +57,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int N, int KC>   // KC = min(C, 64): channels per plane (one swizzle span)
-__global__ void __launch_bounds__(kHaloThreads, 1) __maxnreg__(N <= 64 ? 128 : 168)
+__global__ void __launch_bounds__(kHaloThreads, 1)
 halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUtensorMap tmA) {
   // accumulator ring: as many 128 x N fp32 tiles as fit in 512 TMEM columns (<= 8): small layers are bound by the
   // MMA -> epilogue -> MMA round trip, not by throughput, so the ring must be deep
-  // N <= 64 (generator layers): at most half of TMEM, <= 128 registers per thread and (host side) a capped plane ring,
-  // so that a CTA of the concurrent weight-gradient stream fits on the same SM
+  // N <= 64 (generator layers): at most half of TMEM and (host side) a capped plane ring, so that a CTA of the concurrent
+  // weight-gradient stream can share the SM (a 128-register cap was tried too: it only bought spills)
   constexpr int NACC = N <= 64 ? (256 / N > kMaxAcc ? kMaxAcc : 256 / N) : 512 / N;
   constexpr int TMEM_COLS = NACC * N < 32 ? 32 : NACC * N;
   // No static shared memory in this kernel, so the dynamic window starts at the CTA's (1024-byte aligned) base; using
@@ -130,18 +130,18 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
 
   if (warp == 0) {
     if (elect_one()) {  // ================= TMA producer: one box per (tile, 64-channel plane) =================
-      int pi = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int img = tile / tiles_per_img;
-        const int tr = tile - img * tiles_per_img;
-        const int thi = tr / P.tiles_w, twi = tr - thi * P.tiles_w;
+      int pbuf = 0;
+      uint32_t ppar = 0;
+      TileWalk<3> tw;
+      { const int radix[3] = {P.tiles_w, P.tiles_h, 1 << 30}; tw.init((int)blockIdx.x, (int)gridDim.x, radix); }
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, tw.next()) {
+        const int twi = tw.d[0], thi = tw.d[1], img = tw.d[2];
         const int h0 = thi * HT_H - P.pad, w0 = twi * HT_W - P.pad;
-        for (int kc = 0; kc < nkc; ++kc, ++pi) {
-          const int buf = pi % P.nbuf;
-          const uint32_t par = (uint32_t)(pi / P.nbuf) & 1u;
-          mbar_wait(&a_empty[buf], par ^ 1);
-          mbar_expect_tx(&a_full[buf], (uint32_t)(HPIX * rowb));
-          tma_load_4d(a_sm + buf * a_bytes, &tmA, &a_full[buf], kc * KC, w0, h0, img);
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(&a_empty[pbuf], ppar ^ 1);
+          mbar_expect_tx(&a_full[pbuf], (uint32_t)(HPIX * rowb));
+          tma_load_4d(a_sm + pbuf * a_bytes, &tmA, &a_full[pbuf], kc * KC, w0, h0, img);
+          if (++pbuf == P.nbuf) { pbuf = 0; ppar ^= 1; }
         }
       }
     }
@@ -206,11 +206,11 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
 #pragma unroll
       for (int j = 0; j < CH / 2; ++j) { s1[j] = 0ull; s2[j] = 0ull; }
       int it = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      TileWalk<3> tw;
+      { const int radix[3] = {P.tiles_w, P.tiles_h, 1 << 30}; tw.init((int)blockIdx.x, (int)gridDim.x, radix); }
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, tw.next()) {
         if (NCH == 1 && (it & 1) != half) continue;
-        const int img = tile / tiles_per_img;
-        const int trm = tile - img * tiles_per_img;
-        const int thi = trm / P.tiles_w, twi = trm - thi * P.tiles_w;
+        const int twi = tw.d[0], thi = tw.d[1], img = tw.d[2];
         const int oh = thi * HT_H + lh, ow = twi * HT_W + lw;
         const bool valid = oh < P.oh && ow < P.ow;
         bf16* orow = P.out + (long long)img * P.out_sn + (long long)oh * P.out_sh + (long long)ow * P.out_sw + c0;
@@ -250,10 +250,10 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
       }
     } else {
     int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-      const int img = tile / tiles_per_img;
-      const int trm = tile - img * tiles_per_img;
-      const int thi = trm / P.tiles_w, twi = trm - thi * P.tiles_w;
+    TileWalk<3> tw;
+    { const int radix[3] = {P.tiles_w, P.tiles_h, 1 << 30}; tw.init((int)blockIdx.x, (int)gridDim.x, radix); }
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, tw.next()) {
+      const int twi = tw.d[0], thi = tw.d[1], img = tw.d[2];
       const int oh = thi * HT_H + lh, ow = twi * HT_W + lw;
       const bool valid = oh < P.oh && ow < P.ow;
       bf16* orow = P.out + (long long)img * P.out_sn + (long long)oh * P.out_sh + (long long)ow * P.out_sw;

@@ -187,13 +187,10 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
     if (elect_one()) {  // ================= TMA producer (one thread) =================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int nt = t % P.n_tiles; t /= P.n_tiles;
-        const int twi = t % P.tiles_w; t /= P.tiles_w;
-        const int thi = t % P.tiles_h; t /= P.tiles_h;
-        const int tni = t % P.tiles_n; t /= P.tiles_n;
-        const int cls = t;
+      TileWalk<5> tw5;
+      { const int radix[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30}; tw5.init((int)blockIdx.x, (int)gridDim.x, radix); }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw5.next()) {
+        const int nt = tw5.d[0], twi = tw5.d[1], thi = tw5.d[2], tni = tw5.d[3], cls = tw5.d[4];
         const int w0 = (twi * MT) << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
         for (int tap = P.cls_tap_begin[cls]; tap < P.cls_tap_begin[cls + 1]; ++tap) {
           const int mi = P.tap_map[tap];
@@ -221,13 +218,10 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
     int cur_cls = -1, ntaps = 0, dh = 0, dw = 0, slab = 0;
     const CUtensorMap* mA = &tmA0;
     uint32_t cnt = 0;   // ring position of the tile's first stage (identical in all lanes)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int t = tile;
-      const int nt = t % P.n_tiles; t /= P.n_tiles;
-      const int twi = t % P.tiles_w; t /= P.tiles_w;
-      const int thi = t % P.tiles_h; t /= P.tiles_h;
-      const int tni = t % P.tiles_n; t /= P.tiles_n;
-      const int cls = t;
+    TileWalk<5> tw5;
+    { const int radix[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30}; tw5.init((int)blockIdx.x, (int)gridDim.x, radix); }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw5.next()) {
+      const int nt = tw5.d[0], twi = tw5.d[1], thi = tw5.d[2], tni = tw5.d[3], cls = tw5.d[4];
       if (cls != cur_cls) {
         cur_cls = cls;
         const int tb = P.cls_tap_begin[cls];
@@ -265,8 +259,10 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int cls = tile / per_cls;
+      TileWalk<2> tw2;
+      { const int radix[2] = {per_cls, 1 << 30}; tw2.init((int)blockIdx.x, (int)gridDim.x, radix); }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it, tw2.next()) {
+        const int cls = tw2.d[1];
         const int buf = it % NACC;
         const uint32_t par = (uint32_t)(it / NACC) & 1u;
         mbar_wait(&tempty[buf], par ^ 1);
@@ -323,14 +319,11 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         for (int j = 0; j < CH / 2; ++j) { s1[j] = 0ull; s2[j] = 0ull; }
       };
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      TileWalk<5> tw5;
+      { const int radix[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30}; tw5.init((int)blockIdx.x, (int)gridDim.x, radix); }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it, tw5.next()) {
         if (NCH == 1 && (it & 1) != half) continue;
-        int t = tile;
-        const int nt = t % P.n_tiles; t /= P.n_tiles;
-        const int twi = t % P.tiles_w; t /= P.tiles_w;
-        const int thi = t % P.tiles_h; t /= P.tiles_h;
-        const int tni = t % P.tiles_n; t /= P.tiles_n;
-        const int cls = t;
+        const int nt = tw5.d[0], twi = tw5.d[1], thi = tw5.d[2], tni = tw5.d[3], cls = tw5.d[4];
         const int ow = (twi << P.tw_log2) + lw, oh = (thi << P.th_log2) + lh, img = (tni << tn_log2) + ln;
         const bool valid = img < P.nimg && oh < P.cls_oh[cls] && ow < P.cls_ow[cls];
         const int nbase = nt * BN;
@@ -360,13 +353,10 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
       if (P.stats && stat_base >= 0) flush();
     } else {
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      int t = tile;
-      const int nt = t % P.n_tiles; t /= P.n_tiles;
-      const int twi = t % P.tiles_w; t /= P.tiles_w;
-      const int thi = t % P.tiles_h; t /= P.tiles_h;
-      const int tni = t % P.tiles_n; t /= P.tiles_n;
-      const int cls = t;
+    TileWalk<5> tw5;
+    { const int radix[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30}; tw5.init((int)blockIdx.x, (int)gridDim.x, radix); }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it, tw5.next()) {
+      const int nt = tw5.d[0], twi = tw5.d[1], thi = tw5.d[2], tni = tw5.d[3], cls = tw5.d[4];
       const int nbase = nt * BN;
       const int buf = it % NACC;
       const uint32_t par = (uint32_t)(it / NACC) & 1u;

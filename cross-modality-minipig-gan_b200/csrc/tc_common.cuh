@@ -137,6 +137,36 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 
+// Mixed-radix counter over a persistent CTA's tile sequence tile0, tile0 + step, ...  (digit 0 = fastest index, the last
+// digit is unbounded).  The divisions happen once, in init(); next() is ND adds with carry -- a per-tile decode with
+// 3-10 runtime divisions (~40 cycles each) on a single producer / epilogue thread was a measurable part of the
+// 7-28-tile generator kernels.
+template <int ND> struct TileWalk {
+  int d[ND], s[ND], r[ND];
+  __device__ __forceinline__ void init(int tile0, int step, const int (&radix)[ND]) {
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      r[k] = radix[k];
+      if (k < ND - 1) {
+        d[k] = tile0 % r[k]; tile0 /= r[k];
+        s[k] = step % r[k]; step /= r[k];
+      } else {
+        d[k] = tile0; s[k] = step;
+      }
+    }
+  }
+  __device__ __forceinline__ void next() {
+    int carry = 0;
+#pragma unroll
+    for (int k = 0; k < ND - 1; ++k) {
+      const int v = d[k] + s[k] + carry;
+      carry = v >= r[k] ? 1 : 0;
+      d[k] = v - (carry ? r[k] : 0);
+    }
+    d[ND - 1] += s[ND - 1] + carry;
+  }
+};
+
 // ---- small-N epilogue arithmetic (shared by the halo, tap-GEMM and one-channel kernels) ----
 // Blackwell issues fp32 FMAs at full rate in the packed form (two lanes of a 64-bit register pair).
 __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
