@@ -289,7 +289,8 @@ class GAN(nn.Module):
     def fused_step(self, batch, logs=None, grad_probe=None):
         """One full two-optimizer training step (variant "final").  Returns ``logs`` (device fp32):
         [g_adv, g_recon, d_real/2, d_fake/2];  g_loss = logs[0]+logs[1], d_loss = logs[2]+logs[3]."""
-        assert self.variant == "final", "fused_step covers the GAN_final.py step"
+        if self.variant != "final":
+            return self._fused_step_perceptual(batch, logs, grad_probe)
         t1, t2 = batch["t1w"], batch["t2w"]
         G, D, hp = self.generator, self.discriminator, self.hparams
         n, dev = t1.shape[0], t1.device
@@ -330,14 +331,93 @@ class GAN(nn.Module):
         D.runtime.zero_grad()
         return logs
 
+    def _fused_step_perceptual(self, batch, logs=None, grad_probe=None):
+        """The test_runs/GAN.py:300-438 two-optimizer step as one static kernel sequence.  ``batch`` carries the patch
+        origins as ``batch["origins"]`` (int32 device tensor (B*num_samples, dims); sampled on the host like MONAI's
+        RandSpatialCropSamplesd when absent).  Returns ``logs`` (device fp32):
+        [g_adv, g_recon, g_perceptual, d_real/2, d_fake/2];  g_loss = sum of the first three, d_loss = last two.
+        The discriminator's 16 activations stay in their internal channels-last layout: the feature-matching loss is
+        an element-wise L1, so no NCHW copies are made and its gradients enter the backward plan in place."""
+        t1, t2 = batch["t1w"], batch["t2w"]
+        G, D, hp = self.generator, self.discriminator, self.hparams
+        n, dev = t1.shape[0], t1.device
+        sp = tuple(t1.shape[2:])
+        o_dev = batch.get("origins")
+        if o_dev is None:
+            o_dev = torch.as_tensor(np.asarray(self.sample_patch_origins(n, sp)).reshape(-1, self.dims), dtype=torch.int32,
+                                    device=dev)
+        m = n * self.num_samples
+        ones, soft, zeros = self._consts(m, dev)
+        if logs is None:
+            logs = torch.zeros(5, dtype=torch.float32, device=dev)
+        else:
+            logs.zero_()
+        patch_shape = (m, 1) + (self.roi,) * self.dims
+
+        def gather(vol):   # (B,1,*S) fp32 -> (m,1,roi..) fp32 patches (one channel: NCHW == channels-last)
+            v = vol.contiguous().reshape((n,) + sp + (1,))
+            return ops.patch_gather(v, o_dev, self.num_samples, self.roi).reshape(patch_shape)
+
+        real_p = gather(t2)
+        # ---- optimizer 0: generator (discriminator frozen)
+        gen, gplan = G.run_forward(t1, save=True, need_wgrad=True)
+        fake_p = gather(gen)
+        out_f, plan_f = D.run_forward(fake_p, save=True, need_wgrad=False, want_acts=True, logical_acts=False)
+        _, plan_r = D.run_forward(real_p, save=False, need_wgrad=False, want_acts=True, logical_acts=False)
+        acts_f, acts_r = plan_f.extra["acts_raw"], plan_r.extra["acts_raw"]
+        dacts = {}
+        for k, (af, ar) in enumerate(zip(acts_f, acts_r)):   # sum_k l1_loss(y[k], y_hat[k]) / numel_k
+            af, ar = af.contiguous(), ar.contiguous()
+            w = 1.0 / af.numel()
+            ops.l1_fwd(ar, af, w, logs[2:3])
+            dacts[k] = ops.l1_bwd(af, ar, w, None, torch.empty_like(af), False)
+        ops.bce_fwd(out_f, ones, 1.0, logs[0:1])
+        ops.l1_fwd(fake_p, real_p, 1.0, logs[1:2])
+        dprob = ops.bce_bwd(out_f, ones, 1.0, None, torch.empty_like(out_f))
+        dfake = D.run_backward(plan_f, dprob, need_dx=True, act_grads=dacts, internal=True)
+        dfake = dfake.contiguous()
+        ops.l1_bwd(fake_p, real_p, 1.0, None, dfake.reshape(patch_shape), True)
+        dgen = torch.zeros((n,) + sp + (1,), dtype=torch.float32, device=dev)
+        ops.patch_scatter_add(dfake.reshape((m,) + (self.roi,) * self.dims + (1,)), o_dev, self.num_samples, self.roi, dgen)
+        G.run_backward(gplan, dgen.reshape(gen.shape), need_dx=False)
+        if grad_probe is not None:
+            grad_probe("generator", G)
+        if self.comm is not None:
+            self.comm.allreduce(G.runtime.grad)
+        G.runtime.adam_step(hp.g_lr, hp.b1, hp.b2)
+        G.runtime.zero_grad()
+        # ---- optimizer 1: discriminator (the prologue re-runs the updated generator, forward only)
+        gen2, _ = G.run_forward(t1, save=False, need_wgrad=False)
+        fake_p2 = gather(gen2)
+        p_real, plan_r2 = D.run_forward(real_p, save=True, need_wgrad=True, want_acts=False)
+        ops.bce_fwd(p_real, soft, 0.5, logs[3:4])
+        p_fake, plan_f2 = D.run_forward(fake_p2, save=True, need_wgrad=True, want_acts=False)
+        ops.bce_fwd(p_fake, zeros, 0.5, logs[4:5])
+        D.run_backward(plan_f2, ops.bce_bwd(p_fake, zeros, 0.5, None, torch.empty_like(p_fake)), need_dx=False)
+        D.run_backward(plan_r2, ops.bce_bwd(p_real, soft, 0.5, None, torch.empty_like(p_real)), need_dx=False)
+        if grad_probe is not None:
+            grad_probe("discriminator", D)
+        if self.comm is not None:
+            self.comm.allreduce(D.runtime.grad)
+        D.runtime.adam_step(hp.d_lr, hp.b1, hp.b2)
+        D.runtime.zero_grad()
+        return logs
+
     def capture(self, batch):
         """Record ``fused_step`` on static input buffers into a CUDA graph.  Returns (graph, static_batch, logs)."""
         dev = batch["t1w"].device
         static = {k: batch[k].clone() for k in ("t1w", "t2w")}
-        logs = torch.zeros(4, dtype=torch.float32, device=dev)
+        if self.variant != "final":   # the patch origins are a static device tensor the caller refreshes per step
+            o = batch.get("origins")
+            if o is None:
+                n, sp = static["t1w"].shape[0], tuple(static["t1w"].shape[2:])
+                o = torch.as_tensor(np.asarray(self.sample_patch_origins(n, sp)).reshape(-1, self.dims), dtype=torch.int32,
+                                    device=dev)
+            static["origins"] = o.clone()
+        logs = torch.zeros(4 if self.variant == "final" else 5, dtype=torch.float32, device=dev)
         self.generator.runtime.ensure(dev)
         self.discriminator.runtime.ensure(dev)
-        self._consts(static["t1w"].shape[0], dev)
+        self._consts(static["t1w"].shape[0] * (1 if self.variant == "final" else self.num_samples), dev)
         snap = self._snapshot()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())

@@ -578,7 +578,7 @@ class _ConvBnLeakyStack(_PlanNet):
         self.model_linear = nn.Sequential(*lin)
         self._init_runtime(precision)
 
-    def _run(self, x, save, want_acts, need_wgrad=None):
+    def _run(self, x, save, want_acts, need_wgrad=None, logical_acts=True):
         rt = self.runtime
         rt.ensure(x.device)
         plan = Plan(rt, self.training, save, rt.requires_grad() if need_wgrad is None else need_wgrad)
@@ -627,7 +627,10 @@ class _ConvBnLeakyStack(_PlanNet):
         p = ops.sigmoid_fwd(z_in, torch.empty_like(z_in))
         if want_acts:
             acts.append(("raw", p))
-            plan.extra["acts"] = self._acts_to_logical(acts)
+            if logical_acts:
+                plan.extra["acts"] = self._acts_to_logical(acts)
+            else:   # the fused training step consumes the activations in their internal (channels-last) layout
+                plan.extra["acts_raw"] = [a for _, a in acts]
         if save:
             plan.tape.append((lin_tape, p, feat_shape))
         return p, plan
@@ -647,7 +650,9 @@ class _ConvBnLeakyStack(_PlanNet):
                 out.append(a.float().clone())
         return out
 
-    def run_backward(self, plan, dprob, need_dx=True, act_grads=None):
+    def run_backward(self, plan, dprob, need_dx=True, act_grads=None, internal=False):
+        """act_grads: {activation index: gradient} -- logical NC[D]HW fp32 tensors (the autograd bridge) or, with
+        ``internal=True``, tensors in the activations' own layout / dtype (fused perceptual step)."""
         rt = plan.rt
         lin_tape, p, feat_shape = plan.tape.pop()
         linears = [m for m in self.model_linear if isinstance(m, nn.Linear)]
@@ -676,7 +681,10 @@ class _ConvBnLeakyStack(_PlanNet):
                 ops.linear_bwd(z_in, wcl, dz, dx, None, None)
             dz = dx
         dfeat = dz  # (N, prod(feat)) in the compute dtype, channels-last order
-        if 3 * n_conv in ag:  # gradient w.r.t. the Flatten output (NCHW order)
+        if 3 * n_conv in ag and internal:
+            dfeat = ops.add_copy(dfeat.reshape(feat_shape), ag[3 * n_conv].reshape(feat_shape),
+                                 dfeat.reshape(feat_shape)).reshape(dfeat.shape)
+        elif 3 * n_conv in ag:  # gradient w.r.t. the Flatten output (NCHW order)
             g = ag[3 * n_conv].reshape((feat_shape[0], feat_shape[-1]) + tuple(feat_shape[1:-1]))
             nd = self.dims
             g = g.permute((0,) + tuple(range(2, nd + 2)) + (1,)).reshape(dfeat.shape)
@@ -689,13 +697,17 @@ class _ConvBnLeakyStack(_PlanNet):
         for i in range(len(convs) - 1, -1, -1):
             h_in, c, saved, trained, bn_out = plan.tape.pop()
             if (3 * i + 2) in ag:
-                dh = dh + ag[3 * i + 2].permute(to_cl).to(dh.dtype)
+                if internal:
+                    dh = dh.contiguous()
+                    dh = ops.add_copy(dh, ag[3 * i + 2], dh)
+                else:
+                    dh = dh + ag[3 * i + 2].permute(to_cl).to(dh.dtype)
             if bn_out is not None:
                 # activations were exposed: LeakyReLU backward on the saved BN output, add the gradient injected
                 # at the BN output, then the BatchNorm backward proper
                 dbn = ops.act_bwd(dh.contiguous(), bn_out, ACT_LEAKY, 0.2, _new(bn_out, bn_out.shape))
                 if (3 * i + 1) in ag:
-                    dbn = dbn + ag[3 * i + 1].permute(to_cl).to(dbn.dtype)
+                    dbn = ops.add_copy(dbn, ag[3 * i + 1], dbn) if internal else dbn + ag[3 * i + 1].permute(to_cl).to(dbn.dtype)
                 dc = bn_act_backward(dbn, c, saved, bns[i], ACT_NONE, None, 0.0, plan, trained)
                 fused_bias = False
             else:
@@ -703,7 +715,7 @@ class _ConvBnLeakyStack(_PlanNet):
                 dc = bn_act_backward(dh, c, saved, bns[i], ACT_LEAKY, None, 0.2, plan, trained,
                                      conv_db=rt.rec[convs[i]].db if fused_bias else None)
             if (3 * i) in ag:
-                dc = dc + ag[3 * i].permute(to_cl).to(dc.dtype)
+                dc = ops.add_copy(dc, ag[3 * i], dc) if internal else dc + ag[3 * i].permute(to_cl).to(dc.dtype)
             dh = conv_backward(rt.rec[convs[i]], h_in, dc, plan, need_dx=(need_dx or i > 0), bias_done=fused_bias)
         join_wgrad(plan, dp.device)
         if not need_dx:
@@ -750,5 +762,5 @@ class PatchDiscriminator(_ConvBnLeakyStack):
         outs = self._call(x, True)
         return outs[0], {i: a for i, a in enumerate(outs[1:])}
 
-    def run_forward(self, x, save, need_wgrad=None, want_acts=None):
-        return self._run(x, save, self.use_perceptual if want_acts is None else want_acts, need_wgrad)
+    def run_forward(self, x, save, need_wgrad=None, want_acts=None, logical_acts=True):
+        return self._run(x, save, self.use_perceptual if want_acts is None else want_acts, need_wgrad, logical_acts)

@@ -432,6 +432,47 @@ def test_perceptual_training_step_pass_vs_oracle(precision, opt_idx):
         check_grads_bf16(mgrads, rgrads, agrads, f"perceptual pass {opt_idx} bf16")
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_perceptual_step_equals_the_protocol(precision):
+    """test_runs/GAN.py step: the static kernel sequence (fused_step, activations in their internal layout, perceptual
+    gradients injected in place) and its CUDA graph run the arithmetic of the autograd-driven protocol (fit_batch)
+    and of the oracle.  Learning rates 0, like the GAN_final.py twin of this test."""
+    B, S, NS = 2, 32, 6
+    torch.manual_seed(0)
+    kw = dict(variant="perceptual", num_samples=NS, precision=precision, lr=0.0)
+    a, b, c = GAN(1, S, S, **kw), GAN(1, S, S, **kw), GAN(1, S, S, **kw)
+    b.load_state_dict(a.state_dict()), c.load_state_dict(a.state_dict())
+    batch = to_dev(synthetic_batch(B, 2, S, seed=1))
+    origins = sample_patch_origins(np.random.RandomState(2), B, NS, (S, S), 16)
+    o_dev = torch.as_tensor(np.asarray(origins).reshape(-1, 2), dtype=torch.int32, device=DEV)
+    la = a.fit_batch(batch, patch_origins=origins)
+    probe = {}
+    lb = b.fused_step(dict(batch, origins=o_dev), grad_probe=lambda name, net: probe.__setitem__(name, net.runtime.grad.clone()))
+    graph, static, logs = c.capture(dict(batch, origins=o_dev))
+    graph.replay()
+    torch.cuda.synchronize()
+    tol = 2e-5 if precision == "fp32" else 2e-2
+    g_loss, d_loss = float(la[0]), float(la[1])
+    assert abs(float(lb[0] + lb[1] + lb[2]) - g_loss) <= tol * abs(g_loss)
+    assert abs(float(lb[3] + lb[4]) - d_loss) <= tol * abs(d_loss)
+    assert abs(float(lb[2]) - float(a.logged["g_perceptual_loss"])) <= tol * abs(float(a.logged["g_perceptual_loss"])) + 1e-9
+    assert torch.allclose(lb, logs, rtol=tol, atol=1e-6)
+    for (n1, b1), (_, b2), (_, b3) in zip(a.named_buffers(), b.named_buffers(), c.named_buffers()):
+        if b1.dtype.is_floating_point:
+            assert rel_l2(b2, b1) <= tol and rel_l2(b3, b1) <= tol, n1
+    # the gradients handed to Adam == the protocol's (fp32: tight; bf16: the generator cascade is noise dominated)
+    a2 = GAN(1, S, S, **kw)
+    a2.load_state_dict(a.state_dict())
+    _my_pass(a2, batch, 1, patch_origins=origins)
+    want, got = a2.discriminator.runtime.grad, probe["discriminator"]
+    assert rel_l2(got, want) <= (1e-5 if precision == "fp32" else 3e-2)
+    if precision == "fp32":
+        a3 = GAN(1, S, S, **kw)
+        a3.load_state_dict(a.state_dict())
+        _my_pass(a3, batch, 0, patch_origins=origins)
+        assert rel_l2(probe["generator"], a3.generator.runtime.grad) <= 1e-5
+
+
 def test_reference_literal_3d_patch_discriminator_golden():
     """Output of the reference's own test_runs/GAN.py Discriminator (3-D, 16^3), recorded in tests/golden."""
     fix = torch.load(os.path.join(GOLDEN, "ref_patch_discriminator_3d.pt"), weights_only=False)
