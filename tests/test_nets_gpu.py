@@ -325,6 +325,39 @@ def test_fused_step_and_graph_replay_equal_the_protocol(precision):
         assert rel_l2(got, want) <= 1e-5
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_generator_pass_vs_oracle(precision):
+    """BASELINE.json configs[1] at its FULL size (batch 32 of 256x256): the generator pass of the training step --
+    generator output, discriminator probabilities and both losses -- against the CPU oracle on the same seeded weights
+    and inputs.  fp32 mode: north_star's relative L2 <= 1e-4 throughout.  bf16 mode: <= 1e-2 for the discriminator
+    (fed the oracle's generator output); the six cascaded randomly-initialised UNets are checked against the bound
+    any bf16 implementation reaches on them (torch's own autocast run deviates by 1.1e-1, module docstring)."""
+    B, S = 32, 256
+    torch.manual_seed(0)
+    ora = GANOracle("final", dims=2, spatial=S)
+    mine = GAN(1, S, S, precision=precision)
+    mine.load_state_dict(ora.state_dict())
+    batch = synthetic_batch(B, 2, S, seed=1)
+    with torch.no_grad():
+        gen_ref = ora.generator(batch["t1w"])
+        p_ref = ora.discriminator(gen_ref)
+        adv_ref = float(ora.adversarial_loss(p_ref, torch.ones(B, 1)))
+        rec_ref = float(ora.reconstruction_loss(gen_ref, batch["t2w"]))
+    d = to_dev(batch)
+    with torch.no_grad():
+        gen = mine.generator(d["t1w"])
+        p_on_ref = mine.discriminator(gen_ref.to(DEV))
+    tol_d = 1e-4 if precision == "fp32" else 1e-2
+    tol_g = 1e-4 if precision == "fp32" else 1.5e-1
+    assert rel_l2(p_on_ref, p_ref) <= tol_d
+    assert rel_l2(gen, gen_ref) <= tol_g
+    logs = mine.fused_step(d)
+    torch.cuda.synchronize()
+    assert torch.isfinite(logs).all()
+    assert abs(float(logs[0]) - adv_ref) <= (1e-4 if precision == "fp32" else 1e-1) * abs(adv_ref) + 1e-6
+    assert abs(float(logs[1]) - rec_ref) <= (1e-4 if precision == "fp32" else 5e-2) * abs(rec_ref)
+
+
 def test_full_step_tracks_the_oracle():
     """Three full two-optimizer steps with the reference's learning rates (chaotic regime: loose bounds) -- the
     reconstruction loss follows the oracle and the adversarial loss saturates towards the -100 log clamp like the
