@@ -363,6 +363,12 @@ def weight_transpose(src, dst, cy, taps, cx):
     return dst
 
 
+def weight_transpose_batch(table, n, max_elems):
+    """table: (n, 5) int64 device tensor {src ptr, dst ptr, cy, taps, cx} of bf16 tensors."""
+    lib = _lib.require_device()
+    check(lib.mpgan_weight_transpose_batch(ptr(table), n, max_elems, _stream()), "weight_transpose_batch")
+
+
 def permute_flatten(src, dst, rows, c, spatial, to_cl, accumulate=False):
     lib = _lib.require_device()
     check(lib.mpgan_permute_flatten(dt(src), ptr(src), dt(dst), ptr(dst), rows, c, spatial, 1 if to_cl else 0,

@@ -108,6 +108,13 @@ class Runtime:
                 if r.need_wt:
                     r.wt = torch.empty(m.weight.numel(), dtype=torch.bfloat16, device=self.device)
                 self.rec[m] = r
+        # one descriptor table for all transposed copies: refreshed by a single launch
+        wt = [r for r in self.rec.values() if r.wt is not None]
+        self._wt_table = None
+        if wt:
+            rows = [[r.w.data_ptr(), r.wt.data_ptr(), r.spec.cy, r.spec.taps, r.spec.cx] for r in wt]
+            self._wt_table = torch.tensor(rows, dtype=torch.int64, device=self.device)
+            self._wt_max = max(r.spec.cy * r.spec.taps * r.spec.cx for r in wt)
 
     # ------------------------------------------------------------------------------------------------
     def ensure(self, device):
@@ -126,9 +133,7 @@ class Runtime:
         if not force and ver == self._shadow_version:
             return
         ops.cast(self.flat, self.shadow)
-        for r in self.rec.values():
-            if r.wt is not None:
-                ops.weight_transpose(r.w, r.wt, r.spec.cy, r.spec.taps, r.spec.cx)
+        self._refresh_transposes()
         self._shadow_version = ver
 
     def folded(self, conv, bn):
@@ -155,6 +160,10 @@ class Runtime:
         self._folded[conv] = (ver, wf, bf)
         return wf, bf
 
+    def _refresh_transposes(self):
+        if self._wt_table is not None:
+            ops.weight_transpose_batch(self._wt_table, self._wt_table.shape[0], self._wt_max)
+
     def zero_grad(self):
         if self.grad is not None:
             self.grad.zero_()
@@ -163,9 +172,7 @@ class Runtime:
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, b1, b2, eps, self.adam_state, self.shadow)
         self.mark_dirty()
         if self.shadow is not None:  # shadow was written by the Adam kernel; only the transposes remain
-            for r in self.rec.values():
-                if r.wt is not None:
-                    ops.weight_transpose(r.w, r.wt, r.spec.cy, r.spec.taps, r.spec.cx)
+            self._refresh_transposes()
             self._shadow_version = (self.flat._version, self.manual_version)
 
     def requires_grad(self):

@@ -190,6 +190,9 @@ int mpgan_cast(int dtype_src, const void* src, int dtype_dst, void* dst, int64_t
 /* OTI [cy][taps][cx] -> transposed shadow [cx][taps][cy] with dtype conversion. */
 int mpgan_weight_transpose(int dtype_src, const void* src, int dtype_dst, void* dst, int32_t cy, int32_t taps,
                            int32_t cx, void* stream);
+/* the same for n bf16 tensors in one launch: table = n x 5 device int64 {src, dst, cy, taps, cx}; max_elems = the largest
+ * cy*taps*cx (grid sizing) */
+int mpgan_weight_transpose_batch(const int64_t* table_dev, int32_t n, int32_t max_elems, void* stream);
 
 /* ---- RandSpatialCropSamplesd gather (test_runs/GAN.py:263-272,313-337), bit-exact copy ----
  * vol: (batch, *S, c) channels-last; origins: device int32 (batch*num_samples, rank) in (D,H,W) order;
