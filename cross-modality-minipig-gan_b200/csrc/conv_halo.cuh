@@ -108,6 +108,29 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
   {
     const int cpp = C >> 3;
     const int total = N * 9 * cpp;
+    if (P.n_store == 4) {
+      // Stride-2 ConvTranspose / data gradient into ONE channel (k3 s2 p1, X = 2Y) as a stride-1 "pixel-shuffle"
+      // layer: output column n = (i, j) is the parity class of the 2x2 block written by input pixel (a, b), and it
+      // reads the 2x2 neighbourhood Y(a + da, b + db) = halo taps (da + 1, db + 1):
+      //   (0,0): Y00.W11   (0,1): Y01.W10 + Y00.W12   (1,0): Y10.W01 + Y00.W21   (1,1): Y11.W00 + Y10.W02 + Y01.W20 + Y00.W22
+      // P.w is the layer's own [C][9] weight; the [16][9][C] operand is assembled here, zeros elsewhere.
+      for (int e = threadIdx.x; e < N * 9 * C; e += blockDim.x) {
+        const int c = e % C;
+        const int r = e / C;
+        const int tap = r % 9, n = r / 9;
+        int src = -1;
+        if (n == 0) src = tap == 4 ? 4 : -1;
+        else if (n == 1) src = tap == 5 ? 3 : (tap == 4 ? 5 : -1);
+        else if (n == 2) src = tap == 7 ? 1 : (tap == 4 ? 7 : -1);
+        else if (n == 3) src = tap == 8 ? 0 : (tap == 7 ? 2 : (tap == 5 ? 6 : (tap == 4 ? 8 : -1)));
+        const bf16 v = src >= 0 ? P.w[c * 9 + src] : from_f<bf16>(0.f);
+        const int kc = c / KC, cc = c - kc * KC;
+        const uint32_t blk = (uint32_t)((tap * nkc + kc) * N) * rowb;
+        uint32_t off = (uint32_t)n * rowb + (uint32_t)(cc >> 3) * 16;
+        off ^= ((off >> 7) & swz_mask) << 4;
+        *reinterpret_cast<bf16*>(w_sm + blk + off + (cc & 7) * 2) = v;
+      }
+    } else
     for (int g = threadIdx.x; g < total; g += blockDim.x) {
       const int chunk = g % cpp;
       const int r = g / cpp;
@@ -118,7 +141,7 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
       off ^= ((off >> 7) & swz_mask) << 4;
       cp_async16(smem_u32(w_sm + blk + off), P.w + (size_t)g * 8);
     }
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s_bias[i] = P.bias ? __ldg(&P.bias[i]) : 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_bias[i] = P.bias ? __ldg(&P.bias[P.n_store == 4 ? 0 : i]) : 0.f;
     cp_async_wait_all();
     fence_proxy_async();   // these generic-proxy writes are read by tcgen05.mma (async proxy)
   }
@@ -228,6 +251,27 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive(&tempty[acc]);
         const bf16* rrow = P.res ? P.res + (long long)img * P.res_sn + (long long)oh * P.res_sh + (long long)ow * P.res_sw + c0
                                  : nullptr;
+        if (P.n_store == 4) {   // 2x2 pixel shuffle into a one-channel image of twice the size (+ its BatchNorm statistics)
+          if (c0 == 0) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r[e]) + s_bias[0];
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+            if (valid) {
+              bf16* o = P.out + (long long)img * P.out_sn + (long long)(2 * oh) * P.out_sh + 2 * ow;
+              *reinterpret_cast<__nv_bfloat162*>(o) = h0;
+              *reinterpret_cast<__nv_bfloat162*>(o + P.out_sh) = h1;
+              if (P.stats) {
+                const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                const float sa = (f0.x + f0.y) + (f1.x + f1.y);
+                const float sb = fmaf(f0.x, f0.x, f0.y * f0.y) + fmaf(f1.x, f1.x, f1.y * f1.y);
+                s1[0] = fma_f32x2(pack_f32x2(sa, 0.f), pack_f32x2(1.f, 1.f), s1[0]);
+                s2[0] = fma_f32x2(pack_f32x2(sb, 0.f), pack_f32x2(1.f, 1.f), s2[0]);
+              }
+            }
+          }
+          continue;
+        }
         if (P.n_store == 1) {   // one real output channel (data gradient of a one-input-channel layer)
           if (valid && c0 == 0) {
             float v = __uint_as_float(r[0]) + s_bias[0];
@@ -335,7 +379,9 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
       double s = 0.0;
 #pragma unroll
       for (int e = 0; e < 8; ++e) s += (double)s_stats[e * 2 * N + i];
-      if (s != 0.0) atomicAdd(&P.stats[i], s);
+      if (P.n_store == 4) {   // one real channel: {sum, sum of squares} live in slots 0 and N
+        if (i == 0 || i == N) atomicAdd(&P.stats[i == 0 ? 0 : 1], s);
+      } else if (s != 0.0) atomicAdd(&P.stats[i], s);
     }
   }
   if (warp == 2) {
@@ -365,11 +411,11 @@ static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, in
                        const void* res, int64_t ldres, cudaStream_t s, int n_store = 0, const float* slope = nullptr) {
   if (!(C == 16 || C == 32 || C == 64 || C == 128)) return 1;
   if (!(N == 16 || N == 32 || N == 64 || N == 128)) return 1;
-  if (ldi % 8 != 0 || ((uintptr_t)in & 15) || ((uintptr_t)w & 15)) return 1;
+  if (ldi % 8 != 0 || ((uintptr_t)in & 15) || (n_store != 4 && ((uintptr_t)w & 15))) return 1;
   if (n_store == 0) {
     if (ldo % 8 != 0 || ((uintptr_t)out & 15)) return 1;
     if (res && (ldres % 8 != 0 || ((uintptr_t)res & 15))) return 1;
-  } else if (N != 16 || stats) {
+  } else if (N != 16 || (n_store == 1 && stats)) {
     return 1;
   }
   const int KC = C < 64 ? C : 64;
@@ -396,6 +442,7 @@ static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, in
   P.nbuf = nbuf;
   P.w = (const bf16*)w; P.out = (bf16*)out;
   P.out_sn = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo; P.out_sw = ldo;
+  if (n_store == 4) { P.out_sn = 4LL * oh * ow; P.out_sh = 2LL * ow; P.out_sw = 1; }   // one-channel image of twice the size
   P.bias = bias; P.stats = stats;
   P.wide = (n_store == 0 && ldo % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
   P.n_store = n_store;

@@ -1102,6 +1102,24 @@ extern "C" int mpgan_tc_conv_bprop_c1out(const MpganConvGeom* g, const void* y, 
   return rc;
 }
 
+// ConvTranspose(C -> 1, k3 s2 p1 op1) forward == data gradient of a one-input-channel stride-2 3x3 convolution: the
+// halo kernel in its pixel-shuffle mode (conv_halo.cuh, n_store == 4).  w: the layer's bf16 [C][9] weight;
+// x: (n, 2*yh, 2*yw) one channel contiguous; stats (optional): fp64 {sum, sum of squares} of the stored values.
+extern "C" int mpgan_tc_convt_to1(const MpganConvGeom* g, const void* y, int64_t ldy, const void* w, const float* bias,
+                                  void* x, double* stats, void* stream) {
+  MPGAN_REQUIRE(g && g->rank == 2 && g->cx == 1, MPGAN_ERR_UNSUPPORTED, "convt_to1: rank-2 layer with one X channel");
+  MPGAN_REQUIRE(g->k[1] == 3 && g->k[2] == 3 && g->stride[1] == 2 && g->stride[2] == 2 && g->pad[1] == 1 && g->pad[2] == 1,
+                MPGAN_ERR_UNSUPPORTED, "convt_to1: 3x3, stride 2, pad 1");
+  MPGAN_REQUIRE(g->xs[1] == 2 * g->ys[1] && g->xs[2] == 2 * g->ys[2], MPGAN_ERR_UNSUPPORTED, "convt_to1: X = 2 Y only");
+  MPGAN_REQUIRE(g->cy == 16 || g->cy == 32 || g->cy == 64, MPGAN_ERR_UNSUPPORTED, "convt_to1: cy in {16, 32, 64}");
+  MPGAN_REQUIRE(y && w && x && ((uintptr_t)x & 3) == 0, MPGAN_ERR_SHAPE, "convt_to1: bad arguments");
+  // out strides describe the one-channel OUTPUT image (row pitch 2*yw); the tile grid is the Y grid
+  int rc = halo3x3_run(0, g->n, g->ys[1], g->ys[2], g->ys[1], g->ys[2], g->cy, 16, 1, y, ldy, w, bias, x,
+                       /*ldo, patched below*/ 1, stats, nullptr, 0, (cudaStream_t)stream, 4);
+  MPGAN_REQUIRE(rc != 1, MPGAN_ERR_UNSUPPORTED, "convt_to1: layer not covered by the halo kernel (alignment / size)");
+  return rc;
+}
+
 extern "C" size_t mpgan_tc_conv_wgrad_workspace(const MpganConvGeom* g) {
   (void)g;
   return 0;  // split partials are reduced with fp32 atomics straight into dw

@@ -37,6 +37,7 @@ _SIGS = {
     "mpgan_tc_conv_fprop": (c_int, [_G, _P, c_int64, _P, _P, _P, c_int64, _P, _P]),
     "mpgan_tc_conv_bprop": (c_int, [_G, _P, c_int64, _P, _P, _P, c_int64, _P, _P]),
     "mpgan_tc_conv_act": (c_int, [_G, c_int, _P, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P]),
+    "mpgan_tc_convt_to1": (c_int, [_G, _P, c_int64, _P, _P, _P, _P, _P]),
     "mpgan_tc_conv_bprop_c1out": (c_int, [_G, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P]),
     "mpgan_tc_conv_bprop_res": (c_int, [_G, _P, c_int64, _P, _P, _P, c_int64, _P, c_int64, _P, _P]),
     "mpgan_tc_conv_wgrad_workspace": (c_size_t, [_G]),

@@ -148,6 +148,7 @@ def conv_act(spec, x, w, bias, slope, res=None, out=None):
 
 
 _C1OUT = os.environ.get("MPGAN_NO_C1OUT", "0") != "1"
+_CONVT1 = os.environ.get("MPGAN_NO_CONVT1", "0") != "1"
 
 
 def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True, use_c1=True, res=None,
@@ -174,6 +175,16 @@ def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True,
         check(lib.mpgan_tc_conv_bprop_c1out(ctypes.byref(g), ptr(y), ld(y), ptr(wt16), ptr(out), ld(out), ptr(res),
                                             ld(res) if res is not None else 0, _stream()), "tc_conv_bprop_c1out")
         return out, False
+    if (use_tc and use_c1 and w is not None and w.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and spec.rank == 2
+            and spec.cx == 1 and spec.k == (3, 3) and spec.stride == (2, 2) and spec.pad == (1, 1) and spec.cy in (16, 32, 64)
+            and tuple(xs) == (2 * ys[0], 2 * ys[1]) and ld(y) % 8 == 0 and out.is_contiguous() and _CONVT1
+            and ys[1] % 8 == 0):
+        # stride-2 ConvTranspose / data gradient into one channel: halo tcgen05 kernel in pixel-shuffle mode
+        check(lib.mpgan_tc_convt_to1(ctypes.byref(g), ptr(y), ld(y), ptr(w), ptr(bias), ptr(out), ptr(stats), _stream()),
+              "tc_convt_to1")
+        if res is not None:
+            add_copy(out, res, out)
+        return out, stats is not None
     if use_tc and wt is not None and y.dtype == torch.bfloat16 and tc_supported(g, 1):
         if res is not None and res.dtype == torch.bfloat16 and ld(res) % 8 == 0 and res.data_ptr() % 16 == 0:
             check(lib.mpgan_tc_conv_bprop_res(ctypes.byref(g), ptr(y), ld(y), ptr(wt), ptr(bias), ptr(out), ld(out),

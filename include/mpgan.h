@@ -80,6 +80,11 @@ int mpgan_tc_conv_bprop(const MpganConvGeom* g, const void* y, int64_t ldy, cons
 int mpgan_tc_conv_act(const MpganConvGeom* g, int direction, const void* in, int64_t ldi, const void* w,
                       const float* bias, const float* slope, const void* res, int64_t ldres, void* out, int64_t ldo,
                       void* stream);
+/* ConvTranspose(cy -> 1, k3 s2 p1 op1) forward == data gradient of a one-input-channel stride-2 3x3 convolution, through
+ * the halo tcgen05 kernel in pixel-shuffle mode: w = the layer's bf16 [cy][9] weight, x = (n, 2*yh, 2*yw) one channel,
+ * stats (optional) = fp64 {sum, sum of squares} of the stored values (fused BatchNorm(1) statistics). */
+int mpgan_tc_convt_to1(const MpganConvGeom* g, const void* y, int64_t ldy, const void* w, const float* bias, void* x,
+                       double* stats, void* stream);
 /* data gradient of a one-input-channel stride-1 3x3 layer (cx == 1; dY has cy in {16,32,64,128} channels) through the
  * halo-resident tcgen05 kernel: w_b16 = bf16 [16][9][cy], row 0 the layer's transposed weights, rows 1..15 zero;
  * x: (n, xh, xw) one channel, pixel stride ldx; res (optional, same layout, stride ldres) is added. */

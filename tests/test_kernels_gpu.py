@@ -128,6 +128,28 @@ def test_c1_dgrad_through_tensor_cores(n, cout, size, p):
     assert rel_l2(dx2.float() - r.float(), dx.float()) <= 6e-3
 
 
+@pytest.mark.parametrize("n,cin,size", [(2, 32, 24), (3, 16, 40), (1, 64, 16)])
+def test_convt_into_one_channel_through_tensor_cores(n, cin, size):
+    """ConvTranspose2d(cin -> 1, k3 s2 p1 op1) forward (== data gradient of a 1 -> cin stride-2 conv) through the halo
+    kernel's pixel-shuffle mode, with the fused one-channel BatchNorm statistics."""
+    ct = torch.nn.ConvTranspose2d(cin, 1, 3, stride=2, padding=1, output_padding=1).to(DEV)
+    with torch.no_grad():
+        ct.weight.copy_(ct.weight.bfloat16().float())
+    x = rnd(n, cin, size, size, seed=3).bfloat16().float()
+    ref = ct(x)
+    spec = ops.ConvSpec.from_module(ct)
+    assert spec.transposed and spec.cx == 1 and spec.cy == cin
+    w = ct.weight.detach().permute(0, 2, 3, 1).reshape(cin, 9, 1).contiguous().bfloat16()    # [cy][taps][cx]
+    stats = torch.zeros(2, dtype=torch.float64, device=DEV)
+    calls0 = ops._lib.ABI_CALLS
+    y, fused = ops.conv_bprop(spec, cl(x, torch.bfloat16), w, None, ct.bias.detach(), stats=stats)
+    assert ops._lib.ABI_CALLS - calls0 == 1 and fused
+    assert y.shape == (n, 2 * size, 2 * size, 1)
+    assert rel_l2(uncl(y), ref) <= 6e-3
+    yd = y.double().reshape(-1)
+    assert torch.allclose(stats, torch.stack([yd.sum(), (yd * yd).sum()]), rtol=1e-6, atol=1e-6)
+
+
 def test_conv_transpose_is_bprop():
     """ConvTranspose2d(k3,s2,p1,op1) forward == bprop of the underlying conv with the same OTI weight."""
     ct = torch.nn.ConvTranspose2d(24, 8, 3, stride=2, padding=1, output_padding=1).to(DEV)
