@@ -151,7 +151,9 @@ def test_inference_volume_matches_oracle_and_batching_is_invisible():
     out = inference.infer_volume(model, t1.cuda(), batch=2)            # 2 + 1: ragged last batch
     assert out.shape == t1.shape and rel_l2(out, ref) <= 1e-4           # fp32 mode tolerance (north_star)
     one = inference.infer_volume(model.generator, t1.cuda(), batch=64)
-    assert torch.equal(one, out)                                        # eval-mode BN: batching cannot change a bit
+    assert torch.equal(one, out)
+    gg = inference.GraphedGenerator(model, (2, 1, 512, 512), torch.device("cuda"))
+    assert torch.equal(inference.infer_volume(model, t1.cuda(), batch=2, graphed=gg), out)   # graph replay + eager tail                                        # eval-mode BN: batching cannot change a bit
     disp = inference.to_display_range(out)
     assert np.array_equal(disp.cpu().numpy(), ot.to_display_range(out.cpu().numpy()))
     m = inference.evaluate(out, t2.cuda())
