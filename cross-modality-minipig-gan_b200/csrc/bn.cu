@@ -633,6 +633,75 @@ c1_tail_fwd_kernel(const bf16* __restrict__ c, int n, int H, int W, const BnTrai
   }
 }
 
+
+// Backward twin of c1_tail_fwd_kernel: for the one-channel tail  y = conv3x3(h) + bias + h,  h = prelu(bn(c)):
+//   dh = conv3x3^T(dy) + dy        (data gradient of the 1->1 conv plus the identity residual, rounded to bf16 at the same
+//                                    two points as the unfused kernels)
+// and, in the same pass, the BatchNorm(1) + PReLU backward REDUCTION of the layer below it:
+//   sums[0] += sum dz,  sums[1] += sum dz * xhat,  sums[2] += sum_{z<=0} dh * z      with z = c*scale + shift, dz = dh * prelu'(z)
+// (replaces c1f::bprop_kernel<1,1> + add_copy + bn_act_bwd_reduce_kernel<1>: three launches on the backward critical path).
+__global__ void __launch_bounds__(kThreads)
+c1_tail_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ c, int n, int H, int W,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
+                          const float* __restrict__ shift, const float* __restrict__ alpha, const bf16* __restrict__ w9,
+                          bf16* __restrict__ dh_out, double* __restrict__ sums) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ double red[3][kThreads / 32];
+  const float sc = scale[0], sh = shift[0], mu = mean[0], is = invstd[0], slope = alpha[0];
+  float wt[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wt[t] = to_f(w9[8 - t]);      // flipped taps: dh[q] = sum_t w[8 - t] * dy[q - 1 + t]
+  const int wq = (W + 3) / 4;
+  const int64_t runs = (int64_t)n * H * wq;
+  float a0 = 0.f, a1 = 0.f, fs = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < runs; r += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(r % wq);
+    const int64_t row = r / wq;
+    const int hh = (int)(row % H), img = (int)(row / H);
+    const int w0 = q * 4;
+    const bf16* di = dy + (int64_t)img * H * W;
+    float dv[3][6];
+#pragma unroll
+    for (int rh = 0; rh < 3; ++rh) {
+      const int y = hh - 1 + rh;
+      const bool oky = (unsigned)y < (unsigned)H;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int x = w0 - 1 + j;
+        dv[rh][j] = (oky && (unsigned)x < (unsigned)W) ? to_f(di[(int64_t)y * W + x]) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (w0 + i >= W) break;
+      float acc = 0.f;
+#pragma unroll
+      for (int rh = 0; rh < 3; ++rh)
+#pragma unroll
+        for (int rw = 0; rw < 3; ++rw) acc = fmaf(dv[rh][i + rw], wt[rh * 3 + rw], acc);
+      const bf16 dhb = from_f<bf16>(to_f(from_f<bf16>(acc)) + dv[1][i + 1]);
+      const int64_t o = ((int64_t)img * H + hh) * W + w0 + i;
+      dh_out[o] = dhb;
+      const float g = to_f(dhb), cv = to_f(c[o]);
+      const float z = fmaf(cv, sc, sh);
+      if (z <= 0.f) fs = fmaf(g, z, fs);
+      const float gz = g * (z > 0.f ? 1.f : slope);
+      a0 += gz;
+      a1 = fmaf(gz, (cv - mu) * is, a1);
+    }
+  }
+  double r0 = warp_sum((double)a0), r1 = warp_sum((double)a1), r2 = warp_sum((double)fs);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = r0; red[1][threadIdx.x >> 5] = r1; red[2][threadIdx.x >> 5] = r2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) t += red[threadIdx.x][i];
+    atomicAdd(&sums[threadIdx.x], t);
+  }
+}
+
 }  // namespace mpgan
 
 extern "C" int mpgan_c1_tail_fwd(const void* c_bf16, int32_t n, int32_t h, int32_t w, const double* stats,
@@ -654,6 +723,24 @@ extern "C" int mpgan_c1_tail_fwd(const void* c_bf16, int32_t n, int32_t h, int32
   launch_k(c1_tail_fwd_kernel, (int)blocks, kThreads, 0, (cudaStream_t)stream, (const bf16*)c_bf16, (int)n, (int)h, (int)w, f,
            alpha, (const bf16*)w9_bf16, bias, (bf16*)h_out_bf16, (bf16*)y_out_bf16);
   MPGAN_CHECK_LAUNCH("c1_tail_fwd_kernel");
+  return 0;
+}
+
+extern "C" int mpgan_c1_tail_bwd_reduce(const void* dy_bf16, const void* c_bf16, int32_t n, int32_t h, int32_t w,
+                                        const float* mean, const float* invstd, const float* scale, const float* shift,
+                                        const float* alpha, const void* w9_bf16, void* dh_bf16, double* sums3,
+                                        void* stream) {
+  MPGAN_REQUIRE(dy_bf16 && c_bf16 && mean && invstd && scale && shift && alpha && w9_bf16 && dh_bf16 && sums3,
+                MPGAN_ERR_SHAPE, "c1_tail_bwd_reduce: null pointer");
+  MPGAN_REQUIRE(n > 0 && h > 0 && w > 0, MPGAN_ERR_SHAPE, "c1_tail_bwd_reduce: empty tensor");
+  const int64_t runs = (int64_t)n * h * ((w + 3) / 4);
+  int64_t blocks = ceil_div(runs, (int64_t)kThreads * 2);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  launch_k(c1_tail_bwd_reduce_kernel, (int)blocks, kThreads, 0, (cudaStream_t)stream, (const bf16*)dy_bf16,
+           (const bf16*)c_bf16, (int)n, (int)h, (int)w, mean, invstd, scale, shift, alpha, (const bf16*)w9_bf16,
+           (bf16*)dh_bf16, sums3);
+  MPGAN_CHECK_LAUNCH("c1_tail_bwd_reduce_kernel");
   return 0;
 }
 

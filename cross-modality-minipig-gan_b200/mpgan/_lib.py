@@ -73,6 +73,7 @@ _SIGS = {
     "mpgan_patch_scatter_add": (c_int, [c_int, _P, c_int32, c_int32, _P, c_int32, _P, c_int32, c_int32, _P, _P]),
     "mpgan_c1_tail_fwd": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P,
                                   _P, _P, _P, _P, _P, _P, _P]),
+    "mpgan_c1_tail_bwd_reduce": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mpgan_im2col_c1": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "mpgan_fold_dw16": (c_int, [_P, c_int32, _P, _P]),
     "mpgan_order_stats_workspace": (c_size_t, [c_int32]),

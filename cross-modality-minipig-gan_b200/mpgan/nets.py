@@ -411,12 +411,38 @@ class UNet(nn.Module):
         return y
 
     @staticmethod
+    def _tail_bwd(up, dy, plan):
+        """Backward of the fused tail (see _tail_fwd): the 1->1 conv's weight gradient goes to the weight-gradient
+        stream as usual; its data gradient, the residual add and the BatchNorm(1) backward reduction are one kernel,
+        the BatchNorm apply the second; then the ConvTranspose backward.  None when the pattern does not apply."""
+        conv0, ru = up[0], up[1]
+        if (plan.dtype != torch.bfloat16 or conv0.out_channels != 1 or conv0.conv_only or dy.dim() != 4
+                or len(ru.conv) != 1 or not ru.conv[0].conv_only or not isinstance(ru.residual, nn.Identity)
+                or len(plan.tape) < 3 or len(plan.tape[-3]) != 4 or not plan.tape[-3][3]      # trained BatchNorm only
+                or os.environ.get("MPGAN_NO_TAIL_FUSION", "0") == "1"):
+            return None
+        rec0, rec1 = plan.rt.rec[conv0.conv], plan.rt.rec[ru.conv[0].conv]
+        plan.tape.pop()                       # ResidualUnit (h,)
+        (h,) = plan.tape.pop()                # conv-only Convolution (h,)
+        cat, c, saved, _ = plan.tape.pop()    # ConvTranspose Convolution
+        dyc = dy if dy.is_contiguous() else dy.contiguous()
+        conv_backward(rec1, h, dyc, plan, need_dx=False)          # weight / bias gradient of the 1->1 conv
+        wg = plan.need_wgrad
+        sums = plan.zeros64(3, dy.device)
+        dc = ops.c1_tail_bwd(dyc, c, saved, conv0.norm, conv0.act.weight, rec1.w, sums,
+                             conv0.norm.weight.grad if wg else None, conv0.norm.bias.grad if wg else None,
+                             conv0.act.weight.grad if wg else None, rec0.db if wg else None)
+        return conv_backward(rec0, cat, dc, plan, need_dx=True, bias_done=True)
+
+    @staticmethod
     def _block_bwd(block, dy, plan, need_dx=True, res=None):
         down, skip, up = block[0], block[1], block[2]
         sub = skip.submodule
         cd = down.out_channels
-        dh = up[1]._bwd(dy, plan)
-        dcat = up[0]._bwd(dh, plan)
+        dcat = UNet._tail_bwd(up, dy, plan)
+        if dcat is None:
+            dh = up[1]._bwd(dy, plan)
+            dcat = up[0]._bwd(dh, plan)
         # the sub-block's gradient is the upper channel slice of dcat: one packing copy (7 us) lets its BatchNorm
         # backward run on the contiguous streaming kernels (2 x 8 us) instead of the strided ones (2 x 20 us)
         dsub = dcat[..., cd:]

@@ -308,6 +308,24 @@ def c1_tail_fwd(c, stats, bn, saved, alpha, w9, bias, want_h):
     return hmap, y
 
 
+def c1_tail_bwd(dy, c, saved, bn, alpha, w9, sums, dgamma, dbeta, dalpha, dbias):
+    """Backward of the fused UNet tail down to the ConvTranspose output: dc (gradient of the raw ConvTranspose
+    output c) from dy (gradient of the tail's output).  Two launches: fused data-gradient + BatchNorm reduction, then
+    the BatchNorm / PReLU backward apply."""
+    lib = _lib.require_device()
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and c.is_contiguous() and c.shape == dy.shape
+    n, h, w = c.shape[0], c.shape[1], c.shape[2]
+    mean, invstd, scale, shift = saved
+    dh = torch.empty_like(c)
+    check(lib.mpgan_c1_tail_bwd_reduce(ptr(dy), ptr(c), n, h, w, ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(alpha),
+                                       ptr(w9), ptr(dh), ptr(sums), _stream()), "c1_tail_bwd_reduce")
+    dc = torch.empty_like(c)
+    check(lib.mpgan_bn_act_bwd_apply(dt(c), ptr(dh), ld(dh), ptr(c), ld(c), pixels(c), 1, ptr(mean), ptr(invstd),
+                                     ptr(scale), ptr(shift), ACT_PRELU, ptr(alpha), 0.0, ptr(sums), ptr(dgamma),
+                                     ptr(dbeta), ptr(dalpha), ptr(dbias), ptr(dc), ld(dc), _stream()), "bn_act_bwd_apply")
+    return dc
+
+
 def bn_act_bwd(dy, x, mean, invstd, scale, shift, act, alpha, leaky, sums, dgamma, dbeta, dalpha, dx, dbias=None):
     lib = _lib.require_device()
     check_act(dy), check_act(x), check_act(dx)

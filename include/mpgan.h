@@ -218,6 +218,12 @@ int mpgan_c1_tail_fwd(const void* c_bf16, int32_t n, int32_t h, int32_t w, const
                       int64_t* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
                       const float* alpha, const void* w9_bf16, const float* bias, void* h_out_bf16, void* y_out_bf16,
                       void* stream);
+/* backward twin: dh = conv3x3^T(dy, w9) + dy (bf16, same layout) and the BatchNorm(1) + PReLU backward reduction of c in
+ * the same pass: sums3[0] += sum dz, sums3[1] += sum dz*xhat, sums3[2] += sum_{z<=0} dh*z (the layout
+ * mpgan_bn_act_bwd_apply reads with c == 1); mean / invstd / scale / shift = the values saved by the forward. */
+int mpgan_c1_tail_bwd_reduce(const void* dy_bf16, const void* c_bf16, int32_t n, int32_t h, int32_t w, const float* mean,
+                             const float* invstd, const float* scale, const float* shift, const float* alpha,
+                             const void* w9_bf16, void* dh_bf16, double* sums3, void* stream);
 
 /* ---- one-input-channel 3x3 weight gradient through the tensor cores (conv_c1col.cu) ----
  * im2col_c1: x (n, ih, iw) contiguous bf16, one channel -> xcol (n, oh, ow, 16) bf16: the 9 taps of every output pixel
