@@ -1,4 +1,6 @@
 """Per-kernel parity on the GPU, through the C ABI, against plain torch fp32 references of the same op."""
+import copy
+
 import numpy as np
 import pytest
 import torch
@@ -148,6 +150,45 @@ def test_convt_into_one_channel_through_tensor_cores(n, cin, size):
     assert rel_l2(uncl(y), ref) <= 6e-3
     yd = y.double().reshape(-1)
     assert torch.allclose(stats, torch.stack([yd.sum(), (yd * yd).sum()]), rtol=1e-6, atol=1e-6)
+
+
+def test_fused_unet_tail_forward_and_backward():
+    """c1_tail_fwd / c1_tail_bwd (one-channel UNet tail: BatchNorm(1) -> PReLU -> conv3x3(1->1) + residual) against
+    torch autograd on the same bf16-rounded tensors: outputs, running statistics and every gradient."""
+    n, H, W = 3, 40, 24
+    c = (rnd(n, 1, H, W, seed=1) * 3 + 0.7).bfloat16().float().requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(1).to(DEV)
+    with torch.no_grad():
+        bn.weight.fill_(1.3), bn.bias.fill_(-0.2)
+    act = torch.nn.PReLU().to(DEV)
+    conv = torch.nn.Conv2d(1, 1, 3, padding=1).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.bfloat16().float())
+    bn2 = copy.deepcopy(bn)
+    h_ref = act(bn(c))
+    y_ref = conv(h_ref) + h_ref
+    dy = rnd(n, 1, H, W, seed=2).bfloat16().float()
+    y_ref.backward(dy)
+    # ---- forward
+    ccl = cl(c.detach(), torch.bfloat16)
+    stats = torch.zeros(2, dtype=torch.float64, device=DEV)
+    ops.bn_stats(ccl, stats)
+    saved = torch.empty((4, 1), dtype=torch.float32, device=DEV)
+    w9 = conv.weight.detach().reshape(9).bfloat16().contiguous()
+    hk, yk = ops.c1_tail_fwd(ccl, stats, bn2, saved, act.weight.detach(), w9, conv.bias.detach(), True)
+    assert rel_l2(uncl(hk), h_ref) <= 6e-3 and rel_l2(uncl(yk), y_ref) <= 6e-3
+    assert torch.allclose(bn2.running_mean, bn.running_mean, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(bn2.running_var, bn.running_var, rtol=1e-4, atol=1e-6)
+    assert int(bn2.num_batches_tracked) == 1
+    # ---- backward down to dc (gradient of the BatchNorm input)
+    sums = torch.zeros(3, dtype=torch.float64, device=DEV)
+    dgamma, dbeta, dalpha, dbias = (torch.zeros(1, device=DEV) for _ in range(4))
+    dc = ops.c1_tail_bwd(cl(dy, torch.bfloat16), ccl, (saved[0], saved[1], saved[2], saved[3]), bn2, act.weight.detach(), w9,
+                         sums, dgamma, dbeta, dalpha, dbias)
+    assert rel_l2(uncl(dc), c.grad) <= 1.5e-2          # bf16-rounded dh feeds the BatchNorm backward
+    assert abs(float(dgamma) - float(bn.weight.grad)) <= 1e-2 * abs(float(bn.weight.grad)) + 1e-3
+    assert abs(float(dbeta) - float(bn.bias.grad)) <= 1e-2 * abs(float(bn.bias.grad)) + 1e-3
+    assert abs(float(dalpha) - float(act.weight.grad)) <= 1e-2 * abs(float(act.weight.grad)) + 1e-3
 
 
 def test_conv_transpose_is_bprop():
