@@ -47,6 +47,7 @@ struct TapGemmParams {
   int tw_log2, th_log2;
   int nimg;
   int n_total, n_tiles;
+  int cls_minor;       // tile order: the parity classes of one spatial tile are consecutive (equal tap counts only)
   int mt;              // 128-pixel tiles per weight stage (1, or 2 for large BN = 128 layers)
   int lane_parallel;   // taps of a tile are loaded by different lanes (needs max taps per class * nkc <= STAGES)
   long long out_sn, out_sh, out_sw;
@@ -188,9 +189,14 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       TileWalk<5> tw5;
-      { const int radix[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30}; tw5.init((int)blockIdx.x, (int)gridDim.x, radix); }
+      {
+        const int rmaj[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30};
+        const int rmin[5] = {P.ncls, P.n_tiles, P.tiles_w, P.tiles_h, 1 << 30};
+        if (P.cls_minor) tw5.init((int)blockIdx.x, (int)gridDim.x, rmin); else tw5.init((int)blockIdx.x, (int)gridDim.x, rmaj);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw5.next()) {
-        const int nt = tw5.d[0], twi = tw5.d[1], thi = tw5.d[2], tni = tw5.d[3], cls = tw5.d[4];
+        const int o5 = P.cls_minor ? 1 : 0;   // class-minor order puts the class digit first
+        const int nt = tw5.d[o5], twi = tw5.d[o5 + 1], thi = tw5.d[o5 + 2], tni = tw5.d[o5 + 3], cls = P.cls_minor ? tw5.d[0] : tw5.d[4];
         const int w0 = (twi * MT) << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
         for (int tap = P.cls_tap_begin[cls]; tap < P.cls_tap_begin[cls + 1]; ++tap) {
           const int mi = P.tap_map[tap];
@@ -219,9 +225,14 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
     const CUtensorMap* mA = &tmA0;
     uint32_t cnt = 0;   // ring position of the tile's first stage (identical in all lanes)
     TileWalk<5> tw5;
-    { const int radix[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30}; tw5.init((int)blockIdx.x, (int)gridDim.x, radix); }
+    {
+        const int rmaj[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30};
+        const int rmin[5] = {P.ncls, P.n_tiles, P.tiles_w, P.tiles_h, 1 << 30};
+        if (P.cls_minor) tw5.init((int)blockIdx.x, (int)gridDim.x, rmin); else tw5.init((int)blockIdx.x, (int)gridDim.x, rmaj);
+      }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw5.next()) {
-      const int nt = tw5.d[0], twi = tw5.d[1], thi = tw5.d[2], tni = tw5.d[3], cls = tw5.d[4];
+      const int o5 = P.cls_minor ? 1 : 0;   // class-minor order puts the class digit first
+        const int nt = tw5.d[o5], twi = tw5.d[o5 + 1], thi = tw5.d[o5 + 2], tni = tw5.d[o5 + 3], cls = P.cls_minor ? tw5.d[0] : tw5.d[4];
       if (cls != cur_cls) {
         cur_cls = cls;
         const int tb = P.cls_tap_begin[cls];
@@ -260,9 +271,9 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
       uint32_t phase = 0;
       int it = 0;
       TileWalk<2> tw2;
-      { const int radix[2] = {per_cls, 1 << 30}; tw2.init((int)blockIdx.x, (int)gridDim.x, radix); }
+      { const int radix[2] = {P.cls_minor ? P.ncls : per_cls, 1 << 30}; tw2.init((int)blockIdx.x, (int)gridDim.x, radix); }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it, tw2.next()) {
-        const int cls = tw2.d[1];
+        const int cls = P.cls_minor ? tw2.d[0] : tw2.d[1];
         const int buf = it % NACC;
         const uint32_t par = (uint32_t)(it / NACC) & 1u;
         mbar_wait(&tempty[buf], par ^ 1);
@@ -320,10 +331,15 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
       };
       int it = 0;
       TileWalk<5> tw5;
-      { const int radix[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30}; tw5.init((int)blockIdx.x, (int)gridDim.x, radix); }
+      {
+        const int rmaj[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30};
+        const int rmin[5] = {P.ncls, P.n_tiles, P.tiles_w, P.tiles_h, 1 << 30};
+        if (P.cls_minor) tw5.init((int)blockIdx.x, (int)gridDim.x, rmin); else tw5.init((int)blockIdx.x, (int)gridDim.x, rmaj);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it, tw5.next()) {
         if (NCH == 1 && (it & 1) != half) continue;
-        const int nt = tw5.d[0], twi = tw5.d[1], thi = tw5.d[2], tni = tw5.d[3], cls = tw5.d[4];
+        const int o5 = P.cls_minor ? 1 : 0;   // class-minor order puts the class digit first
+        const int nt = tw5.d[o5], twi = tw5.d[o5 + 1], thi = tw5.d[o5 + 2], tni = tw5.d[o5 + 3], cls = P.cls_minor ? tw5.d[0] : tw5.d[4];
         const int ow = (twi << P.tw_log2) + lw, oh = (thi << P.th_log2) + lh, img = (tni << tn_log2) + ln;
         const bool valid = img < P.nimg && oh < P.cls_oh[cls] && ow < P.cls_ow[cls];
         const int nbase = nt * BN;
@@ -354,9 +370,14 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
     } else {
     int it = 0;
     TileWalk<5> tw5;
-    { const int radix[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30}; tw5.init((int)blockIdx.x, (int)gridDim.x, radix); }
+    {
+        const int rmaj[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30};
+        const int rmin[5] = {P.ncls, P.n_tiles, P.tiles_w, P.tiles_h, 1 << 30};
+        if (P.cls_minor) tw5.init((int)blockIdx.x, (int)gridDim.x, rmin); else tw5.init((int)blockIdx.x, (int)gridDim.x, rmaj);
+      }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it, tw5.next()) {
-      const int nt = tw5.d[0], twi = tw5.d[1], thi = tw5.d[2], tni = tw5.d[3], cls = tw5.d[4];
+      const int o5 = P.cls_minor ? 1 : 0;   // class-minor order puts the class digit first
+        const int nt = tw5.d[o5], twi = tw5.d[o5 + 1], thi = tw5.d[o5 + 2], tni = tw5.d[o5 + 3], cls = P.cls_minor ? tw5.d[0] : tw5.d[4];
       const int nbase = nt * BN;
       const int buf = it % NACC;
       const uint32_t par = (uint32_t)(it / NACC) & 1u;
@@ -800,6 +821,16 @@ static int launch_tapgemm_t(const TapGemmParams& P, const CUtensorMap* mA, const
   int max_taps = 0;
   for (int c = 0; c < P.ncls; ++c) max_taps = std::max(max_taps, P.cls_tap_begin[c + 1] - P.cls_tap_begin[c]);
   TapGemmParams Q = P;
+  {
+    // stride-2 data gradients sweep dY once per parity class; with equal tap counts (4x4 kernels) the four classes of a
+    // spatial tile are made consecutive so that the dY region is re-read from L2 instead of HBM (D3: dY is 256 MB)
+    bool equal = P.ncls > 1;
+    for (int c = 1; c < P.ncls; ++c)
+      equal = equal && (P.cls_tap_begin[c + 1] - P.cls_tap_begin[c] == P.cls_tap_begin[1] - P.cls_tap_begin[0]);
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("MPGAN_NO_CLS_MINOR"); off = (e && e[0] == '1') ? 1 : 0; }
+    Q.cls_minor = (equal && !off) ? 1 : 0;
+  }
   Q.lane_parallel = (max_taps * P.nkc <= Cfg::STAGES && max_taps <= 32) ? 1 : 0;
   launch_k(tapgemm_kernel<BN, KC, MT>, grid, EpiCfg<BN>::THREADS, Cfg::SMEM_BYTES, s, Q, mA[0], mA[1], mA[2], mA[3], mB);
   MPGAN_CHECK_LAUNCH("tapgemm_kernel");
