@@ -13,9 +13,16 @@ e2e    : the same step driven from pinned HOST buffers (H2D of both image batche
          inside the timed region every step).
 roofline: the tcgen05 implicit-GEMM conv kernel on D's 128->256 k4 s2 layer (the FLOP-dominant launch), timed in
          situ with CUDA events around its launches inside eager training steps; FLOPs are algorithmic
-         (2 * pixels * Cout * taps * Cin).
-cpu_baseline / --impl reference: the reference path (oracle = the reference's classes restated, pinned against
-         them in tests/golden) on the host cores, batch 1 per step (BASELINE.json configs[0]).
+         (2 * pixels * Cout * taps * Cin); `frac` = against the measured BURST bf16 peak (the conservative denominator),
+         `frac_sustained` against the sustained one; `traffic` is read from the ncu capture named in `traffic_source`.
+cpu_baseline / --impl reference: the reference path on the host cores, batch 1 per step (BASELINE.json configs[0]):
+         the reference's OWN `GAN` class (training_step / losses / configure_optimizers executed verbatim from
+         oracle/_ref, see oracle/build_ref.py) when that copy travelled with the snapshot -- kind "reference" -- else
+         the oracle restatement (kind "port").  The reference's network classes are 3-D only, so on this 2-D config
+         they are its 2-D twins (same layer lists, oracle/nets.py) in both cases.
+extra  : (N = 1) BASELINE.json configs[2] (perceptual / patch-discriminator step, pairs/s) and configs[4]
+         (generator-only inference at 512x512, slices/s), device-timed from CUDA graphs, in the same run.
+ddp_check: (N > 1) the all-reduced gradient bucket equals the mean of the all-gathered per-rank buckets.
 """
 import argparse
 import json
@@ -88,14 +95,40 @@ def synthetic_batch(batch, dims, spatial, seed=1):
     return {"t1w": torch.rand(shape, generator=g) * 2 - 1, "t2w": torch.rand(shape, generator=g) * 2 - 1}
 
 
+def reference_model():
+    """(model, kind): the reference's own LightningModule (GAN_final.py `GAN`, executed verbatim from oracle/_ref
+    through oracle/ref_shim.py) carrying the 2-D twins of its 3-D-only networks -- kind "reference" --, or the oracle
+    restatement when the copy is absent -- kind "port"."""
+    from oracle.gan import GANOracle
+    from oracle.nets import CasNetGenerator, Discriminator
+    torch.manual_seed(0)
+    try:
+        from oracle import ref_shim
+        if ref_shim.available(ref_shim.REF_COPY_ROOT):
+            ref = ref_shim.load_reference_module("code/GAN/GAN_final.py", "ref_gan_final", root=ref_shim.REF_COPY_ROOT)
+            model = ref.GAN.__new__(ref.GAN)            # the reference ctor builds 128^3 3-D nets: skip it, keep its methods
+            ref_shim.LightningModule.__init__(model)
+            model.hparams.update(latent_dim=100, g_lr=5e-4, d_lr=5e-4, b1=0.5, b2=0.999, batch_size=1,
+                                 one_sided_label_value=0.9)
+            model.generator = CasNetGenerator((1, SIZE, SIZE), 6, 2)
+            model.discriminator = Discriminator((1, SIZE, SIZE), dims=2, spatial=SIZE)
+            model.variant = "final"
+            return model, "reference"
+    except Exception as e:  # noqa: BLE001
+        print(f"# oracle/_ref unusable ({e!r}); timing the oracle port", file=sys.stderr)
+    torch.manual_seed(0)
+    return GANOracle("final", dims=2, spatial=SIZE), "port"
+
+
 def cpu_reference_run(steps, warmup):
-    """The reference path on the host cores: oracle two-optimizer step, batch 1, 256x256, fp32."""
-    from oracle.gan import GANOracle, lightning_step
+    """The reference path on the host cores: two-optimizer step, batch 1, 256x256, fp32."""
+    import contextlib
+    from oracle.gan import lightning_step
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    model = GANOracle("final", dims=2, spatial=SIZE)
-    opts, _ = model.configure_optimizers()
+    model, kind = reference_model()
+    with contextlib.redirect_stdout(sys.stderr):          # the reference's configure_optimizers prints its learning rates
+        opts, _ = model.configure_optimizers()
     batch = synthetic_batch(1, 2, SIZE, seed=1)
     for i in range(warmup):
         lightning_step(model, opts, batch, i)
@@ -103,20 +136,22 @@ def cpu_reference_run(steps, warmup):
     for i in range(steps):
         lightning_step(model, opts, batch, warmup + i)
     dt = time.perf_counter() - t0
-    return steps / dt, dt / steps * 1e3, cores
+    return steps / dt, dt / steps * 1e3, cores, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, cores = cpu_reference_run(args.steps, args.warmup)
-    sample = f"{args.steps} two-optimizer steps of batch 1 at {SIZE}x{SIZE} (fp32, torch CPU, {cores} threads)"
+    value, ms, cores, kind = cpu_reference_run(args.steps, args.warmup)
+    sample = (f"{args.steps} two-optimizer steps of batch 1 at {SIZE}x{SIZE} (fp32, torch CPU, {cores} threads; "
+              + ("the reference's own GAN.training_step / configure_optimizers from oracle/_ref, 2-D twin networks)"
+                 if kind == "reference" else "oracle restatement)"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "GAN_final.py train step (G 6xUNet + D, BCE+L1, Adam x2), CPU, batch 1, 256x256"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -158,6 +193,107 @@ def time_dominant_kernel(model, batch, reps=3):
     return flops / (ms * 1e-3) / 1e12, ms, len(events)
 
 
+def roofline_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel, from the committed
+    `ncu --set full` capture of the final build (profiles/roofline_kernel_traffic.json names the report)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "roofline_kernel_traffic.json")))
+        return float(t["dram_bytes_per_launch"]), t.get("source")
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
+def ddp_check(model, batch, dev):
+    """N > 1, once, outside the timed region: every rank computes its generator-pass gradients on its own shard; the
+    bucket averaged by the production all-reduce (mpgan.ddp.GradComm, NCCL) must equal the mean of the all-gathered
+    per-rank buckets."""
+    import torch.distributed as dist
+    grabbed = {}
+    comm, model.comm = model.comm, None
+    snap = model._snapshot()
+    try:
+        model.fused_step(batch, grad_probe=lambda name, net: grabbed.setdefault(name, net.runtime.grad.clone()))
+    finally:
+        model.comm = comm
+        model._restore(snap)
+    out = {}
+    for name, g in grabbed.items():
+        world = dist.get_world_size()
+        parts = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(parts, g)
+        mean = torch.stack(parts).double().mean(0)
+        red = comm.allreduce(g.clone()).double()
+        out[name] = float((red - mean).norm() / mean.norm().clamp_min(1e-30))
+        out[name + "_rank_spread"] = float((parts[0].double() - parts[-1].double()).norm() / mean.norm().clamp_min(1e-30))
+    torch.cuda.synchronize()
+    return {"rel_l2_allreduce_vs_mean_of_gathered": {k: v for k, v in out.items() if not k.endswith("_rank_spread")},
+            "rel_l2_rank0_vs_last_rank_grads": {k[:-12]: v for k, v in out.items() if k.endswith("_rank_spread")},
+            "ranks": dist.get_world_size(), "bucket_bytes": {k: int(g.numel() * 4) for k, g in grabbed.items()}}
+
+
+def _timed_graph(graph, steps, warmup=3):
+    for _ in range(warmup):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def extra_cfg3(dev, steps=5):
+    """BASELINE.json configs[2]: test_runs/GAN.py step (G 4 x UNet(32..256), 128 patches of 16x16 per image, patch
+    discriminator + 16 activations, adversarial + L1(patches) + perceptual), batch 32 of 256x256, bf16, one CUDA graph."""
+    import numpy as np
+    import mpgan
+    torch.manual_seed(0)
+    model = mpgan.GAN(1, SIZE, SIZE, variant="perceptual", precision="bf16")
+    batch = {k: v.to(dev) for k, v in synthetic_batch(BATCH, 2, SIZE, seed=1).items()}
+    origins = np.random.RandomState(2).randint(0, SIZE - 16 + 1, size=(BATCH, 128, 2))      # SURVEY.md section 8d
+    batch["origins"] = torch.as_tensor(origins.reshape(-1, 2), dtype=torch.int32, device=dev)
+    graph, static, logs = model.capture(batch)
+    ms = _timed_graph(graph, steps)
+    lg = logs.tolist()
+    flop = 3.480e11
+    pk, _ = peaks()
+    v = BATCH / (ms * 1e-3)
+    return {"workload": "cfg 3: test_runs/GAN.py step, G 4xUNet(32,64,128,256), 128 patches of 16x16 / image, patch-D + "
+                        "perceptual, batch 32 of 256x256, bf16, CUDA graph", "value": v, "unit": UNIT, "ms_per_step": ms,
+            "steps": steps, "step_tflops": v * flop / 1e12, "frac_of_sustained_compute_roofline": v * flop / 1e12 / float(pk["bf16_tflops_sustained"]),
+            "launches_per_step": model.abi_calls_per_step,
+            "losses": {"g_adv": lg[0], "g_recon": lg[1], "g_perceptual": lg[2], "d_loss": lg[3] + lg[4]}}
+
+
+def extra_cfg5(dev, reps=3):
+    """BASELINE.json configs[4]: generator-only eval forward over a synthetic 256-slice volume at 512x512, batch 64."""
+    import mpgan
+    from mpgan import inference
+    torch.manual_seed(0)
+    model = mpgan.GAN(1, 512, 512, precision="bf16").to(dev)
+    model.freeze()
+    g = torch.Generator().manual_seed(1)
+    vol = (torch.rand((256, 1, 512, 512), generator=g) * 2 - 1).to(dev)
+    gg = inference.GraphedGenerator(model, (64, 1, 512, 512), dev)
+    inference.infer_volume(model, vol, batch=64, graphed=gg)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = inference.infer_volume(model, vol, batch=64, graphed=gg)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    sl = 256 / (ms * 1e-3)
+    pk, _ = peaks()
+    return {"workload": "cfg 5: G 6xUNet(16,32,64,128)+tanh eval forward, 256 slices of 512x512, batch 64, bf16, CUDA graph",
+            "value": sl, "unit": "slices/s", "ms_per_volume": ms, "reps": reps,
+            "algorithmic_gbs": sl * 276.8e6 / 1e9, "frac_of_hbm_roofline": sl * 276.8e6 / 1e9 / float(pk["hbm_gbs"]),
+            "finite": bool(torch.isfinite(out).all())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,6 +303,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg 3 / cfg 5 legs (N = 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -185,7 +322,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank, local = 0, 0
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MPGAN_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout (one JSON line)
+        # INFO (unless the caller chose otherwise): the driver counts the ranks of the communicator from NCCL's own log;
+        # stdout was redirected to stderr above, so the JSON line stays the only thing on the real stdout
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("MPGAN_NCCL_DEBUG", "INFO"))
         rank, world, local = ddp.init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -200,6 +339,7 @@ def main():
         model.generator.runtime.ensure(dev), model.discriminator.runtime.ensure(dev)
         comm.broadcast_parameters(model)
 
+    ddp = ddp_check(model, batch, dev) if world > 1 else None
     calls0 = _lib.ABI_CALLS
     use_graph = not args.no_graph
     if use_graph:
@@ -270,6 +410,8 @@ def main():
         e2e = world * BATCH * args.steps / (ms_e2e * 1e-3)
         tf, kms, nk = time_dominant_kernel(model, static if use_graph else batch)
         peak_tf = float(pk["bf16_tflops"])
+        peak_sus = float(pk.get("bf16_tflops_sustained", peak_tf))
+        traffic, traffic_src = roofline_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -286,16 +428,33 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel<256,64> (D conv 128->256 k4 s2, batch 32)",
                          "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                         "peak_kind": f"{pk_kind} burst bf16", "kernel_ms": kms,
+                         "peak_kind": f"{pk_kind} burst bf16 (cuBLAS 8192^3 best of 10); the kernel is timed in situ, so "
+                                      "frac_sustained is the like-for-like figure and frac the conservative one",
+                         "frac_burst": tf / peak_tf, "frac_sustained": tf / peak_sus, "peak_sustained": peak_sus,
+                         "kernel_ms": kms,
                          "timed": f"median of {nk} in-situ launches (CUDA events around the launch inside eager steps)",
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this
-                         # kernel on this shape (profiles/ncu_r1_s3_tapgemm256.md); algorithmic bytes are 776.2e6
-                         "traffic": 744.0e6, "traffic_unit": "B/launch", "algorithmic_bytes": 776.2e6},
+                         "traffic": traffic, "traffic_unit": "B/launch", "traffic_source": traffic_src,
+                         "algorithmic_bytes": 776.2e6,
+                         "step_frac_of_sustained_compute_roofline": value * FLOP_PER_PAIR / 1e12 / world / peak_sus},
             "losses": {"g_adv": final_logs[0], "g_recon": final_logs[1], "d_loss": final_logs[2] + final_logs[3]},
         }
+        if ddp is not None:
+            line["ddp_check"] = ddp
+        if world == 1 and not args.no_extra:
+            graph = None
+            model._graph = None
+            del model
+            torch.cuda.empty_cache()
+            line["extra"] = {}
+            for name, fn in (("cfg3_perceptual_train", extra_cfg3), ("cfg5_inference", extra_cfg5)):
+                try:
+                    line["extra"][name] = fn(dev)
+                except Exception as e:  # noqa: BLE001
+                    line["extra"][name] = {"error": repr(e)}
+                torch.cuda.empty_cache()
         if world == 1 and not args.no_cpu_baseline:
-            v, ms, cores = cpu_reference_run(5, 1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            v, ms, cores, kind = cpu_reference_run(5, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"5 two-optimizer steps of batch 1 at {SIZE}x{SIZE}, fp32 torch CPU "
                                               f"({ms:.0f} ms/step)"}
         os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -9,6 +9,21 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__
 sys.path.insert(0, os.path.join(_ROOT, "cross-modality-minipig-gan_b200"))
 
 from mpgan import GAN, CasNetGenerator, Discriminator, PatchDiscriminator  # noqa: E402,F401
+from mpgan import transforms  # noqa: E402,F401  (ScaleIntensityRangePercentilesd: the intensity transform either side of the path)
+
+
+class HumanBrainDataModule:
+    """/root/reference/code/GAN/GAN_final.py:321-437.  OUT OF SCOPE: it reads the authors' private
+    PREDICT-HD volumes through ITK / MONAI ``CacheDataset`` and cannot run anywhere else.  Kept under its reference
+    name so that a caller gets an explanation instead of an ImportError; feed ``GAN`` dict batches
+    ``{"t1w": (B,1,...), "t2w": (B,1,...)}`` of fp32 CUDA tensors scaled to [-1, 1] from any loader
+    (``mpgan.transforms.ScaleIntensityRangePercentilesd`` is the on-device 1/99-percentile rescale of :386-394)."""
+
+    def __init__(self, spatial_size=(128, 128, 128)):
+        raise NotImplementedError(
+            "HumanBrainDataModule is the reference's ITK/MONAI loader for a private dataset and is outside the B200 hot "
+            "path; build batches {'t1w','t2w'} with your own DataLoader (see INTEGRATION.md) -- the GAN / "
+            "CasNetGenerator / Discriminator classes exported here are the drop-in part")
 
 if __name__ == "__main__":
     import argparse

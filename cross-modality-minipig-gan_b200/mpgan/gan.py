@@ -15,13 +15,23 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .nets import CasNetGenerator, Discriminator, PatchDiscriminator, DEFAULT_PRECISION
+from .nets import CasNetGenerator, Discriminator, PatchDiscriminator, DEFAULT_PRECISION, remap_monai_keys
 from .runtime import FlatAdam
 
 
 class _Hparams(dict):
     __getattr__ = dict.__getitem__
     __setattr__ = dict.__setitem__
+
+
+try:   # the reference's base class (GAN_final.py:212) when pytorch-lightning is installed; a plain nn.Module otherwise
+    import pytorch_lightning as _pl
+    _Base = _pl.LightningModule
+    HAVE_LIGHTNING = True
+except Exception:  # noqa: BLE001  (absent in this image: SURVEY.md section 7)
+    _pl = None
+    _Base = nn.Module
+    HAVE_LIGHTNING = False
 
 
 class _BCE(torch.autograd.Function):
@@ -63,7 +73,12 @@ class _L1(torch.autograd.Function):
         return da, db
 
 
-class GAN(nn.Module):
+class GAN(_Base):
+    """``pl.LightningModule`` when pytorch-lightning is importable (so ``pl.Trainer.fit`` drives it as it drives the
+    reference's class: ``training_step(batch, batch_idx, optimizer_idx)``, ``configure_optimizers`` returning two real
+    ``torch.optim.Optimizer``s, ``on_epoch_end``), ``nn.Module`` with the same surface otherwise (``fit_batch`` is the
+    Lightning 1.2.1 two-optimizer loop)."""
+
     def __init__(self, channels, width, height, depth=None, latent_dim: int = 100, d_lr: float = 0.0005,
                  g_lr: float = 0.0005, b1: float = 0.5, b2: float = 0.999, batch_size: int = 64,
                  example_data=None, one_sided_label_value=0.9, variant="final", lr=None, precision=None,
@@ -75,8 +90,11 @@ class GAN(nn.Module):
             g_lr = d_lr = 0.0002 if lr is None else lr
         self._ctor_args = dict(channels=channels, width=width, height=height, depth=depth, variant=variant, lr=lr,
                                precision=precision, n_unet_blocks=n_unet_blocks, num_samples=num_samples, roi=roi)
-        self.hparams = _Hparams(latent_dim=latent_dim, g_lr=g_lr, d_lr=d_lr, b1=b1, b2=b2, batch_size=batch_size,
-                                one_sided_label_value=one_sided_label_value)
+        if HAVE_LIGHTNING:   # GAN_final.py:231 (names are looked up in this frame's locals)
+            self.save_hyperparameters("latent_dim", "g_lr", "d_lr", "b1", "b2", "batch_size", "one_sided_label_value")
+        else:
+            self.hparams = _Hparams(latent_dim=latent_dim, g_lr=g_lr, d_lr=d_lr, b1=b1, b2=b2, batch_size=batch_size,
+                                    one_sided_label_value=one_sided_label_value)
         data_shape = (channels, width, height) if depth is None else (channels, width, height, depth)
         self.dims = len(data_shape) - 1
         self.precision = precision or DEFAULT_PRECISION
@@ -99,24 +117,51 @@ class GAN(nn.Module):
         self._rng = np.random.RandomState()  # RandSpatialCropSamplesd's unseeded RandomState
         self._opt = None
         self._graph = None
+        self._const_cache = {}
         self.comm = None  # set by mpgan.ddp.attach()
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts both MONAI namings of the generator's BatchNorm / PReLU keys (``remap_monai_keys``)."""
+        return super().load_state_dict(remap_monai_keys(state_dict, "legacy"), strict=strict, **kw)
+
+    def reference_state_dict(self, key_style="adn"):
+        """State dict under the reference's parameter names.  ``key_style``: "adn" (``unitN.adn.N.* / adn.A.*``, MONAI
+        with the acti-norm-dropout block -- the 0.4.0 changelog lists it, and the reference pins monai==0.4.0) or
+        "legacy" (``unitN.norm.* / act.*``)."""
+        sd = {k: v.detach().cpu().clone() for k, v in self.state_dict().items()}
+        return remap_monai_keys(sd, key_style) if key_style == "adn" else sd
 
     # ---------------------------------------------------------------- Lightning checkpoint wire format (8f, N3)
     _CTOR_KEYS = ("channels", "width", "height", "depth", "latent_dim", "d_lr", "g_lr", "b1", "b2", "batch_size",
                   "one_sided_label_value", "variant", "lr", "precision", "n_unet_blocks", "num_samples", "roi")
 
-    def save_checkpoint(self, path, epoch=0, global_step=0):
+    def save_checkpoint(self, path, epoch=0, global_step=0, key_style="adn", optimizers=None):
         """Write a pytorch-lightning 1.2.1 style ``.ckpt`` (a ``torch.save``d dict with ``state_dict`` under the
-        reference's parameter names -- the module tree is the reference's -- and ``hyper_parameters``), the file
-        ``ModelCheckpoint`` produces at GAN_final.py:448-472 and ``load_from_checkpoint`` reads at
-        inferrence.py:97-106.  Logical (NC[D]HW / OI[D]HW) tensors, so the reference can load it back."""
+        reference's parameter names, ``hyper_parameters``, ``optimizer_states`` in ``torch.optim.Adam``'s layout and an
+        empty ``lr_schedulers`` list), the file ``ModelCheckpoint`` produces at GAN_final.py:448-472 and
+        ``load_from_checkpoint`` reads at inferrence.py:97-106.  Logical (NC[D]HW / OI[D]HW) tensors, so the reference
+        can load it back.  ``key_style``: see ``reference_state_dict``."""
         hp = dict(self.hparams)
         hp.update(self._ctor_args)
+        opts = optimizers if optimizers is not None else self._opt
         ckpt = {"epoch": int(epoch), "global_step": int(global_step), "pytorch-lightning_version": "1.2.1",
-                "state_dict": {k: v.detach().cpu().clone() for k, v in self.state_dict().items()},
-                "hyper_parameters": hp}
+                "state_dict": self.reference_state_dict(key_style),
+                "hyper_parameters": hp,
+                "optimizer_states": [o.state_dict() for o in opts] if opts else [],
+                "lr_schedulers": []}
         torch.save(ckpt, path)
         return path
+
+    def load_optimizer_states(self, states, device=None):
+        """Resume: restore Adam's moments / step counters (``ckpt["optimizer_states"]``) into the flat buffers."""
+        if self._opt is None:
+            self._opt = self.configure_optimizers()[0]
+        dev = device or next(self.discriminator.parameters()).device
+        for net in (self.generator, self.discriminator):
+            net.runtime.ensure(dev)
+        for opt, st in zip(self._opt, states):
+            opt.load_state_dict(st)
+        return self._opt
 
     @classmethod
     def load_from_checkpoint(cls, checkpoint_path, map_location=None, hparams_file=None, strict=True, **kwargs):
@@ -141,6 +186,7 @@ class GAN(nn.Module):
             if net._runtime is not None:
                 net._runtime.mark_dirty()
         model.load_result = result
+        model.optimizer_states = ckpt.get("optimizer_states", [])   # restored by load_optimizer_states() on the device
         return model
 
     def freeze(self):
@@ -168,6 +214,8 @@ class GAN(nn.Module):
 
     def log(self, name, value, **kw):
         self.logged[name] = value.detach()
+        if HAVE_LIGHTNING and getattr(self, "trainer", None) is not None:
+            super().log(name, value, **kw)
 
     def sample_patch_origins(self, batch, spatial):
         o = np.empty((batch, self.num_samples, len(spatial)), dtype=np.int64)
@@ -238,6 +286,7 @@ class GAN(nn.Module):
         hp = self.hparams
         opt_g = FlatAdam(self.generator, lr=hp.g_lr, betas=(hp.b1, hp.b2))
         opt_d = FlatAdam(self.discriminator, lr=hp.d_lr, betas=(hp.b1, hp.b2))
+        self._opt = [opt_g, opt_d]
         return [opt_g, opt_d], []
 
     def on_epoch_end(self):
@@ -278,13 +327,15 @@ class GAN(nn.Module):
 
     # ---------------------------------------------------------------- fused static step
     def _consts(self, n, dev):
-        key = (n, str(dev))
-        c = getattr(self, "_const_cache", None)
-        if c is None or c[0] != key:
+        """Label tensors (ones / one-sided 0.9 / zeros) per (batch, device).  Never evicted: a captured CUDA graph holds
+        raw pointers to the entry it was recorded with, and an eager step with another batch size must not free it."""
+        key = (n, str(dev), float(self.hparams.one_sided_label_value))
+        c = self._const_cache.get(key)
+        if c is None:
             ones = torch.ones(n, 1, device=dev)
-            c = (key, ones, ones * self.hparams.one_sided_label_value, torch.zeros(n, 1, device=dev))
-            self._const_cache = c
-        return c[1], c[2], c[3]
+            c = (ones, ones * self.hparams.one_sided_label_value, torch.zeros(n, 1, device=dev))
+            self._const_cache[key] = c
+        return c
 
     def fused_step(self, batch, logs=None, grad_probe=None):
         """One full two-optimizer training step (variant "final").  Returns ``logs`` (device fp32):

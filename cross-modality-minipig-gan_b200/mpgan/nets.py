@@ -26,6 +26,20 @@ _BN = {2: nn.BatchNorm2d, 3: nn.BatchNorm3d}
 DEFAULT_PRECISION = "bf16"
 
 
+def remap_monai_keys(state_dict, to="legacy"):
+    """MONAI changed ``Convolution``'s sub-module names when it introduced the ADN block: ``...unitN.norm.* / .act.*``
+    (pre-ADN, the names this module tree uses) vs ``...unitN.adn.N.* / .adn.A.*`` (ADN).  The arithmetic is the same
+    (conv -> norm -> act).  ``to="legacy"`` accepts either naming; ``to="adn"`` emits the ADN naming."""
+    out = type(state_dict)() if isinstance(state_dict, dict) else {}
+    for k, v in state_dict.items():
+        if to == "legacy":
+            k = k.replace(".adn.N.", ".norm.").replace(".adn.A.", ".act.")
+        elif "generator." in k or k.startswith("model."):
+            k = k.replace(".norm.", ".adn.N.").replace(".act.", ".adn.A.")
+        out[k] = v
+    return out
+
+
 def _no_direct_forward(self, *a, **k):
     raise RuntimeError(f"{type(self).__name__} is executed by its owning network's kernel plan; call the "
                        "CasNetGenerator / Discriminator instead")
@@ -145,6 +159,7 @@ def bn_act_forward(c, bn, act, alpha, leaky, res, out, plan, stats, fused_stats)
         out = _new(c, c.shape)
     if plan.training:
         ops.bn_train_apply(c, stats, bn, buf, act, alpha, leaky, res, out)
+        plan.rt.bn_version += 1      # running statistics moved (raw-pointer write): folded inference weights are stale
     else:
         ops.bn_finalize(None, ops.pixels(c), bn, False, mean, invstd, scale, shift)
         ops.bn_act_apply(c, scale, shift, act, alpha, leaky, res, out)
@@ -404,6 +419,7 @@ class UNet(nn.Module):
             ops.bn_stats(c, stats)
         saved = torch.empty((4, 1), dtype=torch.float32, device=c.device)
         h, y = ops.c1_tail_fwd(c, stats, conv0.norm, saved, conv0.act.weight, rec1.w, rec1.bias, plan.save)
+        plan.rt.bn_version += 1
         if plan.save:
             plan.tape.append((cat, c, (saved[0], saved[1], saved[2], saved[3]), plan.training))   # Convolution (ConvT)
             plan.tape.append((h,))                                                              # conv-only Convolution
@@ -507,6 +523,10 @@ class _PlanNet(nn.Module):
         assert precision in ("bf16", "fp32")
         self.precision = precision
         return self
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts both MONAI namings of the BatchNorm / PReLU keys (``remap_monai_keys``)."""
+        return super().load_state_dict(remap_monai_keys(state_dict, "legacy"), strict=strict, **kw)
 
     def _call(self, x, want_acts=False):
         """Route a user-level call through the autograd bridge (tape recorded only when a backward can follow)."""

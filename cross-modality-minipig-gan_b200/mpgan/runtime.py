@@ -30,8 +30,13 @@ class Runtime:
         self.adam_state = None
         self.rec = {}
         self._shadow_version = None
-        self.manual_version = 0
+        self.manual_version = 0      # bumped by every write this runtime knows about (Adam, load_state_dict, broadcast)
+        self.bn_version = 0          # bumped by every training-mode BatchNorm launch (running statistics move)
         self._folded = {}
+        self._folded_bn = {}
+        self._plist = None
+        # load_state_dict copies into the flat views without touching any counter this runtime could see
+        net.register_load_state_dict_post_hook(lambda module, incompatible: self.mark_dirty())
 
     # ------------------------------------------------------------------------------------------------
     def _params(self):
@@ -86,10 +91,22 @@ class Runtime:
         self.shadow = torch.zeros(total, dtype=torch.bfloat16, device=device) if self.dtype == torch.bfloat16 else None
         self._build_records()
         self._shadow_version = None
+        self._plist = None
+        self._folded, self._folded_bn = {}, {}
 
     def _native(self, buf, p):
         off, n = self.offsets[id(p)], p.numel()
         return buf[off:off + n]
+
+    def logical_view(self, buf, p):
+        """View of a flat buffer (moments, gradients) with parameter ``p``'s logical shape (conv weights: the permuted
+        view of the native [d0][taps][d1] block, like ``p`` itself)."""
+        flat = self._native(buf, p)
+        if p.dim() >= 3:
+            perm = (0,) + tuple(range(2, p.dim())) + (1,)
+            inv = (0, p.dim() - 1) + tuple(range(1, p.dim() - 1))
+            return flat.view(tuple(p.shape[i] for i in perm)).permute(inv)
+        return flat.view(p.shape)
 
     def _build_records(self):
         self.rec = {}
@@ -123,13 +140,24 @@ class Runtime:
         self.refresh_shadows()
 
     def mark_dirty(self):
+        """Call after writing parameters or BatchNorm buffers behind the runtime's back (``p.data`` edits)."""
         self.manual_version += 1
+        self.bn_version += 1
+
+    def _weights_version(self):
+        """Everything that can tell that the master weights changed since the shadows were cast.  The flat buffer's
+        own ``_version`` is useless here: the parameters are views re-pointed with ``p.data = ...``, so in-place
+        parameter writes (``p.copy_``, ``nn.init.*``, ``p.mul_``) bump the PARAMETER's counter, not the buffer's.
+        ``p.data.<op>_()`` edits bump nothing -- those need ``mark_dirty()``."""
+        if self._plist is None:
+            self._plist = self._params()
+        return (self.manual_version, sum(p._version for p in self._plist))
 
     def refresh_shadows(self, force=False):
         """bf16 copies of the master weights (whole buffer in one launch) + transposed conv copies."""
         if self.shadow is None:
             return
-        ver = (self.flat._version, self.manual_version)
+        ver = self._weights_version()
         if not force and ver == self._shadow_version:
             return
         ops.cast(self.flat, self.shadow)
@@ -142,8 +170,9 @@ class Runtime:
         fp32 bias.  Recomputed only when the weights or the running statistics change (host-side glue, a handful
         of tiny torch kernels per layer per weight version)."""
         r = self.rec[conv]
-        ver = (self.flat._version, self.manual_version, bn.running_mean._version, bn.running_var._version,
-               bn.weight._version, bn.bias._version)
+        self._folded_bn[conv] = bn
+        # bn_version: the BatchNorm kernels update the running statistics through raw pointers (no tensor counter moves)
+        ver = (self._weights_version(), self.bn_version, bn.running_mean._version, bn.running_var._version)
         hit = self._folded.get(conv)
         if hit is not None and hit[0] == ver:
             return hit[1], hit[2]
@@ -157,8 +186,19 @@ class Runtime:
             else:
                 wf = (w3 * scale.view(-1, 1, 1)).contiguous().to(torch.bfloat16)
             bf = ((b0 - bn.running_mean.float()) * scale + bn.bias.detach().float()).contiguous()
+        if hit is not None and hit[1].shape == wf.shape:
+            # refresh IN PLACE: a captured CUDA graph (inference.GraphedGenerator) holds these pointers
+            hit[1].copy_(wf), hit[2].copy_(bf)
+            wf, bf = hit[1], hit[2]
         self._folded[conv] = (ver, wf, bf)
         return wf, bf
+
+    def refold_all(self):
+        """Recompute every cached folded (weights, bias) pair in place (same device pointers)."""
+        for conv in list(self._folded.keys()):
+            bn = self._folded_bn.get(conv)
+            if bn is not None:
+                self.folded(conv, bn)
 
     def _refresh_transposes(self):
         if self._wt_table is not None:
@@ -170,30 +210,93 @@ class Runtime:
 
     def adam_step(self, lr, b1, b2, eps=1e-8):
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, b1, b2, eps, self.adam_state, self.shadow)
-        self.mark_dirty()
+        self.manual_version += 1
         if self.shadow is not None:  # shadow was written by the Adam kernel; only the transposes remain
             self._refresh_transposes()
-            self._shadow_version = (self.flat._version, self.manual_version)
+            self._shadow_version = self._weights_version()
 
     def requires_grad(self):
         return any(p.requires_grad for p in self.net.parameters())
 
 
-class FlatAdam:
-    """Drop-in for torch.optim.Adam over one network: ``step`` / ``zero_grad`` run one fused launch each."""
+class FlatAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam`` over one network (GAN_final.py:298-308) as ONE fused launch on the flat buffers.
+
+    A real ``torch.optim.Optimizer``: ``param_groups`` hold the network's own ``nn.Parameter``s (pytorch-lightning's
+    ``toggle_optimizer`` flips ``requires_grad`` through them), ``state_dict()`` / ``load_state_dict()`` speak
+    ``torch.optim.Adam``'s per-parameter layout (``step``, ``exp_avg``, ``exp_avg_sq`` in the logical NC[D]HW weight
+    shapes), so optimizer states round-trip with the reference's checkpoints.  Hyper-parameters are read from
+    ``param_groups[0]`` at every step (lr schedulers work); per-group differences are not supported."""
 
     def __init__(self, net, lr, betas=(0.9, 0.999), eps=1e-8):
-        self.net, self.lr, self.betas, self.eps = net, lr, betas, eps
-        self.param_groups = [{"params": list(net.parameters()), "lr": lr, "betas": betas, "eps": eps}]
+        self.net = net
+        super().__init__(list(net.parameters()), dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=0, amsgrad=False))
+        self.lr, self.betas, self.eps = lr, betas, eps
 
+    @torch.no_grad()
     def step(self, closure=None):
-        loss = closure() if closure is not None else None
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
         rt = self.net.runtime
         if rt.flat is None:
             raise RuntimeError("optimizer.step() before the network ran on a CUDA device")
         g = self.param_groups[0]
+        if g.get("weight_decay", 0) or g.get("amsgrad", False):
+            raise RuntimeError("FlatAdam implements the reference's plain Adam (no weight decay / amsgrad)")
         rt.adam_step(g["lr"], g["betas"][0], g["betas"][1], g["eps"])
         return loss
 
     def zero_grad(self, set_to_none=False):
-        self.net.runtime.zero_grad()
+        rt = self.net.runtime
+        if rt.grad is not None:
+            rt.zero_grad()
+
+    # ---- torch.optim.Adam wire format -------------------------------------------------------------------------
+    def state_dict(self):
+        rt = self.net.runtime
+        params = self.param_groups[0]["params"]
+        state = {}
+        if rt.flat is not None:
+            step = int(rt.adam_state[0:1].view(torch.int32).item())
+            if step > 0:
+                for i, p in enumerate(params):
+                    state[i] = {"step": torch.tensor(float(step)),
+                                "exp_avg": rt.logical_view(rt.exp_avg, p).detach().clone(),
+                                "exp_avg_sq": rt.logical_view(rt.exp_avg_sq, p).detach().clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(params)))
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, state_dict):
+        rt = self.net.runtime
+        params = self.param_groups[0]["params"]
+        groups = state_dict.get("param_groups", [])
+        if groups:
+            if len(groups[0]["params"]) != len(params):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
+            for k, v in groups[0].items():
+                if k != "params":
+                    self.param_groups[0][k] = v
+        st = state_dict.get("state", {})
+        if not st:   # a fresh optimizer: zero moments, step 0
+            if rt.flat is not None:
+                rt.exp_avg.zero_(), rt.exp_avg_sq.zero_(), rt.adam_state.zero_()
+            return
+        if rt.flat is None:
+            raise RuntimeError("load the optimizer state after the network has been moved to its CUDA device "
+                               "(net.runtime.ensure(device))")
+        steps = set()
+        with torch.no_grad():
+            for i, p in enumerate(params):
+                e = st.get(i, st.get(str(i)))
+                if e is None:
+                    continue
+                rt.logical_view(rt.exp_avg, p).copy_(e["exp_avg"].to(rt.device))
+                rt.logical_view(rt.exp_avg_sq, p).copy_(e["exp_avg_sq"].to(rt.device))
+                steps.add(int(float(e["step"])))
+            if len(steps) > 1:
+                raise ValueError(f"FlatAdam keeps one step counter per network; the loaded state has {sorted(steps)}")
+            if steps:
+                rt.adam_state[0:1].view(torch.int32).fill_(steps.pop())

@@ -21,6 +21,9 @@ import torch.nn as nn
 from . import monai_unet
 
 REFERENCE_ROOT = "/root/reference"
+# oracle/build_ref.py copies the two reference files of the path here (git-ignored; travels to the GPU box with the
+# snapshot) so that `bench.py --impl reference` can time the reference's OWN classes there
+REF_COPY_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 class _Anything:
@@ -127,9 +130,12 @@ def _restore(saved):
             sys.modules[n] = m
 
 
-def load_reference_module(relpath, name):
-    """Execute a reference file verbatim (e.g. 'code/GAN/GAN_final.py') and return it as a module."""
-    path = os.path.join(REFERENCE_ROOT, relpath)
+def load_reference_module(relpath, name, root=None):
+    """Execute a reference file verbatim (e.g. 'code/GAN/GAN_final.py') and return it as a module.  ``root``: the
+    reference tree (default /root/reference, else the oracle/_ref copy)."""
+    if root is None:
+        root = REFERENCE_ROOT if os.path.exists(os.path.join(REFERENCE_ROOT, relpath)) else REF_COPY_ROOT
+    path = os.path.join(root, relpath)
     if not os.path.exists(path):
         raise FileNotFoundError(path)
     saved = _install_stubs()
@@ -142,5 +148,6 @@ def load_reference_module(relpath, name):
     return mod
 
 
-def available():
-    return os.path.exists(os.path.join(REFERENCE_ROOT, "code/GAN/GAN_final.py"))
+def available(root=None):
+    roots = (root,) if root else (REFERENCE_ROOT, REF_COPY_ROOT)
+    return any(os.path.exists(os.path.join(r, "code/GAN/GAN_final.py")) for r in roots)

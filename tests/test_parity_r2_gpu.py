@@ -1,0 +1,457 @@
+"""Round-2 parity gates (GPU): the configurations and regimes the round-1 suite did not reach.
+
+* network-level bf16 FORWARD parity at north_star's 1e-2 against the rounding-matched oracle (oracle/rounding.py) --
+  the whole 6-UNet cascade on the tcgen05 path, at the smoke size and at BASELINE configs[1]'s full size;
+* BASELINE configs[1] at full size (batch 32 of 256x256): parameter gradients of both optimizer passes (the 2.0 M-pixel
+  split-K weight gradients with fp32 atomics, ragged 125^2 / 61^2 tiles), full-tensor compare of D layers 2-4
+  fprop / dgrad / wgrad against torch on the same GPU;
+* BASELINE configs[2] at batch 32 x 128 patches (test_runs/GAN.py:300-438);
+* the saturated regime over three teacher-forced steps (inferrence.py:102: g_loss = 100.03, d_loss = 45.00);
+* on_epoch_end's BatchNorm side effect (GAN_final.py:310-317), stale-weight detection, optimizer-state round trip and a
+  Lightning-style trainer loop that toggles requires_grad through optimizer.param_groups.
+Measured values of every gate: profiles/parity_r2.md (tools/parity_report.py).
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+from mpgan import GAN, CasNetGenerator, Discriminator, PatchDiscriminator, ops  # noqa: E402
+from oracle.gan import GANOracle, lightning_step, sample_patch_origins, synthetic_batch  # noqa: E402
+from oracle.nets import CasNetGenerator as OGen, Discriminator as ODis, PatchDiscriminator as OPatch  # noqa: E402
+from oracle.rounding import bf16_matched  # noqa: E402
+
+DEV = "cuda"
+
+
+def to_dev(batch):
+    return {k: v.to(DEV) for k, v in batch.items()}
+
+
+def flat_grads(net_or_dict, names):
+    if isinstance(net_or_dict, dict):
+        return torch.cat([net_or_dict[n].detach().double().cpu().flatten() for n in names])
+    d = dict(net_or_dict.named_parameters())
+    return torch.cat([d[n].grad.detach().double().cpu().flatten() for n in names])
+
+
+def oracle_pass(ora, batch, opt_idx, **kw):
+    """One optimizer pass of the oracle from its current state on a deep copy: (loss, {name: grad}, copy)."""
+    ora = copy.deepcopy(ora)
+    nets = (ora.generator, ora.discriminator)
+    for i, net in enumerate(nets):
+        for p in net.parameters():
+            p.requires_grad_(i == opt_idx)
+            p.grad = None
+    loss = ora.training_step(batch, 0, opt_idx, **kw)
+    loss.backward()
+    return float(loss), {n: p.grad.detach().clone() for n, p in nets[opt_idx].named_parameters()}, ora
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bf16 forward at network level: north_star's 1e-2 against the rounding-matched oracle
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nblocks,size,batch", [(1, 64, 2), (6, 64, 3), (6, 96, 2)])
+def test_bf16_generator_cascade_vs_rounding_matched_oracle(nblocks, size, batch):
+    torch.manual_seed(0)
+    ref = OGen((1, size, size), nblocks, 2)
+    mine = CasNetGenerator((1, size, size), n_unet_blocks=nblocks, precision="bf16")
+    mine.load_state_dict(ref.state_dict())
+    x = synthetic_batch(batch, 2, size, seed=1)["t1w"]
+    m = bf16_matched(ref)
+    with torch.no_grad():
+        y_m = m(x)
+        y = mine(x.to(DEV))
+    assert rel_l2(y, y_m) <= 1e-2, rel_l2(y, y_m)
+    for (n1, b1), (n2, b2) in zip(mine.named_buffers(), m.named_buffers()):
+        if b2.dtype.is_floating_point:
+            assert rel_l2(b1, b2) <= 1e-2, n1
+
+
+def test_bf16_discriminators_vs_rounding_matched_oracle():
+    torch.manual_seed(0)
+    ref = ODis((1, 71, 71), dims=2, spatial=71)
+    mine = Discriminator((1, 71, 71), spatial=71, precision="bf16")
+    mine.load_state_dict(ref.state_dict())
+    x = synthetic_batch(3, 2, 71, seed=1)["t1w"]
+    with torch.no_grad():
+        assert rel_l2(mine(x.to(DEV)), bf16_matched(ref)(x)) <= 1e-2
+        assert rel_l2(mine(x.to(DEV)), ref(x)) <= 1e-2            # and the plain fp32 oracle: D is well conditioned
+    refp = OPatch((1, 16, 16), dims=2, spatial=16)
+    minep = PatchDiscriminator((1, 16, 16), precision="bf16")
+    minep.load_state_dict(refp.state_dict())
+    xp = synthetic_batch(6, 2, 16, seed=1)["t1w"]
+    with torch.no_grad():
+        v_m, a_m = bf16_matched(refp)(xp)
+        v, a = minep(xp.to(DEV))
+    assert rel_l2(v, v_m) <= 1e-2
+    for k in range(16):
+        assert rel_l2(a[k], a_m[k]) <= 1e-2, k
+
+
+def test_bf16_single_unet_vs_fp32_oracle():
+    """One UNet in train mode against the PLAIN fp32 oracle: the rounding floor of any bf16 implementation is 1.2e-2
+    here (profiles/precision_floor_r2.md), so the bound is 2e-2; eval mode (no batch statistics) meets 1e-2."""
+    torch.manual_seed(0)
+    ref = OGen((1, 64, 64), 1, 2)
+    mine = CasNetGenerator((1, 64, 64), n_unet_blocks=1, precision="bf16")
+    mine.load_state_dict(ref.state_dict())
+    x = synthetic_batch(4, 2, 64, seed=1)["t1w"]
+    with torch.no_grad():
+        assert rel_l2(mine(x.to(DEV)), copy.deepcopy(ref)(x)) <= 2e-2
+        ref.eval(), mine.eval()
+        assert rel_l2(mine(x.to(DEV)), ref(x)) <= 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[1] at full size
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_cfg2():
+    """Oracle side of configs[1] at batch 32 x 256^2, computed once: forward quantities, both optimizer passes."""
+    B, S = 32, 256
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    ora = GANOracle("final", dims=2, spatial=S)
+    batch = synthetic_batch(B, 2, S, seed=1)
+    out = {"B": B, "S": S, "state": copy.deepcopy(ora.state_dict()), "batch": batch}
+    m = bf16_matched(ora)
+    with torch.no_grad():
+        gen_m = m.generator(batch["t1w"])
+        p_m = m.discriminator(gen_m)
+        out["gen_m"], out["p_m"] = gen_m, p_m
+        out["adv_m"] = float(m.adversarial_loss(p_m, torch.ones(B, 1)))
+        out["rec_m"] = float(m.reconstruction_loss(gen_m, batch["t2w"]))
+    for idx in (0, 1):
+        out[f"loss{idx}"], out[f"grads{idx}"], _ = oracle_pass(ora, batch, idx)
+    return out
+
+
+def _my_pass(mine, dbatch, opt_idx, **kw):
+    nets = (mine.generator, mine.discriminator)
+    for i, net in enumerate(nets):
+        net.runtime.zero_grad()
+        for p in net.parameters():
+            p.requires_grad_(i == opt_idx)
+    loss = mine.training_step(dbatch, 0, opt_idx, **kw)
+    loss.backward()
+    names = [n for n, _ in nets[opt_idx].named_parameters()]
+    g = {n: p.grad.detach().clone() for n, p in nets[opt_idx].named_parameters()}
+    for p in mine.parameters():
+        p.requires_grad_(True)
+    return float(loss), g, names
+
+
+def test_full_size_bf16_forward_vs_rounding_matched_oracle(full_cfg2):
+    f = full_cfg2
+    mine = GAN(1, f["S"], f["S"], precision="bf16")
+    mine.load_state_dict(f["state"])
+    d = to_dev(f["batch"])
+    with torch.no_grad():
+        gen = mine.generator(d["t1w"])
+        p = mine.discriminator(gen)
+    assert rel_l2(gen, f["gen_m"]) <= 1e-2, rel_l2(gen, f["gen_m"])
+    assert rel_l2(p, f["p_m"]) <= 1e-2, rel_l2(p, f["p_m"])
+    mine.load_state_dict(f["state"])
+    logs = mine.fused_step(d).tolist()
+    assert abs(logs[0] - f["adv_m"]) <= 1e-2 * abs(f["adv_m"])
+    assert abs(logs[1] - f["rec_m"]) <= 1e-2 * abs(f["rec_m"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_gradients_both_passes(full_cfg2, precision):
+    """Global parameter-gradient rel-L2 of the generator pass and of the discriminator pass at batch 32 x 256^2.
+    fp32 mode: activation-kink flips bound the generator pass (tests/test_nets_gpu.py docstring), the discriminator pass
+    is tight.  bf16 mode: the discriminator pass (D's own gradients on oracle-identical weights, 90 % of the step's
+    FLOPs: split-K weight gradients over 2.0 M pixels) holds a few 1e-2; the generator cascade's gradient is
+    rounding-noise dominated for any bf16 implementation (profiles/precision_floor_r2.md: floor 8.7e-1) and is bounded
+    by that floor."""
+    f = full_cfg2
+    mine = GAN(1, f["S"], f["S"], precision=precision)
+    d = to_dev(f["batch"])
+    errs = {}
+    for idx in (0, 1):
+        mine.load_state_dict(f["state"])
+        loss, g, names = _my_pass(mine, d, idx)
+        ref = f[f"grads{idx}"]
+        errs[idx] = float((flat_grads(g, names) - flat_grads(ref, names)).norm() / flat_grads(ref, names).norm())
+        ltol = 1e-4 if precision == "fp32" else (1e-1 if idx == 0 else 2e-2)
+        assert abs(loss - f[f"loss{idx}"]) <= ltol * abs(f[f"loss{idx}"]), (idx, loss, f[f"loss{idx}"])
+    if precision == "fp32":
+        assert errs[0] <= 5e-3 and errs[1] <= 2e-3, errs
+    else:
+        assert errs[0] <= 1.2 and errs[1] <= 6e-2, errs
+
+
+D_LAYERS_FULL = [
+    # name, n, cin, cout, size, k, s  (valid padding) -- D layers 2-4 at BASELINE size, batch 32
+    ("D2", 32, 64, 128, 254, 3, 1),
+    ("D3", 32, 128, 256, 252, 4, 2),
+    ("D4", 32, 256, 256, 125, 4, 2),
+]
+
+
+@pytest.mark.parametrize("layer", D_LAYERS_FULL, ids=[c[0] for c in D_LAYERS_FULL])
+def test_full_size_discriminator_convs_full_tensor(layer):
+    """The three FLOP-dominant layers at their full BASELINE shapes (odd 252 / 125 / 61 extents: ragged right / bottom
+    tiles, 2.0 M-pixel split-K reductions), whole tensors against torch fp32 convolutions of the same bf16-rounded
+    operands on the same GPU: fprop (+ fused BatchNorm statistics), data gradient, weight gradient."""
+    _, n, cin, cout, size, k, s = layer
+    g = torch.Generator(device=DEV).manual_seed(31)
+    x = (torch.rand((n, size, size, cin), generator=g, device=DEV) * 2 - 1).bfloat16()
+    w = ((torch.rand((cout, k * k, cin), generator=g, device=DEV) * 2 - 1) * 0.05).bfloat16()
+    bias = torch.rand(cout, generator=g, device=DEV)
+    spec = ops.ConvSpec(2, cin, cout, k, s, 0)
+    osz = (size - k) // s + 1
+    w_oihw = w.view(cout, k, k, cin).permute(0, 3, 1, 2).float().contiguous()
+    x_nchw = x.permute(0, 3, 1, 2).float()
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    y, fused = ops.conv_fprop(spec, x, w, bias, stats=stats)
+    assert fused and y.shape == (n, osz, osz, cout)
+    ref = F.conv2d(x_nchw, w_oihw, bias, stride=s).permute(0, 2, 3, 1)
+    assert rel_l2(y, ref) <= 3e-3                                   # bf16 output rounding: 2^-9 / sqrt(3) = 1.1e-3
+    edge = rel_l2(y[:, -3:, -3:, :], ref[:, -3:, -3:, :])           # the ragged bottom-right tiles on their own
+    assert edge <= 3e-3, edge
+    yd = y.double().reshape(-1, cout)
+    assert rel_l2(stats[:cout], yd.sum(0)) <= 1e-6 and rel_l2(stats[cout:], (yd * yd).sum(0)) <= 1e-6
+    del ref, yd
+    dy = (torch.rand((n, osz, osz, cout), generator=g, device=DEV) * 2 - 1).bfloat16()
+    wt = torch.empty(w.numel(), dtype=torch.bfloat16, device=DEV)
+    ops.weight_transpose(w, wt, cout, k * k, cin)
+    dx, _ = ops.conv_bprop(spec, dy, w, wt, None, xs=(size, size))
+    dy_nchw = dy.permute(0, 3, 1, 2).float()
+    ref_dx = torch.nn.grad.conv2d_input((n, cin, size, size), w_oihw, dy_nchw, stride=s).permute(0, 2, 3, 1)
+    assert rel_l2(dx, ref_dx) <= 3e-3
+    assert rel_l2(dx[:, -4:, -4:, :], ref_dx[:, -4:, -4:, :]) <= 3e-3
+    del ref_dx, dx
+    dw = torch.zeros(cout, k * k, cin, device=DEV)
+    ops.conv_wgrad(spec, x, dy, dw)
+    ref_dw = torch.nn.grad.conv2d_weight(x_nchw, (cout, cin, k, k), dy_nchw, stride=s)
+    ref_dw = ref_dw.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+    assert rel_l2(dw, ref_dw) <= 1e-3, rel_l2(dw, ref_dw)           # fp32 accumulation in a different order over 2 M pixels
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2] at batch 32 x 128 patches
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_perceptual_step_batch32_128_patches(precision):
+    """test_runs/GAN.py:300-438 at BASELINE configs[2]'s size: 32 images of 256x256, 128 patches of 16x16 each (4 096
+    patches per discriminator call), fused static step with learning rate 0 so that both passes start from the
+    oracle's state.  Losses of both passes and the gradients handed to Adam."""
+    B, S, NS = 32, 256, 128
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    ora = GANOracle("perceptual", dims=2, spatial=S, num_samples=NS)
+    mine = GAN(1, S, S, variant="perceptual", num_samples=NS, precision=precision, lr=0.0)
+    mine.load_state_dict(ora.state_dict())
+    batch = synthetic_batch(B, 2, S, seed=1)
+    origins = sample_patch_origins(np.random.RandomState(2), B, NS, (S, S), 16)
+    ref = {}
+    for idx in (0, 1):
+        ref[idx] = oracle_pass(ora, batch, idx, patch_origins=origins)
+    logged = ref[0][2].logged
+    probe = {}
+    d = to_dev(batch)
+    d["origins"] = torch.as_tensor(np.asarray(origins).reshape(-1, 2), dtype=torch.int32, device=DEV)
+    logs = mine.fused_step(d, grad_probe=lambda name, net: probe.__setitem__(
+        name, {n: p.grad.detach().clone() for n, p in net.named_parameters()})).tolist()
+    tol = 1e-4 if precision == "fp32" else 5e-2
+    for got, key in ((logs[0], "g_adv_loss"), (logs[1], "g_recon_loss"), (logs[2], "g_perceptual_loss")):
+        want = float(logged[key])
+        assert abs(got - want) <= tol * max(abs(want), 1e-6), (key, got, want)
+    assert abs(logs[3] + logs[4] - ref[1][0]) <= (1e-4 if precision == "fp32" else 2e-2) * abs(ref[1][0])
+    errs = {}
+    for idx, name in ((0, "generator"), (1, "discriminator")):
+        names = list(ref[idx][1].keys())
+        a, b = flat_grads(probe[name], names), flat_grads(ref[idx][1], names)
+        errs[name] = float((a - b).norm() / b.norm())
+    if precision == "fp32":
+        assert errs["generator"] <= 8e-3 and errs["discriminator"] <= 2e-3, errs
+    else:
+        assert errs["discriminator"] <= 6e-2 and errs["generator"] <= 1.2, errs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# saturated regime, three teacher-forced steps
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_teacher_forced_steps_reach_the_saturated_regime(precision):
+    """SURVEY.md section 0 / inferrence.py:102: after ONE optimizer step at 256^2 the discriminator's Linear (fan-in
+    952 576) drives sigmoid to exactly 0, BCE hits torch's -100 log clamp: g_adv = 100.0, d_loss = (0.9*100 + 0)/2 = 45.0,
+    and D's gradients vanish identically.  Each step starts from the ORACLE's state (weights, BatchNorm buffers, Adam
+    moments and step counters loaded into the device model), so Adam's sign-like first updates cannot compound."""
+    B, S = 2, 256
+    torch.manual_seed(0)
+    ora = GANOracle("final", dims=2, spatial=S)
+    opts, _ = ora.configure_optimizers()
+    mine = GAN(1, S, S, precision=precision)
+    batch = synthetic_batch(B, 2, S, seed=1)
+    d = to_dev(batch)
+    for net in (mine.generator, mine.discriminator):
+        net.runtime.ensure(torch.device(DEV, 0))
+    saturated_seen = False
+    for step in range(3):
+        mine.load_state_dict(ora.state_dict())
+        mine.load_optimizer_states([o.state_dict() for o in opts])
+        keep = {}
+        ref = lightning_step(ora, opts, batch, step, keep_grads=keep)
+        probe = {}
+        logs = mine.fused_step(d, grad_probe=lambda name, net: probe.__setitem__(
+            name, {f"{name}.{n}": p.grad.detach().clone() for n, p in net.named_parameters()})).tolist()
+        g_adv_ref, g_rec_ref = float(ora.logged["g_adv_loss"]), float(ora.logged["g_recon_loss"])
+        d_ref = float(ref[1])
+        ftol = 1e-4 if precision == "fp32" else 5e-2
+        assert abs(logs[1] - g_rec_ref) <= ftol * abs(g_rec_ref), (step, logs[1], g_rec_ref)
+        if g_adv_ref == 100.0:      # saturated: exact values, identically-zero discriminator gradients
+            saturated_seen = True
+            assert logs[0] == 100.0, (step, logs[0])
+            assert logs[2] + logs[3] == d_ref == 45.0, (step, logs, d_ref)
+            dn = [k for k in keep if k.startswith("discriminator.")]
+            assert all(float(keep[k].abs().max()) == 0.0 for k in dn)
+            assert all(float(probe["discriminator"][k].abs().max()) == 0.0 for k in dn), step
+        else:
+            assert abs(logs[0] - g_adv_ref) <= ftol * abs(g_adv_ref), (step, logs[0], g_adv_ref)
+            if precision == "fp32":
+                gn = [k for k in keep if k.startswith("generator.")]
+                a, b = flat_grads(probe["generator"], gn), flat_grads(keep, gn)
+                assert float((a - b).norm() / b.norm()) <= 5e-3, step
+    assert saturated_seen, "the reference's saturated regime was never reached"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# on_epoch_end, stale weights, optimizer states, Lightning-style loop
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_on_epoch_end_moves_batchnorm_statistics(precision):
+    """GAN_final.py:310-317: two extra TRAIN-mode generator forwards on the example arrays per epoch -- their only
+    lasting effect is on the BatchNorm running statistics (and num_batches_tracked)."""
+    S = 64
+    torch.manual_seed(0)
+    ora = GANOracle("final", dims=2, spatial=S)
+    ex = (synthetic_batch(1, 2, S, seed=11), synthetic_batch(2, 2, S, seed=12))
+    mine = GAN(1, S, S, precision=precision, example_data=ex)
+    mine.load_state_dict(ora.state_dict())
+    mine.to(DEV)
+    x_eval = synthetic_batch(2, 2, S, seed=3)["t1w"]
+    mine.eval()
+    with torch.no_grad():
+        y_before = mine(x_eval.to(DEV)).clone()          # (bf16: primes the folded-BatchNorm inference cache)
+    mine.train()
+    outs = mine.on_epoch_end()
+    assert len(outs) == 2 and outs[0].shape == ex[0]["t1w"].shape
+    ref = bf16_matched(ora.generator) if precision == "bf16" else ora.generator
+    with torch.no_grad():
+        ref(ex[0]["t1w"]), ref(ex[1]["t1w"])
+    tol = 1e-4 if precision == "fp32" else 1e-2
+    for (n1, b1), (n2, b2) in zip(mine.generator.named_buffers(), ref.named_buffers()):
+        if b2.dtype.is_floating_point:
+            assert rel_l2(b1, b2) <= tol, n1
+        else:
+            assert int(b1) == int(b2) == 2, n1
+    # the eval-mode forward after it must see the NEW running statistics (folded weights are re-derived)
+    mine.eval(), ref.eval()
+    with torch.no_grad():
+        y_after = mine(x_eval.to(DEV))
+        assert rel_l2(y_after, ref(x_eval)) <= tol
+    assert rel_l2(y_after, y_before) > 10 * tol
+
+
+def test_in_place_weight_edits_reach_the_bf16_shadows():
+    """parameter writes after the network has been materialised (in-place ops on the Parameter,
+    load_state_dict) must invalidate the bf16 shadow / transposed copies / folded inference weights."""
+    torch.manual_seed(0)
+    ref = OGen((1, 64, 64), 1, 2)
+    mine = CasNetGenerator((1, 64, 64), n_unet_blocks=1, precision="bf16")
+    mine.load_state_dict(ref.state_dict())
+    x = synthetic_batch(2, 2, 64, seed=1)["t1w"]
+    for mode in ("train", "eval"):
+        getattr(ref, mode)(), getattr(mine, mode)()
+        with torch.no_grad():
+            y0 = mine(x.to(DEV)).clone()
+            name, p = next((n, p) for n, p in mine.named_parameters() if p.dim() == 4 and p.shape[0] == 64)
+            p.mul_(1.5)
+            dict(ref.named_parameters())[name].mul_(1.5)
+            y1 = mine(x.to(DEV)).clone()
+            assert rel_l2(y1, bf16_matched(ref)(x)) <= 1e-2
+            assert rel_l2(y1, y0) > 1e-2
+            sd = {k: v * 0.5 if k.endswith("conv.weight") else v for k, v in ref.state_dict().items()}
+            ref.load_state_dict(sd), mine.load_state_dict(sd)
+            y2 = mine(x.to(DEV))
+            assert rel_l2(y2, bf16_matched(ref)(x)) <= 1e-2
+            assert rel_l2(y2, y1) > 1e-2
+
+
+def test_checkpoint_round_trip_with_optimizer_states(tmp_path):
+    """save_checkpoint -> load_from_checkpoint -> load_optimizer_states resumes bit-identically (weights, BatchNorm
+    buffers, Adam moments and step counters); the optimizer state has torch.optim.Adam's layout and the generator keys
+    the ADN naming."""
+    S = 32
+    torch.manual_seed(0)
+    a = GAN(1, S, S, precision="fp32")
+    batch = to_dev(synthetic_batch(2, 2, S, seed=1))
+    a.fit_batch(batch), a.fit_batch(batch)
+    path = a.save_checkpoint(str(tmp_path / "m.ckpt"), epoch=3)
+    ck = torch.load(path, weights_only=False)
+    assert any(".adn.N.running_mean" in k for k in ck["state_dict"]) and len(ck["optimizer_states"]) == 2
+    st0 = ck["optimizer_states"][0]["state"][0]
+    assert float(st0["step"]) == 2.0 and st0["exp_avg"].shape == a.generator.model[0].model[0].conv.unit0.conv.weight.shape
+    tadam = torch.optim.Adam([torch.nn.Parameter(p.detach().clone().cpu()) for p in a.generator.parameters()], lr=5e-4)
+    tadam.load_state_dict(ck["optimizer_states"][0])     # torch's own Adam accepts the state
+    b = GAN.load_from_checkpoint(path)
+    b.to(DEV)
+    b.load_optimizer_states(b.optimizer_states)
+    for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(p.detach(), q.detach()), n
+    for rt_a, rt_b in ((a.generator.runtime, b.generator.runtime), (a.discriminator.runtime, b.discriminator.runtime)):
+        assert torch.equal(rt_a.exp_avg, rt_b.exp_avg) and torch.equal(rt_a.exp_avg_sq, rt_b.exp_avg_sq)
+        assert torch.equal(rt_a.adam_state[0:1].view(torch.int32), rt_b.adam_state[0:1].view(torch.int32))
+    la, lb = a.fit_batch(batch), b.fit_batch(batch)     # (atomics order: equal to rounding, not bit for bit)
+    assert abs(float(la[0]) - float(lb[0])) <= 1e-5 * abs(float(la[0])) and abs(float(la[1]) - float(lb[1])) <= 1e-4 * abs(float(la[1]))
+
+
+def test_lightning_style_trainer_loop():
+    """A minimal stand-in for pl.Trainer's 1.2.1 multi-optimizer loop (GAN_final.py:480-492): optimizers come from
+    configure_optimizers(), toggle_optimizer flips requires_grad through optimizer.param_groups, the step closure runs
+    training_step + backward inside optimizer.step(closure).  Same losses and weights as fit_batch."""
+    S = 32
+    torch.manual_seed(0)
+    a = GAN(1, S, S, precision="fp32")
+    b = GAN(1, S, S, precision="fp32")
+    b.load_state_dict(a.state_dict())
+    batch = to_dev(synthetic_batch(2, 2, S, seed=1))
+    optimizers, schedulers = b.configure_optimizers()
+    assert schedulers == [] and all(isinstance(o, torch.optim.Optimizer) for o in optimizers)
+    all_params = [p for o in optimizers for g in o.param_groups for p in g["params"]]
+    losses_b = []
+    for step in range(2):
+        for opt_idx, opt in enumerate(optimizers):
+            for p in all_params:                                   # toggle_optimizer
+                p.requires_grad = False
+            for g in opt.param_groups:
+                for p in g["params"]:
+                    p.requires_grad = True
+
+            def closure():
+                loss = b.training_step(batch, step, opt_idx)
+                loss.backward()
+                losses_b.append(float(loss))
+                return loss
+
+            opt.step(closure=closure)
+            opt.zero_grad()
+            for p in all_params:                                   # untoggle
+                p.requires_grad = True
+    losses_a = [float(v) for step in range(2) for v in a.fit_batch(batch, step)]
+    # step 0 is compared tightly; step 1 follows Adam's sign-like first update (atomics order can flip near-zero gradients)
+    assert all(abs(x - y) <= 1e-5 * abs(x) for x, y in zip(losses_a[:2], losses_b[:2])), (losses_a, losses_b)
+    assert all(abs(x - y) <= 2e-2 * abs(x) for x, y in zip(losses_a[2:], losses_b[2:])), (losses_a, losses_b)
+    for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert rel_l2(q, p) <= 1e-2, n

@@ -53,9 +53,22 @@ def test_checkpoint_round_trip_and_reference_key_names(tmp_path):
     from oracle.gan import GANOracle
     torch.manual_seed(0)
     model = mpgan.GAN(1, 64, 64)
-    path = model.save_checkpoint(str(tmp_path / "gen_epoch=3-g_loss=1.00-d_loss=0.50.ckpt"), epoch=3, global_step=12)
+    # default key style "adn": MONAI's acti-norm-dropout naming (unitN.adn.N.* / unitN.adn.A.*); both namings load back
+    adn = model.save_checkpoint(str(tmp_path / "adn.ckpt"), epoch=3, global_step=12)
+    adn_keys = list(torch.load(adn, weights_only=False)["state_dict"].keys())
+    assert "generator.model.0.model.0.conv.unit0.adn.N.running_mean" in adn_keys
+    assert "generator.model.0.model.0.conv.unit0.adn.A.weight" in adn_keys
+    assert "generator.model.0.model.2.0.adn.N.weight" in adn_keys and not any(".norm." in k or ".act." in k for k in adn_keys)
+    assert [k for k in adn_keys if k.startswith("discriminator.")] == [k for k in model.state_dict() if k.startswith("discriminator.")]
+    back_adn = mpgan.GAN.load_from_checkpoint(adn)
+    assert len(back_adn.load_result.missing_keys) == 0 and len(back_adn.load_result.unexpected_keys) == 0
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, back_adn.state_dict()[k]), k
+    path = model.save_checkpoint(str(tmp_path / "gen_epoch=3-g_loss=1.00-d_loss=0.50.ckpt"), epoch=3, global_step=12,
+                                 key_style="legacy")
     ckpt = torch.load(path, weights_only=False)
     assert ckpt["pytorch-lightning_version"] == "1.2.1" and ckpt["epoch"] == 3 and ckpt["global_step"] == 12
+    assert ckpt["optimizer_states"] == [] and ckpt["lr_schedulers"] == []     # no optimizer was ever configured
     # the reference's (oracle = reference classes restated, pinned in tests/golden) module tree loads it strictly
     ora = GANOracle("final", dims=2, spatial=64)
     assert list(ora.state_dict().keys()) == list(ckpt["state_dict"].keys())
