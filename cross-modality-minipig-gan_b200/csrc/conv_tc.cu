@@ -1,4 +1,4 @@
-// tcgen05 implicit-GEMM convolution for sm_100a (rank-2, NHWC, bf16 operands, fp32 TMEM accumulators).
+// tcgen05 implicit-GEMM convolution for sm_100a (rank 2 NHWC and rank 3 NDHWC, bf16 operands, fp32 TMEM accumulators).
 //
 // Replaces cuDNN's convolution forward / backward-data / backward-filter behind nn.Conv2d / nn.ConvTranspose2d for
 // the discriminator (/root/reference/code/GAN/GAN_final.py:167-189 -- 90 % of the step FLOPs) and the >=16-channel
@@ -31,31 +31,35 @@
 namespace mpgan {
 namespace tc {
 
-constexpr int MAXT = 16;
-constexpr int MAXCLS = 4;
+constexpr int MAXT = 64;     // 4 x 4 x 4 taps (rank 3, D layers 3 / 4)
+constexpr int MAXCLS = 8;    // output parity classes of a stride-2 rank-3 data gradient
 constexpr int kSmemLimit = 227 * 1024;
+
+// Activation tensor maps of one launch: one for stride 1; for stride-2 gathers one per input parity class
+// (4 in rank 2, 8 in rank 3).  Passed as ONE __grid_constant__ kernel parameter and indexed by the tap's class.
+struct ActMaps { CUtensorMap m[8]; };
 
 struct TapGemmParams {
   int ncls;
   int cls_tap_begin[MAXCLS + 1];
-  int cls_oh[MAXCLS], cls_ow[MAXCLS];
+  int cls_od[MAXCLS], cls_oh[MAXCLS], cls_ow[MAXCLS];
   long long cls_out_off[MAXCLS];
   signed char tap_map[MAXT];
-  short tap_dh[MAXT], tap_dw[MAXT], tap_slab[MAXT];
+  short tap_dd[MAXT], tap_dh[MAXT], tap_dw[MAXT], tap_slab[MAXT];
   int nkc;
-  int tiles_w, tiles_h, tiles_n;
-  int tw_log2, th_log2;
+  int tiles_w, tiles_h, tiles_d, tiles_n;      // tiles_d / td_log2: rank 3 only (1 / 0 otherwise)
+  int tw_log2, th_log2, td_log2;
   int nimg;
   int n_total, n_tiles;
   int cls_minor;       // tile order: the parity classes of one spatial tile are consecutive (equal tap counts only)
   int mt;              // 128-pixel tiles per weight stage (1, or 2 for large BN = 128 layers)
   int lane_parallel;   // taps of a tile are loaded by different lanes (needs max taps per class * nkc <= STAGES)
-  long long out_sn, out_sh, out_sw;
+  long long out_sn, out_sd, out_sh, out_sw;
   bf16* out;
   const float* bias;
   double* stats;
   const bf16* res;     // optional tensor added to the result before rounding (same grid / classes as out)
-  long long res_sn, res_sh, res_sw;
+  long long res_sn, res_sd, res_sh, res_sw;
   long long cls_res_off[MAXCLS];
   int wide;            // output rows are 32-byte aligned: 256-bit stores
   const float* slope;  // optional device scalar: PReLU applied to (acc + bias) before the residual (inference fusion)
@@ -64,9 +68,9 @@ struct TapGemmParams {
 struct WgradParams {
   int ntaps;
   signed char tap_map[MAXT];
-  short tap_dh[MAXT], tap_dw[MAXT];
+  short tap_dd[MAXT], tap_dh[MAXT], tap_dw[MAXT];
   int taps_per_group, ngroups, m_blocks, splits;
-  int tiles_w, tiles_h, tiles_n, tw_log2, th_log2;
+  int tiles_w, tiles_h, tiles_d, tiles_n, tw_log2, th_log2, td_log2;
   int cx, cy;
   int nprod;           // TMA producer warps (1..7)
   float* dw;
@@ -135,11 +139,40 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
   return v[0];
 }
 
-template <int BN, int KC, int MT_>
+// Decoded position of one tile of the persistent sequence (R3: rank-3 tensors, one more tile dimension).
+struct TileIdx { int nt, twi, thi, tdi, tni, cls; };
+template <bool R3> struct TapWalk {
+  static constexpr int ND = R3 ? 6 : 5;
+  TileWalk<ND> w;
+  int minor;
+  __device__ __forceinline__ void init(const TapGemmParams& P, int tile0, int step) {
+    minor = P.cls_minor;
+    if constexpr (R3) {
+      const int rmaj[6] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_d, P.tiles_n, 1 << 30};
+      const int rmin[6] = {P.ncls, P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_d, 1 << 30};
+      if (minor) w.init(tile0, step, rmin); else w.init(tile0, step, rmaj);
+    } else {
+      const int rmaj[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30};
+      const int rmin[5] = {P.ncls, P.n_tiles, P.tiles_w, P.tiles_h, 1 << 30};
+      if (minor) w.init(tile0, step, rmin); else w.init(tile0, step, rmaj);
+    }
+  }
+  __device__ __forceinline__ void next() { w.next(); }
+  __device__ __forceinline__ TileIdx get() const {
+    const int o = minor ? 1 : 0;   // class-minor order puts the class digit first
+    TileIdx t;
+    t.nt = w.d[o]; t.twi = w.d[o + 1]; t.thi = w.d[o + 2];
+    t.tdi = R3 ? w.d[o + 3] : 0;
+    t.tni = w.d[o + (R3 ? 4 : 3)];
+    t.cls = minor ? w.d[0] : w.d[ND - 1];
+    return t;
+  }
+};
+
+template <int BN, int KC, int MT_, bool R3>
 __global__ void __launch_bounds__(EpiCfg<BN>::THREADS, 1)
-tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ CUtensorMap tmA0,
-               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB) {
+tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ ActMaps tmA,
+               const __grid_constant__ CUtensorMap tmB) {
   using Cfg = TapCfg<BN, KC, MT_>;
   using Epi = EpiCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -161,7 +194,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && elect_one()) {
-    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA.m[0]);
     prefetch_tmap(&tmB);
   }
   if (warp == 1 && elect_one()) {
@@ -179,8 +212,8 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tn_log2 = 7 - P.tw_log2 - P.th_log2;
-  const int per_cls = P.tiles_n * P.tiles_h * P.tiles_w * P.n_tiles;
+  const int tn_log2 = 7 - P.tw_log2 - P.th_log2 - (R3 ? P.td_log2 : 0);
+  const int per_cls = P.tiles_n * (R3 ? P.tiles_d : 1) * P.tiles_h * P.tiles_w * P.n_tiles;
   const int total_tiles = per_cls * P.ncls;
 
   if (warp == 0) {
@@ -188,29 +221,25 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
     if (elect_one()) {  // ================= TMA producer (one thread) =================
       int stage = 0;
       uint32_t phase = 0;
-      TileWalk<5> tw5;
-      {
-        const int rmaj[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30};
-        const int rmin[5] = {P.ncls, P.n_tiles, P.tiles_w, P.tiles_h, 1 << 30};
-        if (P.cls_minor) tw5.init((int)blockIdx.x, (int)gridDim.x, rmin); else tw5.init((int)blockIdx.x, (int)gridDim.x, rmaj);
-      }
+      TapWalk<R3> tw5;
+      tw5.init(P, (int)blockIdx.x, (int)gridDim.x);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw5.next()) {
-        const int o5 = P.cls_minor ? 1 : 0;   // class-minor order puts the class digit first
-        const int nt = tw5.d[o5], twi = tw5.d[o5 + 1], thi = tw5.d[o5 + 2], tni = tw5.d[o5 + 3], cls = P.cls_minor ? tw5.d[0] : tw5.d[4];
-        const int w0 = (twi * MT) << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
-        for (int tap = P.cls_tap_begin[cls]; tap < P.cls_tap_begin[cls + 1]; ++tap) {
-          const int mi = P.tap_map[tap];
-          const CUtensorMap* mA = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
-          const int cw = w0 + P.tap_dw[tap], chh = h0 + P.tap_dh[tap], slab = P.tap_slab[tap];
+        const TileIdx t = tw5.get();
+        const int w0 = (t.twi * MT) << P.tw_log2, h0 = t.thi << P.th_log2, d0 = t.tdi << P.td_log2, n0 = t.tni << tn_log2;
+        for (int tap = P.cls_tap_begin[t.cls]; tap < P.cls_tap_begin[t.cls + 1]; ++tap) {
+          const CUtensorMap* mA = &tmA.m[P.tap_map[tap]];
+          const int cw = w0 + P.tap_dw[tap], chh = h0 + P.tap_dh[tap], cd = d0 + P.tap_dd[tap], slab = P.tap_slab[tap];
           for (int kc = 0; kc < P.nkc; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sB = sA + Cfg::A_BYTES;
             mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_TX);
 #pragma unroll
-            for (int sub = 0; sub < MT; ++sub)
-              tma_load_4d(sA + sub * Cfg::A_TILE, mA, &full[stage], kc * KC, cw + (sub << P.tw_log2), chh, n0);
-            tma_load_3d(sB, &tmB, &full[stage], kc * KC, slab, nt * BN);
+            for (int sub = 0; sub < MT; ++sub) {
+              if constexpr (R3) tma_load_5d(sA + sub * Cfg::A_TILE, mA, &full[stage], kc * KC, cw + (sub << P.tw_log2), chh, cd, n0);
+              else tma_load_4d(sA + sub * Cfg::A_TILE, mA, &full[stage], kc * KC, cw + (sub << P.tw_log2), chh, n0);
+            }
+            tma_load_3d(sB, &tmB, &full[stage], kc * KC, slab, t.nt * BN);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -221,31 +250,26 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
     // A single issuing thread needs ~40 dependent scalar instructions per (tap, chunk) -- for the generator's layers
     // (9 taps of 128 x 16..64 channels per tile) that, not bandwidth, was the tile rate.  The taps of a tile use
     // consecutive ring stages, so each lane owns one tap, waits for its own stage and issues its own two TMA loads.
-    int cur_cls = -1, ntaps = 0, dh = 0, dw = 0, slab = 0;
-    const CUtensorMap* mA = &tmA0;
+    int cur_cls = -1, ntaps = 0, dd = 0, dh = 0, dw = 0, slab = 0;
+    const CUtensorMap* mA = &tmA.m[0];
     uint32_t cnt = 0;   // ring position of the tile's first stage (identical in all lanes)
-    TileWalk<5> tw5;
-    {
-        const int rmaj[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30};
-        const int rmin[5] = {P.ncls, P.n_tiles, P.tiles_w, P.tiles_h, 1 << 30};
-        if (P.cls_minor) tw5.init((int)blockIdx.x, (int)gridDim.x, rmin); else tw5.init((int)blockIdx.x, (int)gridDim.x, rmaj);
-      }
+    TapWalk<R3> tw5;
+    tw5.init(P, (int)blockIdx.x, (int)gridDim.x);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw5.next()) {
-      const int o5 = P.cls_minor ? 1 : 0;   // class-minor order puts the class digit first
-        const int nt = tw5.d[o5], twi = tw5.d[o5 + 1], thi = tw5.d[o5 + 2], tni = tw5.d[o5 + 3], cls = P.cls_minor ? tw5.d[0] : tw5.d[4];
-      if (cls != cur_cls) {
-        cur_cls = cls;
-        const int tb = P.cls_tap_begin[cls];
-        ntaps = P.cls_tap_begin[cls + 1] - tb;
+      const TileIdx t = tw5.get();
+      if (t.cls != cur_cls) {
+        cur_cls = t.cls;
+        const int tb = P.cls_tap_begin[t.cls];
+        ntaps = P.cls_tap_begin[t.cls + 1] - tb;
         if (lane < ntaps) {
           const int tap = tb + lane;
-          const int mi = P.tap_map[tap];
-          mA = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
-          dh = P.tap_dh[tap]; dw = P.tap_dw[tap]; slab = P.tap_slab[tap];
+          mA = &tmA.m[P.tap_map[tap]];
+          dd = P.tap_dd[tap]; dh = P.tap_dh[tap]; dw = P.tap_dw[tap]; slab = P.tap_slab[tap];
         }
       }
       if (lane < ntaps) {
-        const int cw = ((twi * MT) << P.tw_log2) + dw, chh = (thi << P.th_log2) + dh, n0 = tni << tn_log2;
+        const int cw = ((t.twi * MT) << P.tw_log2) + dw, chh = (t.thi << P.th_log2) + dh, cd = (t.tdi << P.td_log2) + dd,
+                  n0 = t.tni << tn_log2;
         for (int kc = 0; kc < P.nkc; ++kc) {
           const uint32_t a = cnt + (uint32_t)(lane * P.nkc + kc);
           const uint32_t stage = a % (uint32_t)STAGES;
@@ -255,9 +279,11 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
           uint8_t* sB = sA + Cfg::A_BYTES;
           mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_TX);
 #pragma unroll
-          for (int sub = 0; sub < MT; ++sub)
-            tma_load_4d(sA + sub * Cfg::A_TILE, mA, &full[stage], kc * KC, cw + (sub << P.tw_log2), chh, n0);
-          tma_load_3d(sB, &tmB, &full[stage], kc * KC, slab, nt * BN);
+          for (int sub = 0; sub < MT; ++sub) {
+            if constexpr (R3) tma_load_5d(sA + sub * Cfg::A_TILE, mA, &full[stage], kc * KC, cw + (sub << P.tw_log2), chh, cd, n0);
+            else tma_load_4d(sA + sub * Cfg::A_TILE, mA, &full[stage], kc * KC, cw + (sub << P.tw_log2), chh, n0);
+          }
+          tma_load_3d(sB, &tmB, &full[stage], kc * KC, slab, t.nt * BN);
         }
       }
       cnt += (uint32_t)(ntaps * P.nkc);
@@ -306,8 +332,10 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
     const int q = ew & 3;           // TMEM lane quarter (== warp % 4)
     const int half = ew >> 2;       // second warp group (BN <= 64 only)
     const int row = q * 32 + lane;
-    const int tw_mask = (1 << P.tw_log2) - 1, th_mask = (1 << P.th_log2) - 1;
-    const int lw = row & tw_mask, lh = (row >> P.tw_log2) & th_mask, ln = row >> (P.tw_log2 + P.th_log2);
+    const int tw_mask = (1 << P.tw_log2) - 1, th_mask = (1 << P.th_log2) - 1, td_mask = R3 ? (1 << P.td_log2) - 1 : 0;
+    const int lw = row & tw_mask, lh = (row >> P.tw_log2) & th_mask;
+    const int ld = R3 ? (row >> (P.tw_log2 + P.th_log2)) & td_mask : 0;
+    const int ln = row >> (P.tw_log2 + P.th_log2 + (R3 ? P.td_log2 : 0));
     constexpr int CH = Epi::CH;
     float* sl = s_stats + ew * 2 * P.n_total;
     if constexpr (Epi::REG) {
@@ -330,21 +358,18 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         for (int j = 0; j < CH / 2; ++j) { s1[j] = 0ull; s2[j] = 0ull; }
       };
       int it = 0;
-      TileWalk<5> tw5;
-      {
-        const int rmaj[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30};
-        const int rmin[5] = {P.ncls, P.n_tiles, P.tiles_w, P.tiles_h, 1 << 30};
-        if (P.cls_minor) tw5.init((int)blockIdx.x, (int)gridDim.x, rmin); else tw5.init((int)blockIdx.x, (int)gridDim.x, rmaj);
-      }
+      TapWalk<R3> tw5;
+      tw5.init(P, (int)blockIdx.x, (int)gridDim.x);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it, tw5.next()) {
         if (NCH == 1 && (it & 1) != half) continue;
-        const int o5 = P.cls_minor ? 1 : 0;   // class-minor order puts the class digit first
-        const int nt = tw5.d[o5], twi = tw5.d[o5 + 1], thi = tw5.d[o5 + 2], tni = tw5.d[o5 + 3], cls = P.cls_minor ? tw5.d[0] : tw5.d[4];
-        const int ow = (twi << P.tw_log2) + lw, oh = (thi << P.th_log2) + lh, img = (tni << tn_log2) + ln;
-        const bool valid = img < P.nimg && oh < P.cls_oh[cls] && ow < P.cls_ow[cls];
+        const TileIdx t = tw5.get();
+        const int nt = t.nt, cls = t.cls;
+        const int ow = (t.twi << P.tw_log2) + lw, oh = (t.thi << P.th_log2) + lh, od = (t.tdi << P.td_log2) + ld,
+                  img = (t.tni << tn_log2) + ln;
+        const bool valid = img < P.nimg && oh < P.cls_oh[cls] && ow < P.cls_ow[cls] && (!R3 || od < P.cls_od[cls]);
         const int nbase = nt * BN;
         bf16* orow = P.out + P.cls_out_off[cls] + (long long)img * P.out_sn + (long long)oh * P.out_sh +
-                     (long long)ow * P.out_sw + nbase + c0;
+                     (long long)ow * P.out_sw + (R3 ? (long long)od * P.out_sd : 0LL) + nbase + c0;
         if (P.stats && nbase != stat_base) {
           if (stat_base >= 0) flush();
           stat_base = nbase;
@@ -362,22 +387,19 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);   // values are in registers: the accumulator is free again
         const bf16* rrow = P.res ? P.res + P.cls_res_off[cls] + (long long)img * P.res_sn + (long long)oh * P.res_sh +
-                                       (long long)ow * P.res_sw + nbase + c0
+                                       (long long)ow * P.res_sw + (R3 ? (long long)od * P.res_sd : 0LL) + nbase + c0
                                  : nullptr;
         epi_chunk_store<CH>(r, s_bias + nbase + c0, orow, valid, P.stats != nullptr, s1, s2, rrow, P.wide != 0, P.slope);
       }
       if (P.stats && stat_base >= 0) flush();
     } else {
     int it = 0;
-    TileWalk<5> tw5;
-    {
-        const int rmaj[5] = {P.n_tiles, P.tiles_w, P.tiles_h, P.tiles_n, 1 << 30};
-        const int rmin[5] = {P.ncls, P.n_tiles, P.tiles_w, P.tiles_h, 1 << 30};
-        if (P.cls_minor) tw5.init((int)blockIdx.x, (int)gridDim.x, rmin); else tw5.init((int)blockIdx.x, (int)gridDim.x, rmaj);
-      }
+    TapWalk<R3> tw5;
+    tw5.init(P, (int)blockIdx.x, (int)gridDim.x);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it, tw5.next()) {
-      const int o5 = P.cls_minor ? 1 : 0;   // class-minor order puts the class digit first
-        const int nt = tw5.d[o5], twi = tw5.d[o5 + 1], thi = tw5.d[o5 + 2], tni = tw5.d[o5 + 3], cls = P.cls_minor ? tw5.d[0] : tw5.d[4];
+      const TileIdx t = tw5.get();
+      const int nt = t.nt, twi = t.twi, thi = t.thi, tni = t.tni, cls = t.cls;
+      const int od = (t.tdi << P.td_log2) + ld;
       const int nbase = nt * BN;
       const int buf = it % NACC;
       const uint32_t par = (uint32_t)(it / NACC) & 1u;
@@ -386,9 +408,9 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub) {
       const int ow = ((twi * MT + sub) << P.tw_log2) + lw, oh = (thi << P.th_log2) + lh, img = (tni << tn_log2) + ln;
-      const bool valid = img < P.nimg && oh < P.cls_oh[cls] && ow < P.cls_ow[cls];
+      const bool valid = img < P.nimg && oh < P.cls_oh[cls] && ow < P.cls_ow[cls] && (!R3 || od < P.cls_od[cls]);
       bf16* orow = P.out + P.cls_out_off[cls] + (long long)img * P.out_sn + (long long)oh * P.out_sh +
-                   (long long)ow * P.out_sw + nbase;
+                   (long long)ow * P.out_sw + (R3 ? (long long)od * P.out_sd : 0LL) + nbase;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * MT + sub) * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
@@ -406,7 +428,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         }
         if (P.res && valid) {
           const bf16* rrow = P.res + P.cls_res_off[cls] + (long long)img * P.res_sn + (long long)oh * P.res_sh +
-                             (long long)ow * P.res_sw + nbase + c0;
+                             (long long)ow * P.res_sw + (R3 ? (long long)od * P.res_sd : 0LL) + nbase + c0;
 #pragma unroll
           for (int j = 0; j < CH / 8; ++j) {
             const uint4 q = *reinterpret_cast<const uint4*>(rrow + j * 8);

@@ -55,8 +55,11 @@ def worst(a, b):
     return w
 
 
-def oracle_pass(ora, batch, opt_idx, autocast=False):
+def oracle_pass(ora, batch, opt_idx, autocast=False, fp64=False):
     ora = copy.deepcopy(ora)
+    if fp64:
+        ora = ora.double()
+        batch = {k: v.double() for k, v in batch.items()}
     nets = (ora.generator, ora.discriminator)
     for i, net in enumerate(nets):
         for p in net.parameters():
@@ -95,6 +98,7 @@ def buffers_rel(mine, ora):
 
 
 def row(name, *vals):
+    vals = list(vals) + [None] * (6 - len(vals))
     print("| " + name + " | " + " | ".join("-" if v is None else (v if isinstance(v, str) else f"{v:.2e}") for v in vals) + " |",
           flush=True)
 
@@ -143,6 +147,17 @@ def report(S, B, with_autocast):
     rl, rg, ora_g = {}, {}, {}
     for idx in (0, 1):
         rl[idx], rg[idx], ora_g[idx] = oracle_pass(ora, batch, idx)
+    # the fp32 oracle against its own fp64 evaluation: how well conditioned each quantity is in fp32 at all
+    g64 = {}
+    for idx in (0, 1):
+        _, g64[idx], _ = oracle_pass(ora, batch, idx, fp64=True)
+    # discriminator pass with both images teacher-forced (t2 and the oracle's generator output)
+    dtf = copy.deepcopy(ora.discriminator)
+    for p in dtf.parameters():
+        p.grad = None
+    ltf = (ora.adversarial_loss(dtf(batch["t2w"]), torch.ones(B, 1) * 0.9) + ora.adversarial_loss(dtf(gen_ref), torch.zeros(B, 1))) / 2
+    ltf.backward()
+    gtf, ltf = grads_of(dtf), float(ltf)
     al, ag = {}, {}
     if with_autocast:
         with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
@@ -152,8 +167,9 @@ def report(S, B, with_autocast):
             al[idx], ag[idx], _ = oracle_pass(ora, batch, idx, autocast=True)
     print(f"\n### {S}x{S}, batch {B}  (oracle side: {time.time() - t0:.0f} s CPU)\n")
     print("| quantity | fp32 mode vs fp32 oracle | bf16 mode vs fp32 oracle | bf16 mode vs rounding-matched oracle | "
-          "rounding-matched oracle vs fp32 oracle (the floor of this rounding scheme) | torch CPU autocast(bf16) vs fp32 oracle |")
-    print("|---|---:|---:|---:|---:|---:|")
+          "rounding-matched oracle vs fp32 oracle (the floor of this rounding scheme) | torch CPU autocast(bf16) vs fp32 oracle | "
+          "fp32 oracle vs its own fp64 evaluation |")
+    print("|---|---:|---:|---:|---:|---:|---:|")
     res = {}
     for prec in ("fp32", "bf16"):
         r = {}
@@ -192,6 +208,14 @@ def report(S, B, with_autocast):
             r[f"w{idx}"] = worst(mg, rg[idx])
             nets_o = (ora_g[idx].generator, ora_g[idx].discriminator)
             r[f"buf{idx}"] = max(buffers_rel(mine.generator, nets_o[0]), buffers_rel(mine.discriminator, nets_o[1]))
+        mine.load_state_dict(state)
+        D = mine.discriminator
+        D.runtime.zero_grad()
+        loss = (mine.adversarial_loss(D(dbatch["t2w"]), torch.ones(B, 1, device=DEV) * 0.9)
+                + mine.adversarial_loss(D(gen_ref.to(DEV)), torch.zeros(B, 1, device=DEV))) / 2
+        loss.backward()
+        r["ltf"] = abs(float(loss) - ltf) / abs(ltf)
+        r["gtf"] = grel(grads_of(D), gtf)
         res[prec] = r
         del mine
         torch.cuda.empty_cache()
@@ -208,10 +232,13 @@ def report(S, B, with_autocast):
     for idx, name in ((0, "generator pass"), (1, "discriminator pass")):
         row(f"{name}: loss (relative)", f[f"loss{idx}"], b[f"loss{idx}"], None, None,
             abs(al[idx] - rl[idx]) / abs(rl[idx]) if A else None)
-        row(f"{name}: global parameter-gradient rel-L2", f[f"g{idx}"], b[f"g{idx}"], None, None, grel(ag[idx], rg[idx]) if A else None)
+        row(f"{name}: global parameter-gradient rel-L2", f[f"g{idx}"], b[f"g{idx}"], None, None, grel(ag[idx], rg[idx]) if A else None,
+            grel(rg[idx], g64[idx]))
         row(f"{name}: worst tensor (err / max(|g|, 10 % of largest))", f"{f[f'w{idx}'][0]:.2e} ({f[f'w{idx}'][1]})",
             f"{b[f'w{idx}'][0]:.2e} ({b[f'w{idx}'][1]})", None, None, None)
         row(f"{name}: BN running buffers (worst)", f[f"buf{idx}"], b[f"buf{idx}"], None, None, None)
+    row("discriminator pass, both images teacher-forced: loss (relative)", f["ltf"], b["ltf"], None, None, None)
+    row("discriminator pass, both images teacher-forced: global parameter-gradient rel-L2", f["gtf"], b["gtf"], None, None, None)
 
 
 def main():
