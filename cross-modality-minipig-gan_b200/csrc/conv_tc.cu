@@ -531,11 +531,10 @@ template <int NX, bool SMALL_> struct WgCfg {
   static constexpr int MAX_TPG = TMEM_COLS / NX;        // taps whose accumulators fit in the TMEM allocation
 };
 
-template <int NX, bool SMALL>
+template <int NX, bool SMALL, bool R3>
 __global__ void __launch_bounds__(256, 1)
 wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUtensorMap tmY,
-             const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
-             const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmX3) {
+             const __grid_constant__ ActMaps tmX) {
   using Cfg = WgCfg<NX, SMALL>;
   using B = WgB<NX>;
   constexpr int STAGES = Cfg::STAGES;
@@ -556,7 +555,7 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
 
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmY);
-    prefetch_tmap(&tmX0);
+    prefetch_tmap(&tmX.m[0]);
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], kWgProducers); mbar_init(&empty[i], 1); }
@@ -577,9 +576,23 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
   const int split = b;
   const int tap0 = grp * P.taps_per_group;
   const int ntap = min(P.taps_per_group, P.ntaps - tap0);
-  const int ptiles = P.tiles_n * P.tiles_h * P.tiles_w;
-  const int tn_log2 = 6 - P.tw_log2 - P.th_log2;
+  const int ptiles = P.tiles_n * (R3 ? P.tiles_d : 1) * P.tiles_h * P.tiles_w;
+  const int tn_log2 = 6 - P.tw_log2 - P.th_log2 - (R3 ? P.td_log2 : 0);
   const int my_tiles = split < ptiles ? (ptiles - split + P.splits - 1) / P.splits : 0;
+  // pixel tile pt -> tile origin (w0, h0, d0, n0)
+  auto tile_origin = [&](int pt, int& w0, int& h0, int& d0, int& n0) {
+    int t = pt;
+    const int twi = t % P.tiles_w; t /= P.tiles_w;
+    const int thi = t % P.tiles_h; t /= P.tiles_h;
+    int tdi = 0;
+    if constexpr (R3) { tdi = t % P.tiles_d; t /= P.tiles_d; }
+    w0 = twi << P.tw_log2; h0 = thi << P.th_log2; d0 = tdi << P.td_log2; n0 = t << tn_log2;
+  };
+  // one box of a 64-pixel tile: channels [c0, c0 + box) of map m at pixel offset (dw, dh, dd) from the tile origin
+  auto load_tile = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int w, int h, int d, int n) {
+    if constexpr (R3) tma_load_5d(dst, m, bar, c0, w, h, d, n);
+    else tma_load_4d(dst, m, bar, c0, w, h, n);
+  };
 
   if (kWgProducers == 1) {
   if (warp == 0) {
@@ -587,27 +600,23 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = split; pt < ptiles; pt += P.splits) {
-        int t = pt;
-        const int twi = t % P.tiles_w; t /= P.tiles_w;
-        const int thi = t % P.tiles_h; t /= P.tiles_h;
-        const int tni = t;
-        const int w0 = twi << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
+        int w0, h0, d0, n0;
+        tile_origin(pt, w0, h0, d0, n0);
         for (int tl0 = 0; tl0 < ntap; tl0 += B::TPS) {
           const int nt = min(B::TPS, ntap - tl0);
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
           mbar_expect_tx(&full[stage], Cfg::A_BYTES + nt * B::BYTES);
-          tma_load_4d(sA, &tmY, &full[stage], mb * 128, w0, h0, n0);
-          tma_load_4d(sA + 8192, &tmY, &full[stage], mb * 128 + 64, w0, h0, n0);
+          load_tile(sA, &tmY, &full[stage], mb * 128, w0, h0, d0, n0);
+          load_tile(sA + 8192, &tmY, &full[stage], mb * 128 + 64, w0, h0, d0, n0);
           for (int q = 0; q < nt; ++q) {
             const int tap = tap0 + tl0 + q;
-            const int mi = P.tap_map[tap];
-            const CUtensorMap* mX = mi == 0 ? &tmX0 : (mi == 1 ? &tmX1 : (mi == 2 ? &tmX2 : &tmX3));
+            const CUtensorMap* mX = &tmX.m[P.tap_map[tap]];
 #pragma unroll
             for (int i = 0; i < B::BOXES; ++i)
-              tma_load_4d(sB + q * B::BYTES + i * 8192, mX, &full[stage], i * 64, w0 + P.tap_dw[tap],
-                          h0 + P.tap_dh[tap], n0);
+              load_tile(sB + q * B::BYTES + i * 8192, mX, &full[stage], i * 64, w0 + P.tap_dw[tap], h0 + P.tap_dh[tap],
+                        d0 + P.tap_dd[tap], n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -625,11 +634,8 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = split; pt < ptiles; pt += P.splits) {
-        int t = pt;
-        const int twi = t % P.tiles_w; t /= P.tiles_w;
-        const int thi = t % P.tiles_h; t /= P.tiles_h;
-        const int tni = t;
-        const int w0 = twi << P.tw_log2, h0 = thi << P.th_log2, n0 = tni << tn_log2;
+        int w0, h0, d0, n0;
+        tile_origin(pt, w0, h0, d0, n0);
         for (int tl0 = 0; tl0 < ntap; tl0 += B::TPS) {
           const int nt = min(B::TPS, ntap - tl0);
           const int items = 2 + nt * B::BOXES;          // item 0,1: dY boxes; 2 + q*BOXES + i: box i of tap q
@@ -642,14 +648,13 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
           else mbar_arrive(&full[stage]);
           for (int it = pw; it < items; it += kWgProducers) {
             if (it < 2) {
-              tma_load_4d(sA + it * 8192, &tmY, &full[stage], mb * 128 + it * 64, w0, h0, n0);
+              load_tile(sA + it * 8192, &tmY, &full[stage], mb * 128 + it * 64, w0, h0, d0, n0);
             } else {
               const int q = (it - 2) / B::BOXES, i = (it - 2) % B::BOXES;
               const int tap = tap0 + tl0 + q;
-              const int mi = P.tap_map[tap];
-              const CUtensorMap* mX = mi == 0 ? &tmX0 : (mi == 1 ? &tmX1 : (mi == 2 ? &tmX2 : &tmX3));
-              tma_load_4d(sB + q * B::BYTES + i * 8192, mX, &full[stage], i * 64, w0 + P.tap_dw[tap],
-                          h0 + P.tap_dh[tap], n0);
+              const CUtensorMap* mX = &tmX.m[P.tap_map[tap]];
+              load_tile(sB + q * B::BYTES + i * 8192, mX, &full[stage], i * 64, w0 + P.tap_dw[tap], h0 + P.tap_dh[tap],
+                        d0 + P.tap_dd[tap], n0);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -765,17 +770,26 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
   return 0;
 }
 
+// Convolution geometry in (depth, height, width); rank 2 = depth extent / kernel 1, depth padding 0.
 struct Geom2 {
-  int n, xh, xw, yh, yw, cx, cy, kh, kw, s, ph, pw;
+  int rank, n, xd, xh, xw, yd, yh, yw, cx, cy, kd, kh, kw, s, pd, ph, pw;
 };
 
 static int to_geom2(const MpganConvGeom* g, Geom2* o) {
-  MPGAN_REQUIRE(g && g->rank == 2, MPGAN_ERR_UNSUPPORTED, "tcgen05 conv path is rank-2 only");
+  MPGAN_REQUIRE(g && (g->rank == 2 || g->rank == 3), MPGAN_ERR_UNSUPPORTED, "tcgen05 conv path is rank 2 or 3");
   MPGAN_REQUIRE(g->stride[1] == g->stride[2] && (g->stride[1] == 1 || g->stride[1] == 2), MPGAN_ERR_UNSUPPORTED,
                 "tcgen05 conv path supports stride 1 or 2");
-  o->n = g->n; o->xh = g->xs[1]; o->xw = g->xs[2]; o->yh = g->ys[1]; o->yw = g->ys[2];
-  o->cx = g->cx; o->cy = g->cy; o->kh = g->k[1]; o->kw = g->k[2]; o->s = g->stride[1]; o->ph = g->pad[1]; o->pw = g->pad[2];
-  MPGAN_REQUIRE(o->kh * o->kw <= MAXT, MPGAN_ERR_UNSUPPORTED, "too many taps");
+  o->rank = g->rank; o->n = g->n;
+  o->xd = g->xs[0]; o->xh = g->xs[1]; o->xw = g->xs[2]; o->yd = g->ys[0]; o->yh = g->ys[1]; o->yw = g->ys[2];
+  o->cx = g->cx; o->cy = g->cy; o->kd = g->k[0]; o->kh = g->k[1]; o->kw = g->k[2]; o->s = g->stride[1];
+  o->pd = g->pad[0]; o->ph = g->pad[1]; o->pw = g->pad[2];
+  if (g->rank == 2) {
+    MPGAN_REQUIRE(o->xd == 1 && o->yd == 1 && o->kd == 1 && o->pd == 0, MPGAN_ERR_SHAPE, "rank-2 geometry with a depth extent");
+  } else {
+    MPGAN_REQUIRE(g->stride[0] == g->stride[1], MPGAN_ERR_UNSUPPORTED, "tcgen05 conv path needs equal strides");
+    MPGAN_REQUIRE(o->yd <= (o->xd + 2 * o->pd - o->kd) / o->s + 1, MPGAN_ERR_SHAPE, "Y extent exceeds conv output size");
+  }
+  MPGAN_REQUIRE(o->kd * o->kh * o->kw <= MAXT, MPGAN_ERR_UNSUPPORTED, "too many taps");
   MPGAN_REQUIRE(o->cx % 16 == 0 && o->cy % 16 == 0, MPGAN_ERR_UNSUPPORTED, "channels must be multiples of 16");
   MPGAN_REQUIRE(o->yh <= (o->xh + 2 * o->ph - o->kh) / o->s + 1 && o->yw <= (o->xw + 2 * o->pw - o->kw) / o->s + 1,
                 MPGAN_ERR_SHAPE, "Y extent exceeds conv output size");
@@ -785,60 +799,71 @@ static int to_geom2(const MpganConvGeom* g, Geom2* o) {
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-// choose a tw x th x tn = npix tile minimising padded work
-static void choose_tile(int ow, int oh, int nimg, int npix, int* tw_log2, int* th_log2) {
+// choose a tw x th x td x tn = npix tile minimising padded work (td > 1 only for rank-3 tensors)
+static void choose_tile(int ow, int oh, int od, int nimg, int npix, bool r3, int* tw_log2, int* th_log2, int* td_log2) {
   double best = 1e300;
-  int bl = 0, bh = 0;
+  int bl = 0, bh = 0, bd = 0;
   for (int lw = 0; lw <= 5; ++lw)
-    for (int lh = 0; lh <= 5; ++lh) {
-      int ln = ilog2(npix) - lw - lh;
-      if (ln < 0 || ln > 4) continue;
-      int tw = 1 << lw, th = 1 << lh, tn = 1 << ln;
-      double work = (double)((ow + tw - 1) / tw * tw) * ((oh + th - 1) / th * th) * ((nimg + tn - 1) / tn * tn);
-      work *= 1.0 + 0.02 * ln + 0.01 * (5 - lw);  // mild preference for wide single-image tiles
-      if (work < best) { best = work; bl = lw; bh = lh; }
-    }
+    for (int lh = 0; lh <= 5; ++lh)
+      for (int ld = 0; ld <= (r3 ? 4 : 0); ++ld) {
+        int ln = ilog2(npix) - lw - lh - ld;
+        if (ln < 0 || ln > 4) continue;
+        int tw = 1 << lw, th = 1 << lh, td = 1 << ld, tn = 1 << ln;
+        double work = (double)((ow + tw - 1) / tw * tw) * ((oh + th - 1) / th * th) * ((od + td - 1) / td * td) *
+                      ((nimg + tn - 1) / tn * tn);
+        work *= 1.0 + 0.02 * ln + 0.01 * (5 - lw) + 0.005 * ld;  // mild preference for wide single-image, single-slice tiles
+        if (work < best) { best = work; bl = lw; bh = lh; bd = ld; }
+      }
   *tw_log2 = bl;
   *th_log2 = bh;
+  *td_log2 = bd;
 }
 
-// tensor maps over the gathered activation tensor (spatial h x w, channels c, pixel stride ld):
-// stride 1 -> one map; stride 2 -> four parity maps
-static int make_act_maps(CUtensorMap* maps, const void* base, int nimg, int h, int w, int c, int64_t ld, int s,
+// tensor maps over the gathered activation tensor (spatial d x h x w, channels c, pixel stride ld):
+// stride 1 -> one map; stride 2 -> one map per parity class, index (pd * 2 + ph) * 2 + pw (pd = 0 for rank 2).
+// box: {channels, tw, th, [td,] tn}
+static int make_act_maps(ActMaps* maps, const void* base, bool r3, int nimg, int d, int h, int w, int c, int64_t ld, int s,
                          const uint32_t* box) {
   const bf16* b = (const bf16*)base;
-  if (s == 1) {
-    uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)nimg};
-    uint64_t str[3] = {(uint64_t)ld, (uint64_t)ld * w, (uint64_t)ld * w * h};
-    int rc = encode_map(&maps[0], b, 4, dims, str, box);
-    if (rc) return rc;
-    for (int i = 1; i < 4; ++i) maps[i] = maps[0];
-    return 0;
-  }
-  for (int ph = 0; ph < 2; ++ph)
-    for (int pw = 0; pw < 2; ++pw) {
-      int hh = (h - ph + 1) / 2, ww = (w - pw + 1) / 2;
-      if (hh < 1) hh = 1;
-      if (ww < 1) ww = 1;
-      uint64_t dims[4] = {(uint64_t)c, (uint64_t)ww, (uint64_t)hh, (uint64_t)nimg};
-      uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)ld * w * 2, (uint64_t)ld * w * h};
-      int rc = encode_map(&maps[ph * 2 + pw], b + ((int64_t)ph * w + pw) * ld, 4, dims, str, box);
-      if (rc) return rc;
-    }
+  const int rank = r3 ? 5 : 4;
+  memset(maps, 0, sizeof(*maps));
+  for (int pd = 0; pd < (r3 && s == 2 ? 2 : 1); ++pd)
+    for (int ph = 0; ph < s; ++ph)
+      for (int pw = 0; pw < s; ++pw) {
+        int dd = (d - pd + s - 1) / s, hh = (h - ph + s - 1) / s, ww = (w - pw + s - 1) / s;
+        if (!r3) dd = 1;
+        if (dd < 1) dd = 1;
+        if (hh < 1) hh = 1;
+        if (ww < 1) ww = 1;
+        const bf16* origin = b + (((int64_t)pd * h + ph) * w + pw) * ld;
+        int rc;
+        if (r3) {
+          uint64_t dims[5] = {(uint64_t)c, (uint64_t)ww, (uint64_t)hh, (uint64_t)dd, (uint64_t)nimg};
+          uint64_t str[4] = {(uint64_t)ld * s, (uint64_t)ld * w * s, (uint64_t)ld * w * h * s, (uint64_t)ld * w * h * d};
+          rc = encode_map(&maps->m[(pd * 2 + ph) * 2 + pw], origin, rank, dims, str, box);
+        } else {
+          uint64_t dims[4] = {(uint64_t)c, (uint64_t)ww, (uint64_t)hh, (uint64_t)nimg};
+          uint64_t str[3] = {(uint64_t)ld * s, (uint64_t)ld * w * s, (uint64_t)ld * w * h};
+          rc = encode_map(&maps->m[ph * 2 + pw], origin, rank, dims, str, box);
+        }
+        if (rc) return rc;
+      }
+  if (s == 1)
+    for (int i = 1; i < 8; ++i) maps->m[i] = maps->m[0];
   return 0;
 }
 
-template <int BN, int KC, int MT>
-static int launch_tapgemm_t(const TapGemmParams& P, const CUtensorMap* mA, const CUtensorMap& mB, cudaStream_t s) {
+template <int BN, int KC, int MT, bool R3>
+static int launch_tapgemm_t(const TapGemmParams& P, const ActMaps& mA, const CUtensorMap& mB, cudaStream_t s) {
   using Cfg = TapCfg<BN, KC, MT>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, KC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, KC, MT, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     MPGAN_REQUIRE(e == cudaSuccess, MPGAN_ERR_CUDA, "cudaFuncSetAttribute(tapgemm): %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  const long long total = (long long)P.ncls * P.tiles_n * P.tiles_h * P.tiles_w * P.n_tiles;
+  const long long total = (long long)P.ncls * P.tiles_n * P.tiles_d * P.tiles_h * P.tiles_w * P.n_tiles;
   int grid = (int)(total < num_sms() ? total : num_sms());
   int max_taps = 0;
   for (int c = 0; c < P.ncls; ++c) max_taps = std::max(max_taps, P.cls_tap_begin[c + 1] - P.cls_tap_begin[c]);
@@ -854,24 +879,23 @@ static int launch_tapgemm_t(const TapGemmParams& P, const CUtensorMap* mA, const
     Q.cls_minor = (equal && !off) ? 1 : 0;
   }
   Q.lane_parallel = (max_taps * P.nkc <= Cfg::STAGES && max_taps <= 32) ? 1 : 0;
-  launch_k(tapgemm_kernel<BN, KC, MT>, grid, EpiCfg<BN>::THREADS, Cfg::SMEM_BYTES, s, Q, mA[0], mA[1], mA[2], mA[3], mB);
+  launch_k(tapgemm_kernel<BN, KC, MT, R3>, grid, EpiCfg<BN>::THREADS, Cfg::SMEM_BYTES, s, Q, mA, mB);
   MPGAN_CHECK_LAUNCH("tapgemm_kernel");
   return 0;
 }
 
-template <int KC>
-static int launch_tapgemm_kc(int bn, const TapGemmParams& P, const CUtensorMap* mA, const CUtensorMap& mB,
-                             cudaStream_t s) {
+template <int KC, bool R3>
+static int launch_tapgemm_kc(int bn, const TapGemmParams& P, const ActMaps& mA, const CUtensorMap& mB, cudaStream_t s) {
   switch (bn) {
-    case 16: return launch_tapgemm_t<16, KC, 1>(P, mA, mB, s);
-    case 32: return launch_tapgemm_t<32, KC, 1>(P, mA, mB, s);
-    case 64: return launch_tapgemm_t<64, KC, 1>(P, mA, mB, s);
+    case 16: return launch_tapgemm_t<16, KC, 1, R3>(P, mA, mB, s);
+    case 32: return launch_tapgemm_t<32, KC, 1, R3>(P, mA, mB, s);
+    case 64: return launch_tapgemm_t<64, KC, 1, R3>(P, mA, mB, s);
     case 128:
       if constexpr (KC == 64) {
-        if (P.mt == 2) return launch_tapgemm_t<128, KC, 2>(P, mA, mB, s);
+        if (P.mt == 2) return launch_tapgemm_t<128, KC, 2, R3>(P, mA, mB, s);
       }
-      return launch_tapgemm_t<128, KC, 1>(P, mA, mB, s);
-    case 256: return launch_tapgemm_t<256, KC, 1>(P, mA, mB, s);
+      return launch_tapgemm_t<128, KC, 1, R3>(P, mA, mB, s);
+    case 256: return launch_tapgemm_t<256, KC, 1, R3>(P, mA, mB, s);
   }
   set_error("bad BN %d", bn);
   return MPGAN_ERR_UNSUPPORTED;
@@ -903,12 +927,12 @@ static bool halo_enabled() {
 static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, const void* w, const float* bias, void* out,
                        int64_t ldo, double* stats, cudaStream_t s, const void* res = nullptr, int64_t ldres = 0,
                        const float* slope = nullptr) {
+  const bool r3 = g.rank == 3;
   const int C = dir == 0 ? g.cx : g.cy;  // reduced channels
   const int N = dir == 0 ? g.cy : g.cx;  // produced channels
-  const int ih = dir == 0 ? g.xh : g.yh, iw = dir == 0 ? g.xw : g.yw;
-  const int oh = dir == 0 ? g.yh : g.xh, ow = dir == 0 ? g.yw : g.xw;
-  const int T = g.kh * g.kw;
-  if (g.s == 1 && g.kh == 3 && g.kw == 3 && g.ph == g.pw && g.ph <= 1 && halo_enabled()) {
+  const int id = dir == 0 ? g.xd : g.yd, ih = dir == 0 ? g.xh : g.yh, iw = dir == 0 ? g.xw : g.yw;
+  const int od = dir == 0 ? g.yd : g.xd, oh = dir == 0 ? g.yh : g.xh, ow = dir == 0 ? g.yw : g.xw;
+  if (!r3 && g.s == 1 && g.kh == 3 && g.kw == 3 && g.ph == g.pw && g.ph <= 1 && halo_enabled()) {
     int rc = halo3x3_run(dir, g.n, ih, iw, oh, ow, C, N, g.ph, in, ldi, w, bias, out, ldo, stats, res, ldres, s, 0, slope);
     if (rc != 1) return rc;
   }
@@ -933,98 +957,132 @@ static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, con
   MPGAN_REQUIRE(!res || (ldres % 8 == 0 && ((uintptr_t)res & 15) == 0), MPGAN_ERR_SHAPE, "residual tensor misaligned");
   MPGAN_REQUIRE(N <= 512, MPGAN_ERR_UNSUPPORTED, "N > 512");
 
+  const int sd = r3 ? g.s : 1;            // stride along depth (rank 2: a single depth slice)
   int ntap = 0;
-  int loh, low;  // logical output grid the tiles cover
+  int lod, loh, low;  // logical output grid the tiles cover
   if (dir == 0) {  // gather X: xpos = ypos*s - pad + r
     P.ncls = 1;
     P.cls_tap_begin[0] = 0;
-    for (int rh = 0; rh < g.kh; ++rh)
-      for (int rw = 0; rw < g.kw; ++rw) {
-        int qh = rh - g.ph, qw = rw - g.pw;
-        int ph = g.s == 2 ? ((qh % 2) + 2) % 2 : 0, pw = g.s == 2 ? ((qw % 2) + 2) % 2 : 0;
-        P.tap_map[ntap] = (signed char)(ph * 2 + pw);
-        P.tap_dh[ntap] = (short)(g.s == 2 ? floordiv(qh - ph, 2) : qh);
-        P.tap_dw[ntap] = (short)(g.s == 2 ? floordiv(qw - pw, 2) : qw);
-        P.tap_slab[ntap] = (short)(rh * g.kw + rw);
-        ++ntap;
-      }
+    for (int rd = 0; rd < g.kd; ++rd)
+      for (int rh = 0; rh < g.kh; ++rh)
+        for (int rw = 0; rw < g.kw; ++rw) {
+          int qd = rd - g.pd, qh = rh - g.ph, qw = rw - g.pw;
+          int pd = sd == 2 ? ((qd % 2) + 2) % 2 : 0;
+          int ph = g.s == 2 ? ((qh % 2) + 2) % 2 : 0, pw = g.s == 2 ? ((qw % 2) + 2) % 2 : 0;
+          P.tap_map[ntap] = (signed char)((pd * 2 + ph) * 2 + pw);
+          P.tap_dd[ntap] = (short)(sd == 2 ? floordiv(qd - pd, 2) : qd);
+          P.tap_dh[ntap] = (short)(g.s == 2 ? floordiv(qh - ph, 2) : qh);
+          P.tap_dw[ntap] = (short)(g.s == 2 ? floordiv(qw - pw, 2) : qw);
+          P.tap_slab[ntap] = (short)((rd * g.kh + rh) * g.kw + rw);
+          ++ntap;
+        }
     P.cls_tap_begin[1] = ntap;
-    P.cls_oh[0] = oh; P.cls_ow[0] = ow; P.cls_out_off[0] = 0; P.cls_res_off[0] = 0;
-    P.out_sn = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo; P.out_sw = ldo;
-    P.res_sn = (long long)oh * ow * ldres; P.res_sh = (long long)ow * ldres; P.res_sw = ldres;
-    loh = oh; low = ow;
+    P.cls_od[0] = od; P.cls_oh[0] = oh; P.cls_ow[0] = ow; P.cls_out_off[0] = 0; P.cls_res_off[0] = 0;
+    P.out_sn = (long long)od * oh * ow * ldo; P.out_sd = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo; P.out_sw = ldo;
+    P.res_sn = (long long)od * oh * ow * ldres; P.res_sd = (long long)oh * ow * ldres; P.res_sh = (long long)ow * ldres; P.res_sw = ldres;
+    lod = od; loh = oh; low = ow;
   } else {  // gather Y: ypos = (xpos + pad - r)/s
-    P.ncls = g.s * g.s;
-    for (int cph = 0; cph < g.s; ++cph)
-      for (int cpw = 0; cpw < g.s; ++cpw) {
-        int cls = cph * g.s + cpw;
-        P.cls_tap_begin[cls] = ntap;
-        for (int rh = 0; rh < g.kh; ++rh)
-          for (int rw = 0; rw < g.kw; ++rw) {
-            int ah = cph + g.ph - rh, aw = cpw + g.pw - rw;
-            if (g.s == 2 && ((ah & 1) || (aw & 1))) continue;
-            P.tap_map[ntap] = 0;
-            P.tap_dh[ntap] = (short)(g.s == 2 ? ah / 2 : ah);   // ah even here, exact
-            P.tap_dw[ntap] = (short)(g.s == 2 ? aw / 2 : aw);
-            P.tap_slab[ntap] = (short)(rh * g.kw + rw);
-            ++ntap;
-          }
-        MPGAN_REQUIRE(ntap > P.cls_tap_begin[cls], MPGAN_ERR_UNSUPPORTED, "empty tap class (k < stride)");
-        P.cls_oh[cls] = (oh - cph + g.s - 1) / g.s;
-        P.cls_ow[cls] = (ow - cpw + g.s - 1) / g.s;
-        P.cls_out_off[cls] = ((long long)cph * ow + cpw) * ldo;
-        P.cls_res_off[cls] = ((long long)cph * ow + cpw) * ldres;
-      }
+    P.ncls = sd * g.s * g.s;
+    for (int cpd = 0; cpd < sd; ++cpd)
+      for (int cph = 0; cph < g.s; ++cph)
+        for (int cpw = 0; cpw < g.s; ++cpw) {
+          int cls = (cpd * g.s + cph) * g.s + cpw;
+          P.cls_tap_begin[cls] = ntap;
+          for (int rd = 0; rd < g.kd; ++rd)
+            for (int rh = 0; rh < g.kh; ++rh)
+              for (int rw = 0; rw < g.kw; ++rw) {
+                int ad = cpd + g.pd - rd, ah = cph + g.ph - rh, aw = cpw + g.pw - rw;
+                if (g.s == 2 && ((ah & 1) || (aw & 1))) continue;
+                if (sd == 2 && (ad & 1)) continue;
+                P.tap_map[ntap] = 0;
+                P.tap_dd[ntap] = (short)(sd == 2 ? ad / 2 : ad);   // even here, exact
+                P.tap_dh[ntap] = (short)(g.s == 2 ? ah / 2 : ah);
+                P.tap_dw[ntap] = (short)(g.s == 2 ? aw / 2 : aw);
+                P.tap_slab[ntap] = (short)((rd * g.kh + rh) * g.kw + rw);
+                ++ntap;
+              }
+          MPGAN_REQUIRE(ntap > P.cls_tap_begin[cls], MPGAN_ERR_UNSUPPORTED, "empty tap class (k < stride)");
+          P.cls_od[cls] = (od - cpd + sd - 1) / sd;
+          P.cls_oh[cls] = (oh - cph + g.s - 1) / g.s;
+          P.cls_ow[cls] = (ow - cpw + g.s - 1) / g.s;
+          P.cls_out_off[cls] = (((long long)cpd * oh + cph) * ow + cpw) * ldo;
+          P.cls_res_off[cls] = (((long long)cpd * oh + cph) * ow + cpw) * ldres;
+        }
     P.cls_tap_begin[P.ncls] = ntap;
-    P.out_sn = (long long)oh * ow * ldo; P.out_sh = (long long)ow * ldo * g.s; P.out_sw = ldo * g.s;
-    P.res_sn = (long long)oh * ow * ldres; P.res_sh = (long long)ow * ldres * g.s; P.res_sw = ldres * g.s;
-    loh = (oh + g.s - 1) / g.s; low = (ow + g.s - 1) / g.s;
+    P.out_sn = (long long)od * oh * ow * ldo; P.out_sd = (long long)oh * ow * ldo * sd;
+    P.out_sh = (long long)ow * ldo * g.s; P.out_sw = ldo * g.s;
+    P.res_sn = (long long)od * oh * ow * ldres; P.res_sd = (long long)oh * ow * ldres * sd;
+    P.res_sh = (long long)ow * ldres * g.s; P.res_sw = ldres * g.s;
+    lod = (od + sd - 1) / sd; loh = (oh + g.s - 1) / g.s; low = (ow + g.s - 1) / g.s;
   }
-  (void)T;
-  choose_tile(low, loh, g.n, 128, &P.tw_log2, &P.th_log2);
-  const int tw = 1 << P.tw_log2, th = 1 << P.th_log2, tn = 128 / (tw * th);
-  P.tiles_w = (low + tw - 1) / tw; P.tiles_h = (loh + th - 1) / th; P.tiles_n = (g.n + tn - 1) / tn;
+  choose_tile(low, loh, lod, g.n, 128, r3, &P.tw_log2, &P.th_log2, &P.td_log2);
+  const int tw = 1 << P.tw_log2, th = 1 << P.th_log2, td = 1 << P.td_log2, tn = 128 / (tw * th * td);
+  P.tiles_w = (low + tw - 1) / tw; P.tiles_h = (loh + th - 1) / th; P.tiles_d = (lod + td - 1) / td;
+  P.tiles_n = (g.n + tn - 1) / tn;
   // two tiles per weight stage only when the layer still has several supertiles per SM (D layer 3 data gradient)
-  P.mt = (BN == 128 && KC == 64 && (long long)P.ncls * P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles >= 8LL * num_sms()) ? 2 : 1;
+  P.mt = (BN == 128 && KC == 64 &&
+          (long long)P.ncls * P.tiles_w * P.tiles_h * P.tiles_d * P.tiles_n * P.n_tiles >= 8LL * num_sms()) ? 2 : 1;
   P.tiles_w = (P.tiles_w + P.mt - 1) / P.mt;
 
-  CUtensorMap mA[4], mB;
-  uint32_t boxA[4] = {(uint32_t)KC, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
-  int rc = make_act_maps(mA, in, g.n, ih, iw, C, ldi, dir == 0 ? g.s : 1, boxA);
+  ActMaps mA;
+  CUtensorMap mB;
+  uint32_t boxA[5] = {(uint32_t)KC, (uint32_t)tw, (uint32_t)th, (uint32_t)(r3 ? td : tn), (uint32_t)tn};
+  int rc = make_act_maps(&mA, in, r3, g.n, id, ih, iw, C, ldi, dir == 0 ? g.s : 1, boxA);
   if (rc) return rc;
   {
-    uint64_t dims[3] = {(uint64_t)C, (uint64_t)(g.kh * g.kw), (uint64_t)N};
-    uint64_t str[2] = {(uint64_t)C, (uint64_t)C * g.kh * g.kw};
+    const int T = g.kd * g.kh * g.kw;
+    uint64_t dims[3] = {(uint64_t)C, (uint64_t)T, (uint64_t)N};
+    uint64_t str[2] = {(uint64_t)C, (uint64_t)C * T};
     uint32_t box[3] = {(uint32_t)KC, 1u, (uint32_t)BN};
     rc = encode_map(&mB, w, 3, dims, str, box);
     if (rc) return rc;
   }
+  if (r3) {
+    switch (KC) {
+      case 64: return launch_tapgemm_kc<64, true>(BN, P, mA, mB, s);
+      case 32: return launch_tapgemm_kc<32, true>(BN, P, mA, mB, s);
+      default: return launch_tapgemm_kc<16, true>(BN, P, mA, mB, s);
+    }
+  }
   switch (KC) {
-    case 64: return launch_tapgemm_kc<64>(BN, P, mA, mB, s);
-    case 32: return launch_tapgemm_kc<32>(BN, P, mA, mB, s);
-    default: return launch_tapgemm_kc<16>(BN, P, mA, mB, s);
+    case 64: return launch_tapgemm_kc<64, false>(BN, P, mA, mB, s);
+    case 32: return launch_tapgemm_kc<32, false>(BN, P, mA, mB, s);
+    default: return launch_tapgemm_kc<16, false>(BN, P, mA, mB, s);
   }
 }
 
-template <int NX, bool SMALL>
-static int launch_wgrad_t(const WgradParams& P, const CUtensorMap& mY, const CUtensorMap* mX, cudaStream_t s) {
+template <int NX, bool SMALL, bool R3>
+static int launch_wgrad_t(const WgradParams& P, const CUtensorMap& mY, const ActMaps& mX, cudaStream_t s) {
   using Cfg = WgCfg<NX, SMALL>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<NX, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<NX, SMALL, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     MPGAN_REQUIRE(e == cudaSuccess, MPGAN_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
     attr_done = true;
   }
   int grid = P.m_blocks * P.ngroups * P.splits;
-  launch_k(wgrad_kernel<NX, SMALL>, grid, 256, Cfg::SMEM_BYTES, s, P, mY, mX[0], mX[1], mX[2], mX[3]);
+  launch_k(wgrad_kernel<NX, SMALL, R3>, grid, 256, Cfg::SMEM_BYTES, s, P, mY, mX);
   MPGAN_CHECK_LAUNCH("wgrad_kernel");
   return 0;
+}
+
+template <bool R3>
+static int dispatch_wgrad(int cx, bool small, const WgradParams& P, const CUtensorMap& mY, const ActMaps& mX, cudaStream_t s) {
+  switch (cx) {
+    case 16: return small ? launch_wgrad_t<16, true, R3>(P, mY, mX, s) : launch_wgrad_t<16, false, R3>(P, mY, mX, s);
+    case 32: return small ? launch_wgrad_t<32, true, R3>(P, mY, mX, s) : launch_wgrad_t<32, false, R3>(P, mY, mX, s);
+    case 64: return small ? launch_wgrad_t<64, true, R3>(P, mY, mX, s) : launch_wgrad_t<64, false, R3>(P, mY, mX, s);
+    case 128: return launch_wgrad_t<128, false, R3>(P, mY, mX, s);
+    default: return launch_wgrad_t<256, false, R3>(P, mY, mX, s);
+  }
 }
 
 static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, int64_t ldy, float* dw, cudaStream_t s) {
   MPGAN_REQUIRE(g.cx == 16 || g.cx == 32 || g.cx == 64 || g.cx == 128 || g.cx == 256, MPGAN_ERR_UNSUPPORTED,
                 "tc wgrad needs cx in {16,32,64,128,256}");
   MPGAN_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, MPGAN_ERR_SHAPE, "pixel strides must be multiples of 8 elements");
+  const bool r3 = g.rank == 3;
+  const int sd = r3 ? g.s : 1;
   WgradParams P;
   memset(&P, 0, sizeof(P));
   P.cx = g.cx; P.cy = g.cy; P.dw = dw;
@@ -1035,27 +1093,31 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
     if (forced >= 1 && forced <= 7) P.nprod = forced;
   }
   int ntap = 0;
-  for (int rh = 0; rh < g.kh; ++rh)
-    for (int rw = 0; rw < g.kw; ++rw) {
-      int qh = rh - g.ph, qw = rw - g.pw;
-      int ph = g.s == 2 ? ((qh % 2) + 2) % 2 : 0, pw = g.s == 2 ? ((qw % 2) + 2) % 2 : 0;
-      P.tap_map[ntap] = (signed char)(ph * 2 + pw);
-      P.tap_dh[ntap] = (short)(g.s == 2 ? floordiv(qh - ph, 2) : qh);
-      P.tap_dw[ntap] = (short)(g.s == 2 ? floordiv(qw - pw, 2) : qw);
-      ++ntap;
-    }
+  for (int rd = 0; rd < g.kd; ++rd)
+    for (int rh = 0; rh < g.kh; ++rh)
+      for (int rw = 0; rw < g.kw; ++rw) {
+        int qd = rd - g.pd, qh = rh - g.ph, qw = rw - g.pw;
+        int pd = sd == 2 ? ((qd % 2) + 2) % 2 : 0;
+        int ph = g.s == 2 ? ((qh % 2) + 2) % 2 : 0, pw = g.s == 2 ? ((qw % 2) + 2) % 2 : 0;
+        P.tap_map[ntap] = (signed char)((pd * 2 + ph) * 2 + pw);
+        P.tap_dd[ntap] = (short)(sd == 2 ? floordiv(qd - pd, 2) : qd);
+        P.tap_dh[ntap] = (short)(g.s == 2 ? floordiv(qh - ph, 2) : qh);
+        P.tap_dw[ntap] = (short)(g.s == 2 ? floordiv(qw - pw, 2) : qw);
+        ++ntap;
+      }
   P.ntaps = ntap;
   // "small" = generator-sized layer (<= 1M output pixels): half of TMEM / ~100 KB of shared memory per CTA so that a
   // CTA of the concurrent data-gradient chain fits on the same SM; large layers (D) take the whole SM
-  const bool small = g.cx <= 64 && (long long)g.n * g.yh * g.yw <= (1LL << 20);
+  const bool small = g.cx <= 64 && (long long)g.n * g.yd * g.yh * g.yw <= (1LL << 20);
   const int max_tpg = (small ? 256 : 512) / g.cx;
   P.ngroups = (ntap + max_tpg - 1) / max_tpg;
   P.taps_per_group = (ntap + P.ngroups - 1) / P.ngroups;   // balanced groups
   P.m_blocks = (g.cy + 127) / 128;
-  choose_tile(g.yw, g.yh, g.n, 64, &P.tw_log2, &P.th_log2);
-  const int tw = 1 << P.tw_log2, th = 1 << P.th_log2, tn = 64 / (tw * th);
-  P.tiles_w = (g.yw + tw - 1) / tw; P.tiles_h = (g.yh + th - 1) / th; P.tiles_n = (g.n + tn - 1) / tn;
-  const int ptiles = P.tiles_w * P.tiles_h * P.tiles_n;
+  choose_tile(g.yw, g.yh, g.yd, g.n, 64, r3, &P.tw_log2, &P.th_log2, &P.td_log2);
+  const int tw = 1 << P.tw_log2, th = 1 << P.th_log2, td = 1 << P.td_log2, tn = 64 / (tw * th * td);
+  P.tiles_w = (g.yw + tw - 1) / tw; P.tiles_h = (g.yh + th - 1) / th; P.tiles_d = (g.yd + td - 1) / td;
+  P.tiles_n = (g.n + tn - 1) / tn;
+  const int ptiles = P.tiles_w * P.tiles_h * P.tiles_d * P.tiles_n;
   const int items = P.m_blocks * P.ngroups;
   // one CTA per SM for the large-channel configurations (~200 KB of shared memory each): the grid must not exceed the
   // SM count or the few extra CTAs run as a second wave and double the kernel time (152 CTAs did, on 148 SMs)
@@ -1064,24 +1126,25 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
   if (splits < 1) splits = 1;
   P.splits = splits;
 
-  CUtensorMap mY, mX[4];
-  {
+  CUtensorMap mY;
+  ActMaps mX;
+  if (r3) {
+    uint64_t dims[5] = {(uint64_t)g.cy, (uint64_t)g.yw, (uint64_t)g.yh, (uint64_t)g.yd, (uint64_t)g.n};
+    uint64_t str[4] = {(uint64_t)ldy, (uint64_t)ldy * g.yw, (uint64_t)ldy * g.yw * g.yh, (uint64_t)ldy * g.yw * g.yh * g.yd};
+    uint32_t box[5] = {64u, (uint32_t)tw, (uint32_t)th, (uint32_t)td, (uint32_t)tn};
+    int rc = encode_map(&mY, y, 5, dims, str, box);
+    if (rc) return rc;
+  } else {
     uint64_t dims[4] = {(uint64_t)g.cy, (uint64_t)g.yw, (uint64_t)g.yh, (uint64_t)g.n};
     uint64_t str[3] = {(uint64_t)ldy, (uint64_t)ldy * g.yw, (uint64_t)ldy * g.yw * g.yh};
     uint32_t box[4] = {64u, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
     int rc = encode_map(&mY, y, 4, dims, str, box);
     if (rc) return rc;
   }
-  uint32_t boxX[4] = {(uint32_t)(g.cx < 64 ? g.cx : 64), (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
-  int rc = make_act_maps(mX, x, g.n, g.xh, g.xw, g.cx, ldx, g.s, boxX);
+  uint32_t boxX[5] = {(uint32_t)(g.cx < 64 ? g.cx : 64), (uint32_t)tw, (uint32_t)th, (uint32_t)(r3 ? td : tn), (uint32_t)tn};
+  int rc = make_act_maps(&mX, x, r3, g.n, g.xd, g.xh, g.xw, g.cx, ldx, g.s, boxX);
   if (rc) return rc;
-  switch (g.cx) {
-    case 16: return small ? launch_wgrad_t<16, true>(P, mY, mX, s) : launch_wgrad_t<16, false>(P, mY, mX, s);
-    case 32: return small ? launch_wgrad_t<32, true>(P, mY, mX, s) : launch_wgrad_t<32, false>(P, mY, mX, s);
-    case 64: return small ? launch_wgrad_t<64, true>(P, mY, mX, s) : launch_wgrad_t<64, false>(P, mY, mX, s);
-    case 128: return launch_wgrad_t<128, false>(P, mY, mX, s);
-    default: return launch_wgrad_t<256, false>(P, mY, mX, s);
-  }
+  return r3 ? dispatch_wgrad<true>(g.cx, small, P, mY, mX, s) : dispatch_wgrad<false>(g.cx, small, P, mY, mX, s);
 }
 
 }  // namespace tc
@@ -1096,7 +1159,7 @@ extern "C" int mpgan_tc_supported(const MpganConvGeom* g, int direction) {
   if (direction == 2) return (g2.cx == 16 || g2.cx == 32 || g2.cx == 64 || g2.cx == 128 || g2.cx == 256) ? 1 : 0;
   const int N = direction == 0 ? g2.cy : g2.cx;
   if (pick_bn(N) == 0 || N > 512) return 0;
-  if (direction == 1 && g2.s == 2 && (g2.kh < 2 || g2.kw < 2)) return 0;
+  if (direction == 1 && g2.s == 2 && (g2.kh < 2 || g2.kw < 2 || (g2.rank == 3 && g2.kd < 2))) return 0;
   return 1;
 }
 

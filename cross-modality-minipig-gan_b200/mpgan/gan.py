@@ -119,6 +119,7 @@ class GAN(_Base):
         self._graph = None
         self._const_cache = {}
         self.comm = None  # set by mpgan.ddp.attach()
+        self.overlap_comm = True   # fused_step: gradient all-reduces overlapped with compute (mpgan/ddp.py)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         """Accepts both MONAI namings of the generator's BatchNorm / PReLU keys (``remap_monai_keys``)."""
@@ -362,22 +363,45 @@ class GAN(_Base):
         G.run_backward(gplan, dgen, need_dx=False)
         if grad_probe is not None:  # test hook: look at the gradients before the optimiser consumes them
             grad_probe("generator", G)
-        if self.comm is not None:
+        # data parallel: G's bucket reduces on the NCCL stream UNDER the discriminator's real-batch forward, which
+        # depends on neither the generator's gradients nor its update
+        overlap = self.comm is not None and self.overlap_comm
+        h_g = self.comm.start(G.runtime.grad) if overlap else None
+        if self.comm is not None and not overlap:
             self.comm.allreduce(G.runtime.grad)
-        G.runtime.adam_step(hp.g_lr, hp.b1, hp.b2)
-        G.runtime.zero_grad()
         # ---- optimizer 1: discriminator (generator frozen: forward only, train-mode BN)
         p_real, plan_r = D.run_forward(t2, save=True, need_wgrad=True)
         ops.bce_fwd(p_real, soft, 0.5, logs[2:3])
+        if overlap:
+            self.comm.finish(h_g)
+        G.runtime.adam_step(hp.g_lr, hp.b1, hp.b2)
+        G.runtime.zero_grad()
         gen2, _ = G.run_forward(t1, save=False, need_wgrad=False)
         p_fake, plan_f = D.run_forward(gen2, save=True, need_wgrad=True)
         ops.bce_fwd(p_fake, zeros, 0.5, logs[3:4])
         D.run_backward(plan_f, ops.bce_bwd(p_fake, zeros, 0.5, None, torch.empty_like(p_fake)), need_dx=False)
-        D.run_backward(plan_r, ops.bce_bwd(p_real, soft, 0.5, None, torch.empty_like(p_real)), need_dx=False)
-        if grad_probe is not None:
-            grad_probe("discriminator", D)
-        if self.comm is not None:
-            self.comm.allreduce(D.runtime.grad)
+        handles = []
+        if overlap and grad_probe is None:
+            # D's bucket is split at layer 3 (flat order: D1, BN1, D2, BN2 | D3, BN3, D4, BN4, Linear): the upper part is
+            # final once layer 3's weight gradient of THIS (last) backward is enqueued, and reduces under layers 2 / 1
+            split = D.runtime.offsets[id(D.model_conv[6].weight)]
+            grad = D.runtime.grad
+
+            def layer_done(i, wgrad_stream):
+                if i == 2:
+                    handles.append(self.comm.start(grad[split:], stream=wgrad_stream))
+
+            D.run_backward(plan_r, ops.bce_bwd(p_real, soft, 0.5, None, torch.empty_like(p_real)), need_dx=False,
+                           on_layer_done=layer_done)
+            handles.append(self.comm.start(grad[:split]))
+            for h in handles:
+                self.comm.finish(h)
+        else:
+            D.run_backward(plan_r, ops.bce_bwd(p_real, soft, 0.5, None, torch.empty_like(p_real)), need_dx=False)
+            if grad_probe is not None:
+                grad_probe("discriminator", D)
+            if self.comm is not None:
+                self.comm.allreduce(D.runtime.grad)
         D.runtime.adam_step(hp.d_lr, hp.b1, hp.b2)
         D.runtime.zero_grad()
         return logs

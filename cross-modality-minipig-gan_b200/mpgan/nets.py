@@ -696,9 +696,12 @@ class _ConvBnLeakyStack(_PlanNet):
                 out.append(a.float().clone())
         return out
 
-    def run_backward(self, plan, dprob, need_dx=True, act_grads=None, internal=False):
+    def run_backward(self, plan, dprob, need_dx=True, act_grads=None, internal=False, on_layer_done=None):
         """act_grads: {activation index: gradient} -- logical NC[D]HW fp32 tensors (the autograd bridge) or, with
-        ``internal=True``, tensors in the activations' own layout / dtype (fused perceptual step)."""
+        ``internal=True``, tensors in the activations' own layout / dtype (fused perceptual step).
+        on_layer_done(i, stream): called after conv layer i's backward has been enqueued; ``stream`` is the stream that
+        is ordered after ALL of that layer's (and the later layers') gradient kernels -- the weight-gradient side stream
+        when the pass forks them, else the current stream (data-parallel bucket overlap, mpgan/ddp.py)."""
         rt = plan.rt
         lin_tape, p, feat_shape = plan.tape.pop()
         linears = [m for m in self.model_linear if isinstance(m, nn.Linear)]
@@ -763,6 +766,11 @@ class _ConvBnLeakyStack(_PlanNet):
             if (3 * i) in ag:
                 dc = ops.add_copy(dc, ag[3 * i], dc) if internal else dc + ag[3 * i].permute(to_cl).to(dc.dtype)
             dh = conv_backward(rt.rec[convs[i]], h_in, dc, plan, need_dx=(need_dx or i > 0), bias_done=fused_bias)
+            if on_layer_done is not None:
+                forked = plan.wgrad_forked and N_WGRAD_STREAMS == 1
+                if plan.wgrad_forked and not forked:   # several weight-gradient streams: order them all behind the current one
+                    join_wgrad(plan, dp.device)
+                on_layer_done(i, side_stream(dp.device, "wgrad0") if forked else torch.cuda.current_stream())
         join_wgrad(plan, dp.device)
         if not need_dx:
             return None

@@ -128,7 +128,7 @@ def conv_act(spec, x, w, bias, slope, res=None, out=None):
     folded into (w, bias).  Transposed layers take the transposed weights.  Returns None when the layer is not covered
     (the caller then runs the unfused kernels)."""
     lib = _lib.require_device()
-    if x.dtype != torch.bfloat16 or spec.rank != 2:
+    if x.dtype != torch.bfloat16:
         return None
     n, ins = x.shape[0], tuple(x.shape[1:-1])
     if spec.transposed:

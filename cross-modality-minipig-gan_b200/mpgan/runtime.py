@@ -121,7 +121,7 @@ class Runtime:
                 r.db = m.bias.grad if m.bias is not None else None
                 r.wt = None
                 # a transposed bf16 copy is needed wherever the tcgen05 kernel runs in the Y -> X direction
-                r.need_wt = self.shadow is not None and r.spec.rank == 2 and r.spec.cx % 16 == 0 and r.spec.cy % 16 == 0
+                r.need_wt = self.shadow is not None and r.spec.cx % 16 == 0 and r.spec.cy % 16 == 0
                 if r.need_wt:
                     r.wt = torch.empty(m.weight.numel(), dtype=torch.bfloat16, device=self.device)
                 self.rec[m] = r

@@ -56,9 +56,16 @@ def _worker(rank, world, port, result_dir):
     ps = list(model.discriminator.parameters())
     flat = torch.cat([p.grad.reshape(-1) for p in ps])
     torch.save({"local": flat.clone(), "w0": ps[0].detach().clone()}, os.path.join(result_dir, f"local{rank}.pt"))
+    local = flat.clone()
     comm.allreduce(flat)
     torch.save(flat, os.path.join(result_dir, f"avg{rank}.pt"))
     assert comm.calls == 1 and comm.bytes == flat.numel() * 4
+    # the overlapped form the fused step uses: two slices of one flat buffer, started one after the other, finished later
+    split = (local.numel() // 3) // 8 * 8
+    h_hi = comm.start(local[split:])
+    h_lo = comm.start(local[:split])
+    comm.finish(h_hi), comm.finish(h_lo)
+    assert torch.allclose(local, flat, rtol=1e-6, atol=1e-8) and comm.calls == 3
     dist.barrier()
     dist.destroy_process_group()
 

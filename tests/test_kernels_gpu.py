@@ -288,6 +288,89 @@ def test_tc_conv_wgrad(case):
     assert rel_l2(dw, 2 * oti(ref)) <= 2e-3
 
 
+# ------------------------------------------------------------------ tcgen05 path, rank 3 (NDHWC, 5-D TMA boxes)
+TC3_CASES = [
+    # n, cin, cout, (d, h, w), k, s, p
+    (2, 64, 128, (12, 11, 13), 3, 1, 0),     # D layer 2 family at 3-D (GAN_final.py:173-176): 27 taps, valid padding
+    (2, 128, 256, (14, 14, 14), 4, 2, 0),    # D layer 3 family: 64 taps, 8 input-parity maps / 8 output-parity classes
+    (1, 256, 256, (13, 11, 9), 4, 2, 0),     # D layer 4 family, odd extents
+    (2, 16, 16, (8, 8, 8), 3, 1, 1),         # G unit: padding through OOB zero fill in all three dimensions
+    (2, 16, 32, (8, 10, 12), 3, 2, 1),       # G down layer: stride 2 with padding
+    (2, 32, 64, (6, 6, 6), 3, 2, 1),
+    (3, 64, 128, (4, 4, 4), 1, 1, 0),        # 1x1x1 residual conv
+    (1, 128, 128, (5, 6, 7), 3, 1, 1),
+    (5, 256, 512, (10, 10, 10), 3, 1, 0),    # patch-D layer 4 at 3-D (test_runs/GAN.py:160-165): two N tiles
+    (1, 192, 32, (5, 5, 5), 3, 1, 1),        # three 64-channel chunks
+]
+
+
+def _conv3_ref(case, seed):
+    n, cin, cout, sp, k, s, p = case
+    x = rnd(n, cin, *sp, seed=seed).bfloat16()
+    w = (rnd(cout, cin, k, k, k, seed=seed + 1) * 0.1).bfloat16()
+    return n, cin, cout, sp, k, s, p, x, w
+
+
+@pytest.mark.parametrize("case", TC3_CASES)
+def test_tc3_conv_fprop(case):
+    n, cin, cout, sp, k, s, p, x, w = _conv3_ref(case, 41)
+    b = rnd(cout, seed=43)
+    ref = F.conv3d(x.float(), w.float(), b, stride=s, padding=p)
+    spec = ops.ConvSpec(3, cin, cout, k, s, p)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    y, fused = ops.conv_fprop(spec, cl(x, torch.bfloat16), oti(w, torch.bfloat16), b, stats=stats)
+    assert fused, "tcgen05 path was not taken"
+    torch.cuda.synchronize()
+    assert rel_l2(uncl(y), ref) <= 6e-3
+    yr = uncl(y).double()
+    assert rel_l2(stats[:cout], yr.sum(dim=(0, 2, 3, 4))) <= 1e-4
+    assert rel_l2(stats[cout:], (yr * yr).sum(dim=(0, 2, 3, 4))) <= 1e-4
+
+
+@pytest.mark.parametrize("case", TC3_CASES)
+def test_tc3_conv_bprop(case):
+    n, cin, cout, sp, k, s, p, _, w = _conv3_ref(case, 44)
+    osp = tuple((v + 2 * p - k) // s + 1 for v in sp)
+    dy = rnd(n, cout, *osp, seed=46).bfloat16()
+    ref = torch.nn.grad.conv3d_input((n, cin) + sp, w.float(), dy.float(), stride=s, padding=p)
+    spec = ops.ConvSpec(3, cin, cout, k, s, p)
+    wt = torch.empty(w.numel(), dtype=torch.bfloat16, device=DEV)
+    ops.weight_transpose(oti(w, torch.bfloat16), wt, cout, k ** 3, cin)
+    res = rnd(n, *sp, cin, seed=47).bfloat16()
+    dx, _ = ops.conv_bprop(spec, cl(dy, torch.bfloat16), oti(w, torch.bfloat16), wt, None, xs=sp)
+    torch.cuda.synchronize()
+    assert rel_l2(uncl(dx), ref) <= 6e-3
+    dx2, _ = ops.conv_bprop(spec, cl(dy, torch.bfloat16), oti(w, torch.bfloat16), wt, None, xs=sp, res=res)   # fused branch sum
+    assert rel_l2(uncl(dx2), ref + uncl(res)) <= 6e-3
+
+
+@pytest.mark.parametrize("case", [c for c in TC3_CASES if c[1] in (16, 32, 64, 128, 256)])
+def test_tc3_conv_wgrad(case):
+    n, cin, cout, sp, k, s, p, x, _ = _conv3_ref(case, 48)
+    osp = tuple((v + 2 * p - k) // s + 1 for v in sp)
+    dy = rnd(n, cout, *osp, seed=50).bfloat16()
+    ref = torch.nn.grad.conv3d_weight(x.float(), (cout, cin, k, k, k), dy.float(), stride=s, padding=p)
+    spec = ops.ConvSpec(3, cin, cout, k, s, p)
+    dw = torch.zeros(cout, k ** 3, cin, device=DEV)
+    ops.conv_wgrad(spec, cl(x, torch.bfloat16), cl(dy, torch.bfloat16), dw)
+    torch.cuda.synchronize()
+    assert rel_l2(dw, oti(ref)) <= 2e-3
+    ops.conv_wgrad(spec, cl(x, torch.bfloat16), cl(dy, torch.bfloat16), dw)  # accumulates
+    assert rel_l2(dw, 2 * oti(ref)) <= 2e-3
+
+
+def test_tc3_inference_fused_layer():
+    """Eval-mode fused layer (folded BatchNorm bias + PReLU + residual in the epilogue) on the rank-3 path."""
+    n, cin, cout, sp = 2, 32, 32, (6, 7, 8)
+    x = rnd(n, cin, *sp, seed=51).bfloat16()
+    w = (rnd(cout, cin, 3, 3, 3, seed=52) * 0.1).bfloat16()
+    b, slope = rnd(cout, seed=53), torch.full((1,), 0.25, device=DEV)
+    res = rnd(n, *sp, cout, seed=54).bfloat16()
+    ref = F.prelu(F.conv3d(x.float(), w.float(), b, padding=1), slope) + uncl(res)
+    y = ops.conv_act(ops.ConvSpec(3, cin, cout, 3, 1, 1), cl(x, torch.bfloat16), oti(w, torch.bfloat16), b, slope, res=res)
+    assert y is not None and rel_l2(uncl(y), ref) <= 6e-3
+
+
 def test_tc_conv_full_size_linearity():
     """BASELINE-size D layer 3 (32 x 252^2 x 128 -> 125^2 x 256): checked through linearity and a sampled window."""
     n, cin, cout, h = 8, 128, 256, 252

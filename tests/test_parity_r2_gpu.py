@@ -83,7 +83,7 @@ def test_bf16_generator_cascade_vs_rounding_floor(nblocks, size, batch):
     assert rel_l2(y, y32) <= FLOOR * floor, (rel_l2(y, y32), floor)
     for (n1, b1), (n2, b2), (_, b3) in zip(mine.named_buffers(), ref.named_buffers(), m.named_buffers()):
         if b2.dtype.is_floating_point:
-            assert rel_l2(b1, b2) <= max(FLOOR * rel_l2(b3, b2), 2e-3), n1
+            assert rel_l2(b1, b2) <= 2 * rel_l2(b3, b2) + 2e-3, n1      # (16..128-element vectors: a noisier ratio than the image)
 
 
 def test_bf16_discriminators_vs_rounding_matched_oracle():
@@ -317,14 +317,13 @@ def test_perceptual_step_batch32_128_patches(precision):
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_teacher_forced_steps_reach_the_saturated_regime(precision):
-    """SURVEY.md section 0 / inferrence.py:102: after ONE optimizer step at 256^2 the discriminator's Linear (fan-in
-    952 576) drives sigmoid to exactly 0, BCE hits torch's -100 log clamp: g_adv = 100.0, d_loss = (0.9*100 + 0)/2 = 45.0,
-    and D's gradients vanish identically.  Each step starts from the ORACLE's state (weights, BatchNorm buffers, Adam
-    moments and step counters loaded into the device model), so Adam's sign-like first updates cannot compound.
-    fp32 mode reproduces the regime exactly.  bf16 mode reproduces the generator side (g_adv = 100.0, fake loss 0); on
-    the real batch the discriminator's convolution outputs after Adam's coherent first update are large per-channel
-    offsets with a small spread, which bf16 STORAGE of the pre-BatchNorm tensor cannot resolve (ulp 0.25 at |c| ~ 50)
-    -- any bf16-output convolution shares this -- so D(t2) is not required to saturate at the same step there."""
+    """SURVEY.md section 0 / inferrence.py:102 (checkpoint names "g_loss=100.03 ... d_loss=45.00"): after ONE optimizer
+    step at 256^2 the discriminator's Linear (fan-in 952 576) drives sigmoid(D(G(x))) to exactly 0 and BCE hits torch's
+    -100 log clamp: g_adv = 100.0 from step 1 on; from step 3 on D(t2) is saturated too (exactly 0 or 1 per sample),
+    d_loss is an exact multiple of the clamp (25.0 with this seed: one real sample at p = 0, one at p = 1) and EVERY
+    discriminator gradient is identically zero.  Oracle trajectory (seed 0 / 1, batch 2): g_adv 0.73, 100, 100, ...;
+    d_loss 1.32, 2.85, 14.52, 25, 25, ...  Each step starts from the ORACLE's state (weights, BatchNorm buffers, Adam
+    moments and step counters loaded into the device model), so Adam's sign-like first updates cannot compound."""
     B, S = 2, 256
     torch.manual_seed(0)
     ora = GANOracle("final", dims=2, spatial=S)
@@ -334,8 +333,8 @@ def test_teacher_forced_steps_reach_the_saturated_regime(precision):
     d = to_dev(batch)
     for net in (mine.generator, mine.discriminator):
         net.runtime.ensure(torch.device(DEV, 0))
-    saturated_seen = False
-    for step in range(3):
+    adv_saturated = d_saturated = 0
+    for step in range(5):
         mine.load_state_dict(ora.state_dict())
         mine.load_optimizer_states([o.state_dict() for o in opts])
         keep = {}
@@ -347,23 +346,28 @@ def test_teacher_forced_steps_reach_the_saturated_regime(precision):
         d_ref = float(ref[1])
         ftol = 1e-4 if precision == "fp32" else 5e-2
         assert abs(logs[1] - g_rec_ref) <= ftol * abs(g_rec_ref), (step, logs[1], g_rec_ref)
-        if g_adv_ref == 100.0:      # saturated: exact values, identically-zero discriminator gradients
-            saturated_seen = True
+        dn = [k for k in keep if k.startswith("discriminator.")]
+        if g_adv_ref == 100.0:      # D(G(x)) == 0 exactly: the clamp value itself, and a zero fake-branch loss
+            adv_saturated += 1
             assert logs[0] == 100.0, (step, logs[0])
             assert logs[3] == 0.0, (step, logs)
-            assert d_ref == 45.0
-            dn = [k for k in keep if k.startswith("discriminator.")]
-            assert all(float(keep[k].abs().max()) == 0.0 for k in dn)
-            if precision == "fp32":
-                assert logs[2] + logs[3] == 45.0, (step, logs)
-                assert all(float(probe["discriminator"][k].abs().max()) == 0.0 for k in dn), step
         else:
             assert abs(logs[0] - g_adv_ref) <= ftol * abs(g_adv_ref), (step, logs[0], g_adv_ref)
             if precision == "fp32":
                 gn = [k for k in keep if k.startswith("generator.")]
                 a, b = flat_grads(probe["generator"], gn), flat_grads(keep, gn)
                 assert float((a - b).norm() / b.norm()) <= 3e-2, step
-    assert saturated_seen, "the reference's saturated regime was never reached"
+        if all(float(keep[k].abs().max()) == 0.0 for k in dn):   # fully saturated discriminator
+            d_saturated += 1
+            assert logs[2] + logs[3] == d_ref, (step, logs, d_ref)
+            assert d_ref * 2 / 10 == round(d_ref * 2 / 10), d_ref         # a multiple of 0.1 * 100 / batch-mean terms
+            assert all(float(probe["discriminator"][k].abs().max()) == 0.0 for k in dn), step
+        elif g_adv_ref != 100.0 or precision == "fp32":
+            # (the half-saturated steps 1-2 in bf16: D(t2)'s logits sit where bf16 rounding of the activations moves the
+            #  loss by tens of percent -- reported in profiles/parity_r2.md, not gated)
+            # d_loss follows the generator's Adam update inside the step (sign-like at step 0: 2*lr per flipped parameter)
+            assert abs(logs[2] + logs[3] - d_ref) <= 5e-2 * abs(d_ref), (step, logs, d_ref)
+    assert adv_saturated >= 3 and d_saturated >= 1, (adv_saturated, d_saturated)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -25,6 +25,12 @@ for w in $WHAT; do
              echo "ref exit $?"; cat gpurun_out/benchref_$TAG.log;;
     phases)  timeout 600 python tools/phase_times.py 10 > gpurun_out/phase_$TAG.log 2>&1; echo "phases exit $?"; cat gpurun_out/phase_$TAG.log;;
     ops)     timeout 900 python tools/bench_ops.py > gpurun_out/ops_$TAG.log 2>&1; echo "ops exit $?"; tail -70 gpurun_out/ops_$TAG.log;;
+    k3d)     timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 600 -k "tc3" > gpurun_out/pytest_k3d_$TAG.log 2>&1
+             echo "k3d exit $?"; tail -30 gpurun_out/pytest_k3d_$TAG.log;;
+    n3d)     timeout 900 python -m pytest tests/test_nets_gpu.py -m gpu -q --timeout 600 -k "3" > gpurun_out/pytest_n3d_$TAG.log 2>&1
+             echo "n3d exit $?"; tail -30 gpurun_out/pytest_n3d_$TAG.log;;
+    b3d)     timeout 900 python tools/bench_3d.py ${B3D_ARGS:-1 3 128} > gpurun_out/bench3d_$TAG.log 2> gpurun_out/bench3d_$TAG.err
+             echo "b3d exit $?"; cat gpurun_out/bench3d_$TAG.log; tail -5 gpurun_out/bench3d_$TAG.err;;
     ncu)     CMD="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-extra"
              timeout 600 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
              timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-2800} -c ${NCU_COUNT:-2800} --csv \
