@@ -10,6 +10,8 @@ Mirrors /root/reference/code/GAN/GAN_final.py:212-308 (variant="final": BCE + L1
 * ``fused_step(batch)`` -- the same arithmetic as one static sequence of kernels with no autograd and no host
   synchronisation, which ``capture()`` records into a CUDA graph.  ``bench.py`` times this path.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -119,7 +121,8 @@ class GAN(_Base):
         self._graph = None
         self._const_cache = {}
         self.comm = None  # set by mpgan.ddp.attach()
-        self.overlap_comm = True   # fused_step: gradient all-reduces overlapped with compute (mpgan/ddp.py)
+        # fused_step: gradient all-reduces overlapped with compute (mpgan/ddp.py); MPGAN_NO_COMM_OVERLAP=1 = blocking form
+        self.overlap_comm = os.environ.get("MPGAN_NO_COMM_OVERLAP", "0") != "1"
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         """Accepts both MONAI namings of the generator's BatchNorm / PReLU keys (``remap_monai_keys``)."""

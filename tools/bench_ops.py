@@ -54,22 +54,24 @@ def report(name, us, nbytes, flops=0.0):
     print(f"{name:58s} {us:9.1f} us  {nbytes / us / 1e3:8.1f} GB/s  {flops / us / 1e6:8.1f} TFLOP/s", flush=True)
 
 
-def conv_case(name, cin, cout, k, s, p, xs, transposed=False, dirs=("f", "b", "w")):
-    """Underlying conv X(cin) -> Y(cout); for a ConvTranspose pass the underlying conv's cin/cout."""
-    spec = ops.ConvSpec(2, cin, cout, k, s, p, transposed, s - 1 if transposed else 0)
-    ys = spec.y_of_x((xs, xs))[0]
-    x = rnd(B, xs, xs, cin)
-    y = rnd(B, ys, ys, cout)
-    w = rnd(cout, k * k, cin) * 0.1
+def conv_case(name, cin, cout, k, s, p, xs, transposed=False, dirs=("f", "b", "w"), rank=2, batch=None):
+    """Underlying conv X(cin) -> Y(cout); for a ConvTranspose pass the underlying conv's cin/cout.  rank 3: the
+    reference's literal volumes (NDHWC, rank-3 tcgen05 path)."""
+    n = batch or B
+    spec = ops.ConvSpec(rank, cin, cout, k, s, p, transposed, s - 1 if transposed else 0)
+    ys = spec.y_of_x((xs,) * rank)[0]
+    x = rnd(n, *([xs] * rank), cin)
+    y = rnd(n, *([ys] * rank), cout)
+    w = rnd(cout, k ** rank, cin) * 0.1
     wt = w.permute(2, 1, 0).contiguous()
-    dw = torch.zeros(cout, k * k, cin, device=DEV)
+    dw = torch.zeros(cout, k ** rank, cin, device=DEV)
     stats = None if os.environ.get("NOSTATS") else torch.zeros(2 * max(cin, cout), dtype=torch.float64, device=DEV)
-    flops = 2.0 * B * ys * ys * cout * k * k * cin
+    flops = 2.0 * n * ys ** rank * cout * k ** rank * cin
     nb = (x.numel() + y.numel()) * 2
     if "f" in dirs:
         report(f"{name} fprop {cin}->{cout} k{k}s{s} @{xs}", timeit(lambda: ops.conv_fprop(spec, x, w, None, out=y, stats=stats)), nb, flops)
     if "b" in dirs:
-        report(f"{name} bprop {cout}->{cin} k{k}s{s} @{ys}", timeit(lambda: ops.conv_bprop(spec, y, w, wt, None, xs=(xs, xs), out=x, stats=stats)), nb, flops)
+        report(f"{name} bprop {cout}->{cin} k{k}s{s} @{ys}", timeit(lambda: ops.conv_bprop(spec, y, w, wt, None, xs=(xs,) * rank, out=x, stats=stats)), nb, flops)
     if "w" in dirs:
         report(f"{name} wgrad {cin}x{cout} k{k}s{s} @{xs}", timeit(lambda: ops.conv_wgrad(spec, x, y, dw)), nb, flops)
 
@@ -124,6 +126,20 @@ CASES = {
     "d2": lambda: conv_case("D2", 64, 128, 3, 1, 0, 254),
     "d3": lambda: conv_case("D3", 128, 256, 4, 2, 0, 252),
     "d4": lambda: conv_case("D4", 256, 256, 4, 2, 0, 125),
+    # rank 3: the reference's literal 128^3 volumes (GAN_final.py:107,167-201), batch 1
+    "v_d1": lambda: conv_case("3D D1", 1, 64, 3, 1, 0, 128, rank=3, batch=1),
+    "v_d2": lambda: conv_case("3D D2", 64, 128, 3, 1, 0, 126, rank=3, batch=1),
+    "v_d3": lambda: conv_case("3D D3", 128, 256, 4, 2, 0, 124, rank=3, batch=1),
+    "v_d4": lambda: conv_case("3D D4", 256, 256, 4, 2, 0, 61, rank=3, batch=1),
+    "v_g1": lambda: conv_case("3D G first", 1, 16, 3, 2, 1, 128, rank=3, batch=1),
+    "v_g16": lambda: conv_case("3D G", 16, 16, 3, 1, 1, 64, rank=3, batch=1),
+    "v_g16_32": lambda: conv_case("3D G", 16, 32, 3, 2, 1, 64, rank=3, batch=1),
+    "v_g32": lambda: conv_case("3D G", 32, 32, 3, 1, 1, 32, rank=3, batch=1),
+    "v_g64": lambda: conv_case("3D G", 64, 64, 3, 1, 1, 16, rank=3, batch=1),
+    "v_g128": lambda: conv_case("3D G", 128, 128, 3, 1, 1, 16, rank=3, batch=1),
+    "v_gT16": lambda: conv_case("3D G ConvT64->16", 16, 64, 3, 2, 1, 64, transposed=True, rank=3, batch=1),
+    "v_gT1": lambda: conv_case("3D G ConvT32->1", 1, 32, 3, 2, 1, 128, transposed=True, rank=3, batch=1),
+    "v_g11": lambda: conv_case("3D G 1->1", 1, 1, 3, 1, 1, 128, rank=3, batch=1),
     # batch norm
     "bn_g16": lambda: bn_case("G", 16, 128, ACT_PRELU),
     "bn_g64": lambda: bn_case("G", 64, 32, ACT_PRELU),

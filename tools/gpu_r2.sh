@@ -24,7 +24,7 @@ for w in $WHAT; do
     ref)     timeout 600 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/benchref_$TAG.log 2> gpurun_out/benchref_$TAG.err
              echo "ref exit $?"; cat gpurun_out/benchref_$TAG.log;;
     phases)  timeout 600 python tools/phase_times.py 10 > gpurun_out/phase_$TAG.log 2>&1; echo "phases exit $?"; cat gpurun_out/phase_$TAG.log;;
-    ops)     timeout 900 python tools/bench_ops.py > gpurun_out/ops_$TAG.log 2>&1; echo "ops exit $?"; tail -70 gpurun_out/ops_$TAG.log;;
+    ops)     timeout 900 python tools/bench_ops.py ${OPS_FILTER:-} > gpurun_out/ops_$TAG.log 2>&1; echo "ops exit $?"; tail -70 gpurun_out/ops_$TAG.log;;
     k3d)     timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 600 -k "tc3" > gpurun_out/pytest_k3d_$TAG.log 2>&1
              echo "k3d exit $?"; tail -30 gpurun_out/pytest_k3d_$TAG.log;;
     n3d)     timeout 900 python -m pytest tests/test_nets_gpu.py -m gpu -q --timeout 600 -k "3" > gpurun_out/pytest_n3d_$TAG.log 2>&1
