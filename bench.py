@@ -324,7 +324,10 @@ def main():
     if world > 1:
         # INFO (unless the caller chose otherwise): the driver counts the ranks of the communicator from NCCL's own log;
         # stdout was redirected to stderr above, so the JSON line stays the only thing on the real stdout
-        os.environ.setdefault("NCCL_DEBUG", os.environ.get("MPGAN_NCCL_DEBUG", "INFO"))
+        pre = os.environ.get("NCCL_DEBUG")
+        want = os.environ.get("MPGAN_NCCL_DEBUG") or (pre if (pre or "").upper() in ("INFO", "TRACE") else "INFO")
+        os.environ["NCCL_DEBUG"] = want
+        print(f"# NCCL_DEBUG: environment had {pre!r}, using {want!r} (override with MPGAN_NCCL_DEBUG)", file=sys.stderr, flush=True)
         rank, world, local = ddp.init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

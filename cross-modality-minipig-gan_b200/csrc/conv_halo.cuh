@@ -47,6 +47,7 @@ struct HaloParams {
   int wide;            // output rows are 32-byte aligned: 256-bit stores
   const float* slope;  // optional device scalar: PReLU applied to (acc + bias) before the residual (inference fusion)
   int n_store;         // 0 = all N channels; 1 = only channel 0 (one-channel output computed with a zero-padded N = 16)
+  int nissue;          // MMA-issuing threads (1 or 2): issuer i takes tiles i, i + nissue, ... (independent accumulators)
   uint32_t idesc;
 };
 
@@ -168,11 +169,14 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 1) {
-    if (elect_one()) {  // ================= MMA issuer =================
-      // ONE thread issues every MMA of the CTA, so for small N (a 128 x 16 x 16 MMA occupies the tensor pipe for
-      // ~8 cycles) its scalar instruction stream is the critical path: descriptors are a precomputed 64-bit base plus
-      // compile-time offsets (fully unrolled taps / k-steps), ring indices advance without divisions.
+  } else if (warp == 1 || warp == 3) {
+    const int iss = warp == 1 ? 0 : 1;
+    if (iss < P.nissue && elect_one()) {  // ================= MMA issuer(s) =================
+      // ONE thread issues every MMA of a tile, so for small N (a 128 x 16 x 16 MMA occupies the tensor pipe for
+      // ~8 cycles) its instruction stream -- and the accumulate-into-the-same-TMEM-tile dependency between the taps of a
+      // tile -- is the critical path: descriptors are a precomputed 64-bit base plus compile-time offsets (fully
+      // unrolled taps / k-steps), ring indices advance without divisions, and with P.nissue == 2 a second thread (warp 3)
+      // issues the odd tiles: two independent accumulation chains in flight.
       constexpr uint32_t layout = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);   // SW128 / SW64 / SW32
       constexpr uint32_t sbo_a = HW * rowb, sbo_b = 8 * rowb;
       constexpr int ksteps = KC >> 4;
@@ -184,7 +188,13 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
       for (int tap = 0; tap < 9; ++tap) boff[tap] = (uint32_t)(((P.flip ? 8 - tap : tap) * nkc * N * rowb) >> 4);
       int acc = 0, buf = 0;
       uint32_t tpar = 0, apar = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int nissue = P.nissue;
+      auto skip_tile = [&]() {   // advance the ring positions over a tile that the other issuer handles
+        for (int kc = 0; kc < nkc; ++kc) { if (++buf == P.nbuf) { buf = 0; apar ^= 1; } }
+        if (++acc == NACC) { acc = 0; tpar ^= 1; }
+      };
+      for (int i = 0; i < iss; ++i) skip_tile();
+      for (int tile = blockIdx.x + iss * gridDim.x; tile < P.total_tiles; tile += nissue * gridDim.x) {
         mbar_wait(&tempty[acc], tpar ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
@@ -208,6 +218,7 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         }
         umma_commit(&tfull[acc]);
         if (++acc == NACC) { acc = 0; tpar ^= 1; }
+        for (int i = 1; i < nissue; ++i) skip_tile();
       }
     }
   } else if (warp >= 4) {  // ================= epilogue (8 warps) =================
@@ -450,6 +461,13 @@ static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, in
   P.res = (const bf16*)res;
   P.res_sn = (long long)oh * ow * ldres; P.res_sh = (long long)ow * ldres; P.res_sw = ldres;
   P.idesc = make_idesc_bf16(128, N, 0, 0);
+  {
+    // two MMA issuers for the small layers (issue / accumulate-dependency bound); one for the MMA-throughput-bound N = 128
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("MPGAN_HALO_ISSUERS"); forced = e ? atoi(e) : 0; }
+    P.nissue = (N == 16 && C == 16) ? 2 : 1;   // measured: 16->16 @128^2 17.2 -> 13.6 us; 32 / 64 channels: no gain
+    if (forced == 1 || forced == 2) P.nissue = forced;
+  }
   CUtensorMap mA;
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)iw, (uint64_t)ih, (uint64_t)n};

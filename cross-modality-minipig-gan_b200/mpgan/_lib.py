@@ -76,6 +76,11 @@ _SIGS = {
     "mpgan_c1_tail_bwd_reduce": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mpgan_im2col_c1": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "mpgan_fold_dw16": (c_int, [_P, c_int32, _P, _P]),
+    "mpgan_im2col_c1_vol": (c_int, [_P, c_int32, POINTER(c_int32), POINTER(c_int32), c_int32, c_int32, _P, _P]),
+    "mpgan_col2im_c1_vol": (c_int, [_P, c_int32, POINTER(c_int32), POINTER(c_int32), c_int32, c_int32, _P, _P, _P, _P]),
+    "mpgan_fold_dw32": (c_int, [_P, c_int32, _P, _P]),
+    "mpgan_stencil27": (c_int, [c_int, c_int, _P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
+    "mpgan_stencil27_wgrad": (c_int, [c_int, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
     "mpgan_order_stats_workspace": (c_size_t, [c_int32]),
     "mpgan_order_stats": (c_int, [_P, c_int64, _P, c_int32, _P, _P, c_size_t, _P]),
     "mpgan_minmax": (c_int, [_P, c_int64, _P, c_int32, _P, _P, c_size_t, _P]),

@@ -93,6 +93,26 @@ class ConvSpec:
         return g
 
 
+_C1VOL = os.environ.get("MPGAN_NO_C1VOL", "0") != "1"
+_SPEC_1X1X1 = {}
+
+
+def _spec_1x1x1(cx, cy):
+    if (cx, cy) not in _SPEC_1X1X1:
+        _SPEC_1X1X1[(cx, cy)] = ConvSpec(3, cx, cy, 1, 1, 0)
+    return _SPEC_1X1X1[(cx, cy)]
+
+
+def _vol_c1(spec):
+    """Rank-3 3x3x3 layer with ONE X-grid channel (csrc/conv_c1vol.cu)."""
+    return (_C1VOL and spec.rank == 3 and spec.cx == 1 and spec.k == (3, 3, 3) and spec.stride[0] in (1, 2)
+            and spec.pad[0] in (0, 1))
+
+
+def _i3(v):
+    return (ctypes.c_int32 * 3)(*v)
+
+
 def tc_supported(geom, direction):
     return bool(_lib.load().mpgan_tc_supported(ctypes.byref(geom), direction))
 
@@ -110,6 +130,22 @@ def conv_fprop(spec, x, w, bias, out=None, stats=None, use_tc=True, use_c1=True)
         out = torch.empty((n,) + ys + (spec.cy,), dtype=x.dtype, device=x.device)
     check_act(out, "conv output")
     g = spec.geom(n, xs, ys)
+    if use_c1 and _vol_c1(spec) and x.is_contiguous():
+        if spec.cy == 1 and spec.stride[0] == 1 and spec.pad[0] == 1 and out.is_contiguous():
+            check(lib.mpgan_stencil27(dt(x), 0, ptr(x), n, xs[0], xs[1], xs[2], ptr(w), ptr(bias), None, ptr(out), _stream()),
+                  "stencil27")
+            return out, False
+        if use_tc and x.dtype == torch.bfloat16 and spec.cy % 16 == 0 and spec.cy <= 512:
+            # one input channel: im2col (27 taps -> 32 "channels") + the tcgen05 1x1x1 convolution (fused statistics)
+            xcol = torch.empty((n,) + ys + (32,), dtype=torch.bfloat16, device=x.device)
+            check(lib.mpgan_im2col_c1_vol(ptr(x), n, _i3(xs), _i3(ys), spec.stride[0], spec.pad[0], ptr(xcol), _stream()),
+                  "im2col_c1_vol")
+            w32 = torch.zeros((spec.cy, 32), dtype=torch.bfloat16, device=x.device)
+            w32[:, :27].copy_(w.reshape(spec.cy, 27))
+            g1 = _spec_1x1x1(32, spec.cy).geom(n, ys, ys)
+            check(lib.mpgan_tc_conv_fprop(ctypes.byref(g1), ptr(xcol), 32, ptr(w32), ptr(bias), ptr(out), ld(out), ptr(stats),
+                                          _stream()), "tc_conv_fprop(im2col vol)")
+            return out, stats is not None
     if use_tc and x.dtype == torch.bfloat16 and tc_supported(g, 0):
         check(lib.mpgan_tc_conv_fprop(ctypes.byref(g), ptr(x), ld(x), ptr(w), ptr(bias), ptr(out), ld(out), ptr(stats),
                                       _stream()), "tc_conv_fprop")
@@ -165,6 +201,24 @@ def conv_bprop(spec, y, w, wt, bias, xs=None, out=None, stats=None, use_tc=True,
         out = torch.empty((n,) + tuple(xs) + (spec.cx,), dtype=y.dtype, device=y.device)
     check_act(out, "conv output")
     g = spec.geom(n, xs, ys)
+    if use_c1 and _vol_c1(spec) and out.is_contiguous() and w is not None and (res is None or (res.is_contiguous() and res.dtype == out.dtype)):
+        if (spec.cy == 1 and spec.stride[0] == 1 and spec.pad[0] == 1 and y.is_contiguous() and tuple(xs) == ys
+                and w.dtype == y.dtype):
+            check(lib.mpgan_stencil27(dt(y), 1, ptr(y), n, ys[0], ys[1], ys[2], ptr(w), ptr(bias), ptr(res), ptr(out), _stream()),
+                  "stencil27")
+            return out, False
+        if (use_tc and y.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and spec.cy % 16 == 0 and ld(y) % 8 == 0
+                and y.data_ptr() % 16 == 0):
+            # one output channel: per-tap partial products through the tcgen05 1x1x1 convolution, then a 27-point gather
+            wt32 = torch.zeros((32, spec.cy), dtype=torch.bfloat16, device=y.device)
+            wt32[:27].copy_(w.reshape(spec.cy, 27).t())
+            part = torch.empty((n,) + ys + (32,), dtype=torch.bfloat16, device=y.device)
+            g1 = _spec_1x1x1(spec.cy, 32).geom(n, ys, ys)
+            check(lib.mpgan_tc_conv_fprop(ctypes.byref(g1), ptr(y), ld(y), ptr(wt32), None, ptr(part), 32, None, _stream()),
+                  "tc_conv_fprop(col2im vol)")
+            check(lib.mpgan_col2im_c1_vol(ptr(part), n, _i3(xs), _i3(ys), spec.stride[0], spec.pad[0], ptr(bias), ptr(res),
+                                          ptr(out), _stream()), "col2im_c1_vol")
+            return out, False
     if (use_tc and use_c1 and w is not None and w.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and spec.rank == 2 and spec.cx == 1
             and spec.k == (3, 3) and spec.stride == (1, 1) and spec.cy in (16, 32, 64, 128) and stats is None
             and bias is None and ld(y) % 8 == 0 and (res is None or res.dtype == torch.bfloat16) and _C1OUT
@@ -225,6 +279,22 @@ def conv_wgrad(spec, x, y, dw, use_tc=True, use_c1=True, force_c1col=False):
     n, xs, ys = x.shape[0], tuple(x.shape[1:-1]), tuple(y.shape[1:-1])
     g = spec.geom(n, xs, ys)
     assert dw.dtype == torch.float32
+    if use_c1 and _vol_c1(spec) and x.is_contiguous():
+        if spec.cy == 1 and spec.stride[0] == 1 and spec.pad[0] == 1 and y.is_contiguous() and x.dtype == y.dtype:
+            check(lib.mpgan_stencil27_wgrad(dt(x), ptr(x), ptr(y), n, xs[0], xs[1], xs[2], ptr(dw), None, _stream()),
+                  "stencil27_wgrad")
+            return
+        if (use_tc and x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and spec.cy % 16 == 0 and ld(y) % 8 == 0
+                and y.data_ptr() % 16 == 0):
+            xcol = torch.empty((n,) + ys + (32,), dtype=torch.bfloat16, device=x.device)
+            check(lib.mpgan_im2col_c1_vol(ptr(x), n, _i3(xs), _i3(ys), spec.stride[0], spec.pad[0], ptr(xcol), _stream()),
+                  "im2col_c1_vol")
+            dw32 = torch.zeros((spec.cy, 32), dtype=torch.float32, device=x.device)
+            g1 = _spec_1x1x1(32, spec.cy).geom(n, ys, ys)
+            check(lib.mpgan_tc_conv_wgrad(ctypes.byref(g1), ptr(xcol), 32, ptr(y), ld(y), ptr(dw32), None, 0, _stream()),
+                  "tc_conv_wgrad(im2col vol)")
+            check(lib.mpgan_fold_dw32(ptr(dw32), spec.cy, ptr(dw), _stream()), "fold_dw32")
+            return
     if (use_tc and use_c1 and x.dtype == torch.bfloat16 and spec.rank == 2 and spec.cx == 1 and spec.k == (3, 3)
             and spec.cy % 16 == 0 and spec.cy <= 256 and ld(x) == 1 and x.is_contiguous() and _C1COL
             and (force_c1col or n * ys[0] * ys[1] > (1 << 20))):   # measured: a win for D layer 1, not for G's 0.5M-pixel layers

@@ -233,6 +233,27 @@ int mpgan_im2col_c1(const void* x_bf16, int32_t n, int32_t ih, int32_t iw, int32
                     int32_t pad, void* xcol_bf16, void* stream);
 int mpgan_fold_dw16(const float* dw16, int32_t cy, float* dw, void* stream);
 
+/* ---- one-channel layers of the rank-3 networks (conv_c1vol.cu; the reference's literal volumes: GAN_final.py:107
+ * dimensions=3, :167-169 Conv3d(1, 64, 3), MONAI UNet's 1 -> 16 entry convolutions / 32 -> 1 ConvTranspose / 1 -> 1 tail) ----
+ * A 3x3x3 convolution with one input channel == a 1x1x1 convolution over xcol (n, *ys, 32) = the 27 taps of every output
+ * voxel + 5 zeros, which the rank-3 tcgen05 kernels run (mpgan_tc_conv_fprop / _wgrad with cx = 32):
+ * im2col_c1_vol: x (n, *xs3) one channel contiguous bf16 -> xcol (n, *ys3, 32) bf16 (zero padded borders).
+ * col2im_c1_vol: t (n, *ys3, 32) bf16 = per-tap partial products of a data gradient / ConvTranspose (the 1x1x1 convolution
+ *   of the Y-grid tensor with the [32][cy] transposed weights) -> x (n, *xs3) one channel bf16:
+ *   x[q] = bias + res[q] + sum over taps r with (q + pad - r) % stride == 0 of t[(q + pad - r) / stride][r].
+ * fold_dw32: dw[c][27] += dw32[c][32] (first 27 columns of the 1x1x1 weight gradient).
+ * stencil27 / stencil27_wgrad: the 1 -> 1 channel k3 s1 p1 layer as direct 27-point stencils (dtype MPGAN_F32 / MPGAN_BF16;
+ *   direction 0: y = bias + conv(x, w27); 1: dx = conv^T(dy, w27) + res; wgrad: dw27[t] += sum dy * x(shifted), dbias += sum dy). */
+int mpgan_im2col_c1_vol(const void* x_bf16, int32_t n, const int32_t* xs3, const int32_t* ys3, int32_t stride, int32_t pad,
+                        void* xcol_bf16, void* stream);
+int mpgan_col2im_c1_vol(const void* t_bf16, int32_t n, const int32_t* xs3, const int32_t* ys3, int32_t stride, int32_t pad,
+                        const float* bias, const void* res_bf16, void* x_bf16, void* stream);
+int mpgan_fold_dw32(const float* dw32, int32_t cy, float* dw, void* stream);
+int mpgan_stencil27(int dtype, int direction, const void* in, int32_t n, int32_t d, int32_t h, int32_t w, const void* w27,
+                    const float* bias, const void* res, void* out, void* stream);
+int mpgan_stencil27_wgrad(int dtype, const void* x, const void* dy, int32_t n, int32_t d, int32_t h, int32_t w, float* dw27,
+                          float* dbias, void* stream);
+
 /* ---- intensity transforms / volume metrics around the generator ----
  * MONAI ScaleIntensityRangePercentilesd (reference: GAN_final.py:386-394 lower=1 upper=99 -> [-1,1];
  * inferrence.py:152-160,190-198 lower=0 upper=100 -> [0,255] followed by np.round) and torchmetrics

@@ -359,6 +359,48 @@ def test_tc3_conv_wgrad(case):
     assert rel_l2(dw, 2 * oti(ref)) <= 2e-3
 
 
+TC3_C1_CASES = [
+    # n, cout, (d, h, w), s, p  -- rank-3 layers with ONE input channel (conv_c1vol.cu)
+    (2, 64, (10, 9, 11), 1, 0),      # D layer 1 at 3-D: Conv3d(1, 64, 3), valid padding (GAN_final.py:167-169)
+    (2, 16, (12, 12, 12), 2, 1),     # UNet entry convolution 1 -> 16, stride 2
+    (1, 32, (8, 10, 6), 2, 1),       # geometry of ConvTranspose3d(32 -> 1) (its forward = this layer's data gradient)
+    (2, 16, (7, 7, 7), 1, 1),
+    (3, 1, (9, 8, 10), 1, 1),        # UNet tail 1 -> 1: direct 27-point stencils
+]
+
+
+@pytest.mark.parametrize("case", TC3_C1_CASES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_tc3_one_channel_layers(case, dtype):
+    n, cout, sp, s, p = case
+    if dtype == torch.float32 and cout != 1:
+        pytest.skip("fp32 mode keeps the generic kernels for these layers (covered by test_conv_generic_fwd_dgrad_wgrad)")
+    x = rnd(n, 1, *sp, seed=61).to(dtype).float().requires_grad_(True)
+    w = (rnd(cout, 1, 3, 3, 3, seed=62) * 0.2).to(dtype).float().requires_grad_(True)
+    b = rnd(cout, seed=63)
+    y = F.conv3d(x, w, b, stride=s, padding=p)
+    dy = rnd(*y.shape, seed=64).to(dtype).float()
+    y.backward(dy)
+    osp = tuple(y.shape[2:])
+    spec = ops.ConvSpec(3, 1, cout, 3, s, p)
+    tol = 6e-3 if dtype == torch.bfloat16 else 1e-5
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV) if cout > 1 else None
+    calls0 = ops._lib.ABI_CALLS
+    yk, fused = ops.conv_fprop(spec, cl(x.detach(), dtype), oti(w.detach(), dtype), b, stats=stats)
+    assert ops._lib.ABI_CALLS - calls0 == (1 if cout == 1 else 2), "the one-channel volume path was not taken"
+    assert rel_l2(uncl(yk), y) <= tol
+    if cout > 1:
+        assert fused
+        ykd = yk.double().reshape(-1, cout)
+        assert rel_l2(stats[:cout], ykd.sum(0)) <= 1e-4 and rel_l2(stats[cout:], (ykd * ykd).sum(0)) <= 1e-4
+    res = rnd(n, *sp, 1, seed=65).to(dtype)
+    dxk, _ = ops.conv_bprop(spec, cl(dy, dtype), oti(w.detach(), dtype), None, None, xs=sp, res=res)
+    assert rel_l2(uncl(dxk), x.grad + uncl(res)) <= tol
+    dw = torch.ones(cout, 27, 1, device=DEV)                       # accumulates onto existing content
+    ops.conv_wgrad(spec, cl(x.detach(), dtype), cl(dy, dtype), dw)
+    assert rel_l2(dw - 1.0, oti(w.grad)) <= (6e-3 if dtype == torch.bfloat16 else 1e-4)
+
+
 def test_tc3_inference_fused_layer():
     """Eval-mode fused layer (folded BatchNorm bias + PReLU + residual in the epilogue) on the rank-3 path."""
     n, cin, cout, sp = 2, 32, 32, (6, 7, 8)

@@ -68,10 +68,13 @@ def conv_case(name, cin, cout, k, s, p, xs, transposed=False, dirs=("f", "b", "w
     stats = None if os.environ.get("NOSTATS") else torch.zeros(2 * max(cin, cout), dtype=torch.float64, device=DEV)
     flops = 2.0 * n * ys ** rank * cout * k ** rank * cin
     nb = (x.numel() + y.numel()) * 2
+    # BatchNorm statistics are fused only where the training step fuses them: in the layer's FORWARD direction (fprop of a
+    # convolution, bprop of a ConvTranspose); the data gradients run without (round 1's table timed them with)
+    sf, sb = (None, stats) if transposed else (stats, None)
     if "f" in dirs:
-        report(f"{name} fprop {cin}->{cout} k{k}s{s} @{xs}", timeit(lambda: ops.conv_fprop(spec, x, w, None, out=y, stats=stats)), nb, flops)
+        report(f"{name} fprop {cin}->{cout} k{k}s{s} @{xs}", timeit(lambda: ops.conv_fprop(spec, x, w, None, out=y, stats=sf)), nb, flops)
     if "b" in dirs:
-        report(f"{name} bprop {cout}->{cin} k{k}s{s} @{ys}", timeit(lambda: ops.conv_bprop(spec, y, w, wt, None, xs=(xs,) * rank, out=x, stats=stats)), nb, flops)
+        report(f"{name} bprop {cout}->{cin} k{k}s{s} @{ys}", timeit(lambda: ops.conv_bprop(spec, y, w, wt, None, xs=(xs,) * rank, out=x, stats=sb)), nb, flops)
     if "w" in dirs:
         report(f"{name} wgrad {cin}x{cout} k{k}s{s} @{xs}", timeit(lambda: ops.conv_wgrad(spec, x, y, dw)), nb, flops)
 
