@@ -72,6 +72,7 @@ struct WgradParams {
   int taps_per_group, ngroups, m_blocks, splits;
   int tiles_w, tiles_h, tiles_d, tiles_n, tw_log2, th_log2, td_log2;
   int cx, cy;
+  int cx_blocks;       // X-channel blocks of NX columns each (cx = cx_blocks * NX; > 1 only for NX = 256)
   int nprod;           // TMA producer warps (1..7)
   float* dw;
 };
@@ -203,10 +204,13 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < Epi::EW * 2 * P.n_total; i += blockDim.x) s_stats[i] = 0.f;
+  // (layers wider than 512 output channels -- the patch discriminator's Linear as a 1x1 convolution -- carry neither a
+  //  bias nor statistics: the 512 bias slots are then all zero and indexed modulo 512)
+  const int n_slots = P.n_total < 512 ? P.n_total : 512;
+  if (P.stats) for (int i = threadIdx.x; i < Epi::EW * 2 * P.n_total; i += blockDim.x) s_stats[i] = 0.f;
   pdl_wait();      // PDL: barrier init / TMEM allocation / descriptor prefetch above overlap the previous kernel
   pdl_launch();
-  for (int i = threadIdx.x; i < P.n_total; i += blockDim.x) s_bias[i] = P.bias ? __ldg(&P.bias[i]) : 0.f;
+  for (int i = threadIdx.x; i < n_slots; i += blockDim.x) s_bias[i] = P.bias ? __ldg(&P.bias[i]) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -389,7 +393,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         const bf16* rrow = P.res ? P.res + P.cls_res_off[cls] + (long long)img * P.res_sn + (long long)oh * P.res_sh +
                                        (long long)ow * P.res_sw + (R3 ? (long long)od * P.res_sd : 0LL) + nbase + c0
                                  : nullptr;
-        epi_chunk_store<CH>(r, s_bias + nbase + c0, orow, valid, P.stats != nullptr, s1, s2, rrow, P.wide != 0, P.slope);
+        epi_chunk_store<CH>(r, s_bias + ((nbase + c0) & 511), orow, valid, P.stats != nullptr, s1, s2, rrow, P.wide != 0, P.slope);
       }
       if (P.stats && stat_base >= 0) flush();
     } else {
@@ -420,7 +424,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams P, const __grid_constant__ 
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + s_bias[nbase + c0 + j];
+        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + s_bias[((nbase + c0) & 511) + j];
         if (P.slope) {
           const float a = __ldg(P.slope);
 #pragma unroll
@@ -573,6 +577,7 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
   int b = blockIdx.x;
   const int mb = b % P.m_blocks; b /= P.m_blocks;
   const int grp = b % P.ngroups; b /= P.ngroups;
+  const int cxo = (b % P.cx_blocks) * NX; b /= P.cx_blocks;   // first X channel of this CTA's block
   const int split = b;
   const int tap0 = grp * P.taps_per_group;
   const int ntap = min(P.taps_per_group, P.ntaps - tap0);
@@ -615,7 +620,7 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
             const CUtensorMap* mX = &tmX.m[P.tap_map[tap]];
 #pragma unroll
             for (int i = 0; i < B::BOXES; ++i)
-              load_tile(sB + q * B::BYTES + i * 8192, mX, &full[stage], i * 64, w0 + P.tap_dw[tap], h0 + P.tap_dh[tap],
+              load_tile(sB + q * B::BYTES + i * 8192, mX, &full[stage], cxo + i * 64, w0 + P.tap_dw[tap], h0 + P.tap_dh[tap],
                         d0 + P.tap_dd[tap], n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -653,7 +658,7 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
               const int q = (it - 2) / B::BOXES, i = (it - 2) % B::BOXES;
               const int tap = tap0 + tl0 + q;
               const CUtensorMap* mX = &tmX.m[P.tap_map[tap]];
-              load_tile(sB + q * B::BYTES + i * 8192, mX, &full[stage], i * 64, w0 + P.tap_dw[tap], h0 + P.tap_dh[tap],
+              load_tile(sB + q * B::BYTES + i * 8192, mX, &full[stage], cxo + i * 64, w0 + P.tap_dw[tap], h0 + P.tap_dh[tap],
                         d0 + P.tap_dd[tap], n0);
             }
           }
@@ -704,7 +709,7 @@ wgrad_kernel(const __grid_constant__ WgradParams P, const __grid_constant__ CUte
     tc_fence_after();
     for (int tl = 0; tl < ntap; ++tl) {
       const int tap = tap0 + tl;
-      float* drow = P.dw + ((long long)m * P.ntaps + tap) * P.cx;
+      float* drow = P.dw + ((long long)m * P.ntaps + tap) * P.cx + cxo;
       constexpr int CH = NX >= 32 ? 32 : 16;
 #pragma unroll 1
       for (int c0 = 0; c0 < NX; c0 += CH) {
@@ -955,7 +960,7 @@ static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, con
   P.slope = slope;
   P.res = (const bf16*)res;
   MPGAN_REQUIRE(!res || (ldres % 8 == 0 && ((uintptr_t)res & 15) == 0), MPGAN_ERR_SHAPE, "residual tensor misaligned");
-  MPGAN_REQUIRE(N <= 512, MPGAN_ERR_UNSUPPORTED, "N > 512");
+  MPGAN_REQUIRE(N <= 512 || (!bias && !stats), MPGAN_ERR_UNSUPPORTED, "N > 512 is supported without bias / statistics only");
 
   const int sd = r3 ? g.s : 1;            // stride along depth (rank 2: a single depth slice)
   int ntap = 0;
@@ -1060,7 +1065,7 @@ static int launch_wgrad_t(const WgradParams& P, const CUtensorMap& mY, const Act
     MPGAN_REQUIRE(e == cudaSuccess, MPGAN_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  int grid = P.m_blocks * P.ngroups * P.splits;
+  int grid = P.m_blocks * P.ngroups * P.cx_blocks * P.splits;
   launch_k(wgrad_kernel<NX, SMALL, R3>, grid, 256, Cfg::SMEM_BYTES, s, P, mY, mX);
   MPGAN_CHECK_LAUNCH("wgrad_kernel");
   return 0;
@@ -1078,14 +1083,16 @@ static int dispatch_wgrad(int cx, bool small, const WgradParams& P, const CUtens
 }
 
 static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, int64_t ldy, float* dw, cudaStream_t s) {
-  MPGAN_REQUIRE(g.cx == 16 || g.cx == 32 || g.cx == 64 || g.cx == 128 || g.cx == 256, MPGAN_ERR_UNSUPPORTED,
-                "tc wgrad needs cx in {16,32,64,128,256}");
+  MPGAN_REQUIRE(g.cx == 16 || g.cx == 32 || g.cx == 64 || g.cx == 128 || (g.cx >= 256 && g.cx % 256 == 0), MPGAN_ERR_UNSUPPORTED,
+                "tc wgrad needs cx in {16,32,64,128} or a multiple of 256");
   MPGAN_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, MPGAN_ERR_SHAPE, "pixel strides must be multiples of 8 elements");
   const bool r3 = g.rank == 3;
   const int sd = r3 ? g.s : 1;
   WgradParams P;
   memset(&P, 0, sizeof(P));
   P.cx = g.cx; P.cy = g.cy; P.dw = dw;
+  const int nx = g.cx > 256 ? 256 : g.cx;       // X channels per CTA
+  P.cx_blocks = g.cx / nx;
   {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("MPGAN_WG_NPROD"); forced = e ? atoi(e) : 0; }
@@ -1109,7 +1116,7 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
   // "small" = generator-sized layer (<= 1M output pixels): half of TMEM / ~100 KB of shared memory per CTA so that a
   // CTA of the concurrent data-gradient chain fits on the same SM; large layers (D) take the whole SM
   const bool small = g.cx <= 64 && (long long)g.n * g.yd * g.yh * g.yw <= (1LL << 20);
-  const int max_tpg = (small ? 256 : 512) / g.cx;
+  const int max_tpg = (small ? 256 : 512) / nx;
   P.ngroups = (ntap + max_tpg - 1) / max_tpg;
   P.taps_per_group = (ntap + P.ngroups - 1) / P.ngroups;   // balanced groups
   P.m_blocks = (g.cy + 127) / 128;
@@ -1118,7 +1125,7 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
   P.tiles_w = (g.yw + tw - 1) / tw; P.tiles_h = (g.yh + th - 1) / th; P.tiles_d = (g.yd + td - 1) / td;
   P.tiles_n = (g.n + tn - 1) / tn;
   const int ptiles = P.tiles_w * P.tiles_h * P.tiles_d * P.tiles_n;
-  const int items = P.m_blocks * P.ngroups;
+  const int items = P.m_blocks * P.ngroups * P.cx_blocks;
   // one CTA per SM for the large-channel configurations (~200 KB of shared memory each): the grid must not exceed the
   // SM count or the few extra CTAs run as a second wave and double the kernel time (152 CTAs did, on 148 SMs)
   int splits = !small ? num_sms() / items : (num_sms() + items - 1) / items;
@@ -1144,7 +1151,7 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
   uint32_t boxX[5] = {(uint32_t)(g.cx < 64 ? g.cx : 64), (uint32_t)tw, (uint32_t)th, (uint32_t)(r3 ? td : tn), (uint32_t)tn};
   int rc = make_act_maps(&mX, x, r3, g.n, g.xd, g.xh, g.xw, g.cx, ldx, g.s, boxX);
   if (rc) return rc;
-  return r3 ? dispatch_wgrad<true>(g.cx, small, P, mY, mX, s) : dispatch_wgrad<false>(g.cx, small, P, mY, mX, s);
+  return r3 ? dispatch_wgrad<true>(nx, small, P, mY, mX, s) : dispatch_wgrad<false>(nx, small, P, mY, mX, s);
 }
 
 }  // namespace tc
@@ -1156,9 +1163,9 @@ using namespace mpgan::tc;
 extern "C" int mpgan_tc_supported(const MpganConvGeom* g, int direction) {
   Geom2 g2;
   if (to_geom2(g, &g2) != 0) return 0;
-  if (direction == 2) return (g2.cx == 16 || g2.cx == 32 || g2.cx == 64 || g2.cx == 128 || g2.cx == 256) ? 1 : 0;
+  if (direction == 2) return (g2.cx == 16 || g2.cx == 32 || g2.cx == 64 || g2.cx == 128 || (g2.cx >= 256 && g2.cx % 256 == 0)) ? 1 : 0;
   const int N = direction == 0 ? g2.cy : g2.cx;
-  if (pick_bn(N) == 0 || N > 512) return 0;
+  if (pick_bn(N) == 0 || N > 512) return 0;   // (wider layers run without bias / statistics only: callers ask explicitly)
   if (direction == 1 && g2.s == 2 && (g2.kh < 2 || g2.kw < 2 || (g2.rank == 3 && g2.kd < 2))) return 0;
   return 1;
 }

@@ -664,9 +664,13 @@ class _ConvBnLeakyStack(_PlanNet):
                                           c_last, spatial, True)
             else:
                 wcl = lin.weight.detach()
-            z = torch.zeros((n, j), dtype=torch.float32, device=x.device)
-            ops.linear_fwd(z_in, wcl, lin.bias.detach(), z)
-            lin_tape.append((z_in, wcl, first))
+            use_gemm = first and ops.linear_tc_ok(z_in, j, k)
+            if use_gemm:   # a real GEMM (patch discriminator: 4 096 patches x 32 768 -> 64): tcgen05, not the split-K GEMV
+                z = ops.linear_tc_fwd(z_in, wcl, lin.bias.detach())
+            else:
+                z = torch.zeros((n, j), dtype=torch.float32, device=x.device)
+                ops.linear_fwd(z_in, wcl, lin.bias.detach(), z)
+            lin_tape.append((z_in, wcl, first, use_gemm))
             if want_acts:
                 acts.append(("raw", z))
             z_in, first = z, False
@@ -714,12 +718,17 @@ class _ConvBnLeakyStack(_PlanNet):
         dfeat = None
         for li in range(len(linears) - 1, -1, -1):
             lin = linears[li]
-            z_in, wcl, first = lin_tape[li]
+            z_in, wcl, first, use_gemm = lin_tape[li]
             if (3 * n_conv + 1 + li) in ag:
                 dz = dz + ag[3 * n_conv + 1 + li].reshape(dz.shape)
             j, k = lin.weight.shape
             dx = torch.empty_like(z_in)
-            if plan.need_wgrad:
+            if use_gemm:
+                dwcl = torch.zeros((j, k), dtype=torch.float32, device=dz.device) if plan.need_wgrad else None
+                ops.linear_tc_bwd(z_in, wcl, dz, dx, dwcl, lin.bias.grad if plan.need_wgrad else None)
+                if plan.need_wgrad:
+                    ops.permute_flatten(dwcl, lin.weight.grad, j, feat_shape[-1], k // feat_shape[-1], False, True)
+            elif plan.need_wgrad:
                 if first:
                     dwcl = torch.zeros((j, k), dtype=torch.float32, device=dz.device)
                     ops.linear_bwd(z_in, wcl, dz, dx, dwcl, lin.bias.grad)

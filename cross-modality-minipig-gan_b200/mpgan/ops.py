@@ -493,6 +493,48 @@ def linear_bwd(x, w, dy, dx, dw, db):
                                _stream()), "linear_bwd")
 
 
+_LINEAR_TC = os.environ.get("MPGAN_NO_LINEAR_TC", "0") != "1"
+
+
+def linear_tc_ok(x, j, k):
+    """A Linear layer that is a real GEMM (the patch discriminator's Linear(512 * 8^d, 64) over 4 096 patches,
+    test_runs/GAN.py:176-181) runs on the tcgen05 kernels as a 1x1 convolution over a (1, B / 16, 16, K) "image"."""
+    b = x.shape[0]
+    return (_LINEAR_TC and x.dtype == torch.bfloat16 and x.is_contiguous() and b % 16 == 0 and b >= 256 and j % 16 == 0
+            and 16 <= j <= 512 and k % 256 == 0)
+
+
+def _gemm_geom(cin, cout, b):
+    return ConvSpec(2, cin, cout, 1, 1, 0).geom(1, (b // 16, 16), (b // 16, 16))
+
+
+def linear_tc_fwd(x, w, bias):
+    """z (B, J) fp32 = x (B, K) bf16 . w (J, K)^T bf16 + bias, fp32 accumulation in TMEM."""
+    lib = _lib.require_device()
+    b, k = x.shape
+    j = w.shape[0]
+    z16 = torch.empty((b, j), dtype=torch.bfloat16, device=x.device)
+    g = _gemm_geom(k, j, b)
+    check(lib.mpgan_tc_conv_fprop(ctypes.byref(g), ptr(x), k, ptr(w), ptr(bias), ptr(z16), j, None, _stream()), "linear_tc_fwd")
+    return cast(z16, torch.empty((b, j), dtype=torch.float32, device=x.device))
+
+
+def linear_tc_bwd(x, w, dz, dx, dw, db):
+    """dx (B, K) bf16 = dz . w;  dw (J, K) fp32 += dz^T . x;  db (J) += column sums of dz.  dz (B, J) fp32."""
+    lib = _lib.require_device()
+    b, k = x.shape
+    j = w.shape[0]
+    dz16 = cast(dz.contiguous(), torch.empty((b, j), dtype=torch.bfloat16, device=x.device))
+    wt = weight_transpose(w, torch.empty(j * k, dtype=torch.bfloat16, device=x.device), j, 1, k)      # [K][J]
+    g = _gemm_geom(j, k, b)
+    check(lib.mpgan_tc_conv_fprop(ctypes.byref(g), ptr(dz16), j, ptr(wt), None, ptr(dx), k, None, _stream()), "linear_tc_dx")
+    if dw is not None:
+        g2 = _gemm_geom(k, j, b)
+        check(lib.mpgan_tc_conv_wgrad(ctypes.byref(g2), ptr(x), k, ptr(dz16), j, ptr(dw), None, 0, _stream()), "linear_tc_dw")
+    if db is not None:
+        colsum(dz16, db)
+
+
 def sigmoid_fwd(z, p):
     lib = _lib.require_device()
     check(lib.mpgan_sigmoid_fwd(ptr(z), ptr(p), z.numel(), _stream()), "sigmoid_fwd")

@@ -413,6 +413,29 @@ def test_tc3_inference_fused_layer():
     assert y is not None and rel_l2(uncl(y), ref) <= 6e-3
 
 
+@pytest.mark.parametrize("b,k,j", [(256, 512, 64), (4096, 32768, 64), (512, 2048, 16), (1024, 1024, 128)])
+def test_linear_as_tcgen05_gemm(b, k, j):
+    """nn.Linear that is a real GEMM (patch discriminator: Linear(512 * 8 * 8, 64) over 4 096 patches,
+    test_runs/GAN.py:176-181): forward, data gradient (N = K > 512 output columns, no bias), weight gradient (blocks of 256
+    X channels) and bias gradient on the tcgen05 kernels against torch fp32 on the same bf16-rounded operands."""
+    assert ops.linear_tc_ok(torch.empty((b, k), dtype=torch.bfloat16, device=DEV), j, k)
+    x = rnd(b, k, seed=71).bfloat16()
+    w = (rnd(j, k, seed=72) * (1.0 / k ** 0.5)).bfloat16()
+    bias = rnd(j, seed=73)
+    z = ops.linear_tc_fwd(x, w, bias)
+    ref = x.float() @ w.float().t() + bias
+    assert z.dtype == torch.float32 and rel_l2(z, ref) <= 4e-3           # (bf16 rounding of the stored result)
+    dz = rnd(b, j, seed=74, ).float()
+    dx = torch.empty_like(x)
+    dw = torch.ones(j, k, device=DEV)
+    db = torch.ones(j, device=DEV)
+    ops.linear_tc_bwd(x, w, dz, dx, dw, db)
+    dzr = dz.bfloat16().float()
+    assert rel_l2(dx, dzr @ w.float()) <= 4e-3
+    assert rel_l2(dw - 1.0, dzr.t() @ x.float()) <= 2e-3
+    assert rel_l2(db - 1.0, dzr.sum(0)) <= 1e-3
+
+
 def test_tc_conv_full_size_linearity():
     """BASELINE-size D layer 3 (32 x 252^2 x 128 -> 125^2 x 256): checked through linearity and a sampled window."""
     n, cin, cout, h = 8, 128, 256, 252
