@@ -65,6 +65,7 @@ _SIGS = {
     "mpgan_bce_bwd": (c_int, [_P, _P, c_float, _P, _P, c_int32, _P]),
     "mpgan_l1_fwd": (c_int, [c_int, _P, _P, c_int64, c_float, _P, _P]),
     "mpgan_l1_bwd": (c_int, [c_int, _P, _P, c_int64, c_float, _P, _P, c_int, _P]),
+    "mpgan_l1_fwd_bwd": (c_int, [c_int, _P, _P, c_int64, c_float, _P, _P, _P, _P, c_int, _P]),
     "mpgan_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, _P, _P]),
     "mpgan_cast": (c_int, [c_int, _P, c_int, _P, c_int64, _P]),
     "mpgan_weight_transpose": (c_int, [c_int, _P, c_int, _P, c_int32, c_int32, c_int32, _P]),

@@ -444,15 +444,16 @@ class GAN(_Base):
         _, plan_r = D.run_forward(real_p, save=False, need_wgrad=False, want_acts=True, logical_acts=False)
         acts_f, acts_r = plan_f.extra["acts_raw"], plan_r.extra["acts_raw"]
         dacts = {}
+        perc64 = torch.zeros(1, dtype=torch.float64, device=dev)   # the 16 terms span 4 decades: summed in fp64
         for k, (af, ar) in enumerate(zip(acts_f, acts_r)):   # sum_k l1_loss(y[k], y_hat[k]) / numel_k
-            af, ar = af.contiguous(), ar.contiguous()
-            w = 1.0 / af.numel()
-            ops.l1_fwd(ar, af, w, logs[2:3])
-            dacts[k] = ops.l1_bwd(af, ar, w, None, torch.empty_like(af), False)
+            # neither the loss terms nor their gradients are materialised here: the discriminator's backward accumulates
+            # each gradient into its own tensor (and the loss term into perc64) with ONE pass over the activation pair
+            dacts[k] = ops.LazyL1(af.contiguous(), ar.contiguous(), 1.0 / af.numel(), perc64)
         ops.bce_fwd(out_f, ones, 1.0, logs[0:1])
         ops.l1_fwd(fake_p, real_p, 1.0, logs[1:2])
         dprob = ops.bce_bwd(out_f, ones, 1.0, None, torch.empty_like(out_f))
         dfake = D.run_backward(plan_f, dprob, need_dx=True, act_grads=dacts, internal=True)
+        logs[2:3].copy_(perc64)
         dfake = dfake.contiguous()
         ops.l1_bwd(fake_p, real_p, 1.0, None, dfake.reshape(patch_shape), True)
         dgen = torch.zeros((n,) + sp + (1,), dtype=torch.float32, device=dev)

@@ -711,16 +711,25 @@ class _ConvBnLeakyStack(_PlanNet):
         linears = [m for m in self.model_linear if isinstance(m, nn.Linear)]
         n_conv = 4
         ag = dict(act_grads or {})
+
+        def dense(g):      # small (linear / probability) activations: a lazily defined L1 gradient is materialised
+            return g.materialize() if isinstance(g, ops.LazyL1) else g
+
+        def inject(target, g):   # target += gradient injected at an activation, in the activation's own layout
+            if isinstance(g, ops.LazyL1):
+                return g.add_to(target)
+            return ops.add_copy(target, g, target)
+
         dp = dprob.detach().float().contiguous().reshape(p.shape)
         if 3 * n_conv + 1 + len(linears) in ag:
-            dp = dp + ag[3 * n_conv + 1 + len(linears)].reshape(p.shape)
+            dp = dp + dense(ag[3 * n_conv + 1 + len(linears)]).reshape(p.shape)
         dz = ops.sigmoid_bwd(dp, p, torch.empty_like(p))
         dfeat = None
         for li in range(len(linears) - 1, -1, -1):
             lin = linears[li]
             z_in, wcl, first, use_gemm = lin_tape[li]
             if (3 * n_conv + 1 + li) in ag:
-                dz = dz + ag[3 * n_conv + 1 + li].reshape(dz.shape)
+                dz = dz + dense(ag[3 * n_conv + 1 + li]).reshape(dz.shape)
             j, k = lin.weight.shape
             dx = torch.empty_like(z_in)
             if use_gemm:
@@ -740,8 +749,8 @@ class _ConvBnLeakyStack(_PlanNet):
             dz = dx
         dfeat = dz  # (N, prod(feat)) in the compute dtype, channels-last order
         if 3 * n_conv in ag and internal:
-            dfeat = ops.add_copy(dfeat.reshape(feat_shape), ag[3 * n_conv].reshape(feat_shape),
-                                 dfeat.reshape(feat_shape)).reshape(dfeat.shape)
+            g = ag[3 * n_conv]
+            dfeat = inject(dfeat.reshape(feat_shape), g if isinstance(g, ops.LazyL1) else g.reshape(feat_shape)).reshape(dfeat.shape)
         elif 3 * n_conv in ag:  # gradient w.r.t. the Flatten output (NCHW order)
             g = ag[3 * n_conv].reshape((feat_shape[0], feat_shape[-1]) + tuple(feat_shape[1:-1]))
             nd = self.dims
@@ -756,8 +765,7 @@ class _ConvBnLeakyStack(_PlanNet):
             h_in, c, saved, trained, bn_out = plan.tape.pop()
             if (3 * i + 2) in ag:
                 if internal:
-                    dh = dh.contiguous()
-                    dh = ops.add_copy(dh, ag[3 * i + 2], dh)
+                    dh = inject(dh.contiguous(), ag[3 * i + 2])
                 else:
                     dh = dh + ag[3 * i + 2].permute(to_cl).to(dh.dtype)
             if bn_out is not None:
@@ -765,7 +773,7 @@ class _ConvBnLeakyStack(_PlanNet):
                 # at the BN output, then the BatchNorm backward proper
                 dbn = ops.act_bwd(dh.contiguous(), bn_out, ACT_LEAKY, 0.2, _new(bn_out, bn_out.shape))
                 if (3 * i + 1) in ag:
-                    dbn = ops.add_copy(dbn, ag[3 * i + 1], dbn) if internal else dbn + ag[3 * i + 1].permute(to_cl).to(dbn.dtype)
+                    dbn = inject(dbn, ag[3 * i + 1]) if internal else dbn + ag[3 * i + 1].permute(to_cl).to(dbn.dtype)
                 dc = bn_act_backward(dbn, c, saved, bns[i], ACT_NONE, None, 0.0, plan, trained)
                 fused_bias = False
             else:
@@ -773,7 +781,7 @@ class _ConvBnLeakyStack(_PlanNet):
                 dc = bn_act_backward(dh, c, saved, bns[i], ACT_LEAKY, None, 0.2, plan, trained,
                                      conv_db=rt.rec[convs[i]].db if fused_bias else None)
             if (3 * i) in ag:
-                dc = ops.add_copy(dc, ag[3 * i], dc) if internal else dc + ag[3 * i].permute(to_cl).to(dc.dtype)
+                dc = inject(dc, ag[3 * i]) if internal else dc + ag[3 * i].permute(to_cl).to(dc.dtype)
             dh = conv_backward(rt.rec[convs[i]], h_in, dc, plan, need_dx=(need_dx or i > 0), bias_done=fused_bias)
             if on_layer_done is not None:
                 forked = plan.wgrad_forked and N_WGRAD_STREAMS == 1

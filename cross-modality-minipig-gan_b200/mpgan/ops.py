@@ -573,6 +573,35 @@ def l1_bwd(a, b, weight, gscale, da, accumulate):
     return da
 
 
+def l1_fwd_bwd(a, b, weight, loss, da, accumulate, gscale=None):
+    """One pass over (a, b): loss += weight * mean|a - b| (loss: fp32 or fp64 one-element device tensor, or None) and
+    da (+)= weight / n * sign(a - b)."""
+    lib = _lib.require_device()
+    assert a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype and a.numel() == b.numel()
+    assert da is None or (da.is_contiguous() and da.dtype == a.dtype and da.numel() == a.numel())
+    l32 = loss if (loss is not None and loss.dtype == torch.float32) else None
+    l64 = loss if (loss is not None and loss.dtype == torch.float64) else None
+    assert loss is None or l32 is not None or l64 is not None
+    check(lib.mpgan_l1_fwd_bwd(dt(a), ptr(a), ptr(b), a.numel(), weight, ptr(gscale), ptr(l32), ptr(l64), ptr(da),
+                               1 if accumulate else 0, _stream()), "l1_fwd_bwd")
+    return da
+
+
+class LazyL1:
+    """Gradient of ``weight * l1_loss(mine, other)`` w.r.t. ``mine`` that has not been materialised: the consumer
+    accumulates it into its own gradient tensor (and the loss into ``loss``) with ONE pass over the pair."""
+
+    def __init__(self, mine, other, weight, loss):
+        self.mine, self.other, self.weight, self.loss = mine, other, weight, loss
+
+    def add_to(self, target):
+        """target += d loss / d mine; the loss term is accumulated by the same kernel."""
+        return l1_fwd_bwd(self.mine, self.other, self.weight, self.loss, target, True)
+
+    def materialize(self):
+        return l1_fwd_bwd(self.mine, self.other, self.weight, self.loss, torch.empty_like(self.mine), False)
+
+
 def adam_step(param, grad, m, v, lr, b1, b2, eps, state, shadow=None):
     lib = _lib.require_device()
     check(lib.mpgan_adam_step(ptr(param), ptr(grad), ptr(m), ptr(v), param.numel(), lr, b1, b2, eps, ptr(state),

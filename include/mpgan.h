@@ -183,6 +183,12 @@ int mpgan_bce_bwd(const float* prob, const float* target, float weight, const fl
 int mpgan_l1_fwd(int dtype, const void* a, const void* b, int64_t n, float weight, float* loss, void* stream);
 int mpgan_l1_bwd(int dtype, const void* a, const void* b, int64_t n, float weight, const float* gscale, void* da,
                  int accumulate, void* stream);
+/* one pass: *loss (fp32) and / or *loss64 (fp64) += weight * mean|a - b| (either may be NULL) and
+ * da (+)= gscale * weight / n * sign(a - b) (da may be NULL; accumulate != 0 adds onto da's contents) -- F.l1_loss forward +
+ * backward fused; the feature-matching loss of test_runs/GAN.py:288-298 accumulates its gradients straight into the
+ * discriminator's backward tensors with it and sums its 16 terms in the fp64 slot. */
+int mpgan_l1_fwd_bwd(int dtype, const void* a, const void* b, int64_t n, float weight, const float* gscale, float* loss,
+                     double* loss64, void* da, int accumulate, void* stream);
 
 /* ---- torch.optim.Adam (GAN_final.py:298-308), one launch over a flat fp32 buffer ----
  * state: 3 device floats {step count (int bits), step_size, sqrt(1-beta2^t)}; zero-initialised by the caller.

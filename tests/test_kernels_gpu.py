@@ -413,6 +413,38 @@ def test_tc3_inference_fused_layer():
     assert y is not None and rel_l2(uncl(y), ref) <= 6e-3
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n", [8 * 1000, 12345])
+def test_l1_forward_backward_in_one_pass(dtype, n):
+    """F.l1_loss forward + backward fused (vector body + scalar tail), plain and accumulating onto an existing gradient."""
+    a, b = rnd(n, seed=81).to(dtype), rnd(n, seed=82).to(dtype)
+    b[:7] = a[:7]                                                    # exact ties: zero sub-gradient like torch
+    ar = a.float().clone().requires_grad_(True)
+    ref = F.l1_loss(ar, b.float()) * 0.37
+    ref.backward()
+    loss = torch.zeros(1, device=DEV)
+    da = ops.l1_fwd_bwd(a, b, 0.37, loss, torch.empty_like(a), False)
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert rel_l2(da, ar.grad) <= (1e-6 if dtype == torch.float32 else 4e-3)
+    base = rnd(n, seed=83).to(dtype)
+    acc = ops.l1_fwd_bwd(a, b, 0.37, None, base.clone(), True)
+    assert rel_l2(acc, base.float() + ar.grad) <= (1e-6 if dtype == torch.float32 else 4e-3)
+    loss64 = torch.full((1,), 1e3, dtype=torch.float64, device=DEV)   # a large running total must not swallow the term
+    ops.l1_fwd_bwd(a, b, 0.37, loss64, None, False)
+    assert abs(float(loss64) - 1e3 - float(ref)) <= 2e-6 * abs(float(ref))
+    lz = ops.LazyL1(a, b, 0.37, loss)
+    assert torch.equal(lz.materialize(), da) and abs(float(loss) - 2 * float(ref)) <= 2e-5 * abs(float(ref))
+
+
+def test_linear_small_weight_gradient():
+    """Linear(64, 1) over 4 096 rows (patch discriminator tail): batch-split weight / bias gradient."""
+    x, w = rnd(4096, 64, seed=84).float(), rnd(1, 64, seed=85).float()
+    dz = rnd(4096, 1, seed=86).float()
+    dx, dw, db = torch.empty_like(x), torch.ones(1, 64, device=DEV), torch.ones(1, device=DEV)
+    ops.linear_bwd(x, w, dz, dx, dw, db)
+    assert rel_l2(dx, dz @ w) <= 1e-5 and rel_l2(dw - 1.0, dz.t() @ x) <= 1e-4 and rel_l2(db - 1.0, dz.sum(0)) <= 1e-4
+
+
 @pytest.mark.parametrize("b,k,j", [(256, 512, 64), (4096, 32768, 64), (512, 2048, 16), (1024, 1024, 128)])
 def test_linear_as_tcgen05_gemm(b, k, j):
     """nn.Linear that is a real GEMM (patch discriminator: Linear(512 * 8 * 8, 64) over 4 096 patches,
