@@ -510,3 +510,56 @@ def test_lightning_style_trainer_loop():
     assert all(abs(x - y) <= 3e-2 * abs(x) for x, y in zip(losses_a[1:], losses_b[1:])), (losses_a, losses_b)
     for o in optimizers:
         assert int(o.state_dict()["state"][0]["step"]) == 2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's LITERAL configuration (3-D, 128^3): outputs of the reference's own classes, recorded by
+# oracle/make_golden.py --full through oracle/ref_shim.py (tests/golden/ref_final_*_128.pt)
+# ---------------------------------------------------------------------------------------------------------------------
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_reference_literal_discriminator_128_cube(precision):
+    """GAN_final.py:159-209 `Discriminator` on (2, 1, 128, 128, 128): validity and the first BatchNorm's running mean
+    as the reference's own class produced them.  bf16 = the rank-3 tcgen05 path (NDHWC, 5-D TMA boxes, Linear fan-in
+    256 * 29^3)."""
+    fix = torch.load(os.path.join(GOLDEN_DIR, "ref_final_discriminator_128.pt"), weights_only=False)
+    torch.manual_seed(fix["seed_weights"])
+    mine = Discriminator((1, 128, 128, 128), precision=precision)
+    assert list(mine.state_dict().keys()) == fix["state_keys"]
+    assert sum(p.numel() for p in mine.parameters()) == fix["n_params"] == 12760065
+    x = torch.rand(fix["input_shape"], generator=torch.Generator().manual_seed(fix["seed_input"])) * 2 - 1
+    with torch.no_grad():
+        p = mine(x.to(DEV))
+    tol = 1e-4 if precision == "fp32" else 1e-2
+    assert rel_l2(p, fix["validity"]) <= tol, rel_l2(p, fix["validity"])
+    assert rel_l2(mine.model_conv[1].running_mean, fix["bn_running_mean_0"]) <= tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_reference_literal_training_step_128_cube(precision):
+    """GAN_final.py:250-296 `GAN.training_step` for both optimizer indices at the reference's own size (batch 1 of
+    128^3): the losses and the per-parameter gradient norms recorded from the reference's class.  fp32: losses 1e-4,
+    gradient norms 3e-2 (generator: kink-flip floor, profiles/parity_r2.md) / 2e-3 (discriminator).  bf16: losses; the
+    discriminator's gradient norms at 1e-1 (its inputs come through the bf16 generator cascade)."""
+    fix = torch.load(os.path.join(GOLDEN_DIR, "ref_final_step_128.pt"), weights_only=False)
+    S = fix["S"]
+    torch.manual_seed(fix["seed_weights"])
+    mine = GAN(1, S, S, S, precision=precision)
+    batch = to_dev(synthetic_batch(1, 3, S, seed=fix["seed_input"]))
+    state = {k: v.detach().clone() for k, v in mine.state_dict().items()}
+    for idx in (0, 1):
+        mine.load_state_dict(state)
+        loss, g, names = _my_pass(mine, batch, idx)
+        want = float(fix[f"loss{idx}"])
+        ltol = 1e-4 if precision == "fp32" else 5e-2
+        assert abs(loss - want) <= ltol * abs(want), (idx, loss, want)
+        summ = fix[f"grad_summary{idx}"]
+        got = torch.tensor([float(g[n].double().norm()) for n in names], dtype=torch.float64)
+        ref = torch.tensor([float(summ[n][0]) for n in names], dtype=torch.float64)
+        err = float((got - ref).norm() / ref.norm())
+        if precision == "fp32":
+            assert err <= (3e-2 if idx == 0 else 2e-3), (idx, err)
+        elif idx == 1:
+            assert err <= 1e-1, (idx, err)
