@@ -87,8 +87,9 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
   uint64_t* tempty = tfull + kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxAcc);
   float* s_stats = reinterpret_cast<float*>(aux + kHaloAux);   // [8 epilogue warps][2*N]
-  uint32_t* s_tr = reinterpret_cast<uint32_t*>(s_stats + 8 * 2 * N);   // [8 epilogue warps][32][kTrW] bf16x2
-  float* s_bias = reinterpret_cast<float*>(s_tr + 8 * 32 * kTrW);      // [N]
+  float* s_bias = s_stats + 8 * 2 * N;                         // [N]
+  // (no transpose scratch: the statistics of the N = 128 layers are reduced with register shuffles -- the 17 KB it took
+  //  are one more activation plane in flight for the layers whose resident weights fill the shared memory, D layer 2)
   // N <= 32: the two epilogue warp groups take alternate tiles (4 arrivals free an accumulator);
   // N >= 64: they take alternate 32-column chunks of every tile (8 arrivals)
   constexpr uint32_t kEmptyArrivals = N <= 32 ? 4u : 8u;
@@ -227,7 +228,6 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
     const int half = ew >> 2;      // alternating column chunks
     const int row = q * 32 + lane;
     const int lh = row >> 3, lw = row & 7;
-    uint32_t* tr = s_tr + ew * 32 * kTrW;
     float* sl = s_stats + ew * 2 * N;
     constexpr int CH = N >= 32 ? 32 : 16;
     if constexpr (N <= 64) {
@@ -317,6 +317,10 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
       mbar_wait(&tfull[acc], par);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
+      const bool has_slope = P.slope != nullptr;
+      const float slope_a = has_slope ? __ldg(P.slope) : 1.f;
+      const bf16* res_row = (P.res && valid) ? P.res + (long long)img * P.res_sn + (long long)oh * P.res_sh + (long long)ow * P.res_sw
+                                             : nullptr;
 #pragma unroll 1
       for (int c0 = half * CH; c0 < N; c0 += 2 * CH) {
         uint32_t r[32];
@@ -328,10 +332,9 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         for (int j = 0; j < CH / 2; ++j) {
           float f0 = __uint_as_float(r[2 * j]), f1 = __uint_as_float(r[2 * j + 1]);
           f0 += s_bias[c0 + 2 * j]; f1 += s_bias[c0 + 2 * j + 1];
-          if (P.slope) { const float a = __ldg(P.slope); f0 = f0 > 0.f ? f0 : a * f0; f1 = f1 > 0.f ? f1 : a * f1; }
-          if (P.res && valid) {
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(P.res + (long long)img * P.res_sn + (long long)oh * P.res_sh +
-                                                                   (long long)ow * P.res_sw + c0 + 2 * j);
+          if (has_slope) { f0 = f0 > 0.f ? f0 : slope_a * f0; f1 = f1 > 0.f ? f1 : slope_a * f1; }
+          if (res_row) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(res_row + c0 + 2 * j);
             f0 += __uint_as_float(u << 16); f1 += __uint_as_float(u & 0xffff0000u);
           }
           __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
@@ -350,30 +353,22 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
                   make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
           }
         }
-        if (P.stats) {  // statistics of the values as stored: transpose through shared memory
-          constexpr int WPR = CH / 2;           // bf16x2 words per row; lane = (row part, column pair)
+        if (P.stats) {  // statistics of the values as stored: register transpose-reduce (lane l ends up with column c0 + l)
+          float v[32], sq[32];
 #pragma unroll
-          for (int j = 0; j < WPR; ++j) tr[lane * kTrW + j] = valid ? packed[j] : 0u;
-          __syncwarp();
-          const int cp = lane % WPR, part = lane / WPR;
-          float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll
-          for (int i = 0; i < WPR; ++i) {
-            const uint32_t u = tr[(part * WPR + i) * kTrW + cp];
-            const float fa = __uint_as_float(u << 16), fb = __uint_as_float(u & 0xffff0000u);
-            s1a += fa; s1b += fb;
-            s2a = fmaf(fa, fa, s2a); s2b = fmaf(fb, fb, s2b);
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t u = (j < CH / 2 && valid) ? packed[j < CH / 2 ? j : 0] : 0u;
+            v[2 * j] = __uint_as_float(u << 16);
+            v[2 * j + 1] = __uint_as_float(u & 0xffff0000u);
+            sq[2 * j] = v[2 * j] * v[2 * j];
+            sq[2 * j + 1] = v[2 * j + 1] * v[2 * j + 1];
           }
-#pragma unroll
-          for (int off = WPR; off < 32; off <<= 1) {
-            s1a += __shfl_xor_sync(0xffffffffu, s1a, off); s1b += __shfl_xor_sync(0xffffffffu, s1b, off);
-            s2a += __shfl_xor_sync(0xffffffffu, s2a, off); s2b += __shfl_xor_sync(0xffffffffu, s2b, off);
+          const float t1 = warp_transpose_reduce32(v, lane);
+          const float t2 = warp_transpose_reduce32(sq, lane);
+          if (lane < CH) {   // slots owned by (this warp, this lane): fixed accumulation order
+            sl[c0 + lane] += t1;
+            sl[N + c0 + lane] += t2;
           }
-          if (lane < WPR) {   // slots owned by (this warp, this lane): fixed accumulation order
-            sl[c0 + 2 * lane] += s1a; sl[c0 + 2 * lane + 1] += s1b;
-            sl[N + c0 + 2 * lane] += s2a; sl[N + c0 + 2 * lane + 1] += s2b;
-          }
-          __syncwarp();
         }
       }
       tc_fence_before();
@@ -432,7 +427,7 @@ static int halo3x3_run(int dir, int n, int ih, int iw, int oh, int ow, int C, in
   const int KC = C < 64 ? C : 64;
   const size_t w_bytes = ((size_t)9 * C * N * 2 + 1023) & ~(size_t)1023;
   const size_t a_bytes = ((size_t)HPIX * KC * 2 + 1023) & ~(size_t)1023;   // one <= 64-channel plane
-  const size_t aux = kHaloAux + (size_t)8 * 2 * N * 4 + (size_t)8 * 32 * kTrW * 4 + (size_t)N * 4;   // barriers, stats slots, transpose scratch, bias
+  const size_t aux = kHaloAux + (size_t)8 * 2 * N * 4 + (size_t)N * 4;   // barriers, stats slots, bias
   const size_t budget = 227 * 1024 - 1024;
   if (w_bytes + 2 * a_bytes + aux > budget) return 1;
   int nbuf = (int)((budget - w_bytes - aux) / a_bytes);

@@ -31,6 +31,10 @@ for w in $WHAT; do
              echo "n3d exit $?"; tail -30 gpurun_out/pytest_n3d_$TAG.log;;
     b3d)     timeout 900 python tools/bench_3d.py ${B3D_ARGS:-1 3 128} > gpurun_out/bench3d_$TAG.log 2> gpurun_out/bench3d_$TAG.err
              echo "b3d exit $?"; cat gpurun_out/bench3d_$TAG.log; tail -5 gpurun_out/bench3d_$TAG.err;;
+    ncud)    timeout 600 python tools/d_convs_once.py > gpurun_out/plain_dconv_$TAG.log 2>&1 &&
+             timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"tapgemm|halo3x3|wgrad_kernel" \
+                 -o gpurun_out/dconvs_$TAG -f python tools/d_convs_once.py > gpurun_out/ncu_dconv_$TAG.log 2>&1
+             echo "ncud exit $?"; ls -la gpurun_out/dconvs_$TAG.ncu-rep;;
     ncu)     CMD="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-extra"
              timeout 600 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
              timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-2800} -c ${NCU_COUNT:-2800} --csv \
