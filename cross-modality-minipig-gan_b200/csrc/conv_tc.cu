@@ -1118,6 +1118,11 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
   const bool small = g.cx <= 64 && (long long)g.n * g.yd * g.yh * g.yw <= (1LL << 20);
   const int max_tpg = (small ? 256 : 512) / nx;
   P.ngroups = (ntap + max_tpg - 1) / max_tpg;
+  // EQUAL groups when a slightly finer split allows it: the CTAs of the different groups of one pixel range walk the same
+  // dY / X tiles side by side; with 5 + 4 taps (D layer 2: 9 taps, 8 accumulators fit) the lighter group ran ahead by more
+  // than the L2 holds and every tile came from DRAM twice (ncu: 1461 MB read for 785 MB of operands)
+  for (int gcount = P.ngroups; gcount <= P.ngroups + 2 && gcount <= ntap; ++gcount)
+    if (ntap % gcount == 0) { P.ngroups = gcount; break; }
   P.taps_per_group = (ntap + P.ngroups - 1) / P.ngroups;   // balanced groups
   P.m_blocks = (g.cy + 127) / 128;
   choose_tile(g.yw, g.yh, g.yd, g.n, 64, r3, &P.tw_log2, &P.th_log2, &P.td_log2);
