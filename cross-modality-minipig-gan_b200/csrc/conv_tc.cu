@@ -919,6 +919,8 @@ static int pick_bn(int n) {
 #include "conv_halo.cuh"
 // one-input-channel forward convolutions (im2col tile built in shared memory, one MMA per tile)
 #include "conv_c1mma.cuh"
+// stride-2 3x3 layers (down-sampling convolutions, transposed convolutions and their data gradients)
+#include "conv_s2.cuh"
 namespace mpgan {
 namespace tc {
 
@@ -939,6 +941,10 @@ static int run_tapgemm(const Geom2& g, int dir, const void* in, int64_t ldi, con
   const int od = dir == 0 ? g.yd : g.xd, oh = dir == 0 ? g.yh : g.xh, ow = dir == 0 ? g.yw : g.xw;
   if (!r3 && g.s == 1 && g.kh == 3 && g.kw == 3 && g.ph == g.pw && g.ph <= 1 && halo_enabled()) {
     int rc = halo3x3_run(dir, g.n, ih, iw, oh, ow, C, N, g.ph, in, ldi, w, bias, out, ldo, stats, res, ldres, s, 0, slope);
+    if (rc != 1) return rc;
+  }
+  if (!r3 && g.s == 2 && g.kh == 3 && g.kw == 3 && g.ph == 1 && g.pw == 1) {
+    int rc = halo_s2_run(dir, g.n, g.xh, g.xw, g.yh, g.yw, C, N, in, ldi, w, bias, out, ldo, stats, res, ldres, s, slope);
     if (rc != 1) return rc;
   }
   const int KC = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);

@@ -206,21 +206,23 @@ __device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, u
 // `slope` (optional, device scalar): PReLU / LeakyReLU applied to (acc + bias) BEFORE the residual is added -- the
 // inference-mode fusion conv -> folded BatchNorm -> PReLU (+ residual) of MONAI's Convolution / ResidualUnit.
 template <int CH>
-__device__ __forceinline__ void epi_chunk_store(const uint32_t (&r)[CH], const float* s_bias_c0, bf16* orow, bool valid,
-                                                bool do_stats, unsigned long long (&s1)[CH / 2],
-                                                unsigned long long (&s2)[CH / 2], const bf16* rrow = nullptr,
-                                                bool wide = false, const float* slope = nullptr) {
+__device__ __forceinline__ void load_res_row(const bf16* rrow, uint32_t (&rq)[CH / 2]) {
+#pragma unroll
+  for (int j = 0; j < CH / 8; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(rrow + j * 8);
+    rq[4 * j] = q.x; rq[4 * j + 1] = q.y; rq[4 * j + 2] = q.z; rq[4 * j + 3] = q.w;
+  }
+}
+
+// core of the chunk epilogue with the residual row already in registers (`rq`, read only when has_res): callers that
+// know the output position before the accumulator is ready request the row early, so that its latency overlaps the MMAs
+template <int CH>
+__device__ __forceinline__ void epi_chunk_store_rq(const uint32_t (&r)[CH], const float* s_bias_c0, bf16* orow, bool valid,
+                                                   bool do_stats, unsigned long long (&s1)[CH / 2],
+                                                   unsigned long long (&s2)[CH / 2], const uint32_t (&rq)[CH / 2],
+                                                   bool has_res, bool wide = false, const float* slope = nullptr) {
   const unsigned long long ones = pack_f32x2(1.f, 1.f);
   uint32_t packed[CH / 2];
-  uint32_t rq[CH / 2];
-  const bool has_res = rrow != nullptr && valid;
-  if (has_res) {
-#pragma unroll
-    for (int j = 0; j < CH / 8; ++j) {
-      const uint4 q = *reinterpret_cast<const uint4*>(rrow + j * 8);
-      rq[4 * j] = q.x; rq[4 * j + 1] = q.y; rq[4 * j + 2] = q.z; rq[4 * j + 3] = q.w;
-    }
-  }
   const bool has_act = slope != nullptr;
   const float a = has_act ? __ldg(slope) : 1.f;
 #pragma unroll
@@ -267,6 +269,17 @@ __device__ __forceinline__ void epi_chunk_store(const uint32_t (&r)[CH], const f
       }
     }
   }
+}
+
+template <int CH>
+__device__ __forceinline__ void epi_chunk_store(const uint32_t (&r)[CH], const float* s_bias_c0, bf16* orow, bool valid,
+                                                bool do_stats, unsigned long long (&s1)[CH / 2],
+                                                unsigned long long (&s2)[CH / 2], const bf16* rrow = nullptr,
+                                                bool wide = false, const float* slope = nullptr) {
+  uint32_t rq[CH / 2];
+  const bool has_res = rrow != nullptr && valid;
+  if (has_res) load_res_row<CH>(rrow, rq);
+  epi_chunk_store_rq<CH>(r, s_bias_c0, orow, valid, do_stats, s1, s2, rq, has_res, wide, slope);
 }
 
 }  // namespace tc

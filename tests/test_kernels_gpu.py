@@ -288,6 +288,81 @@ def test_tc_conv_wgrad(case):
     assert rel_l2(dw, 2 * oti(ref)) <= 2e-3
 
 
+# ------------------------------------------------------------------ stride-2 3x3 halo engines (conv_s2.cuh)
+S2_CASES = [
+    # n, cx (fine-grid channels), cy (coarse-grid channels), (xh, xw)
+    (2, 16, 32, (40, 24)),      # G level-2 down conv / its data gradient; ragged 16 x 8 tiles
+    (3, 32, 64, (36, 20)),      # G level-3 down conv
+    (1, 16, 64, (64, 48)),      # ConvTranspose(64 -> 16) and its data gradient
+    (2, 32, 192, (24, 40)),     # ConvTranspose(192 -> 32): three 64-channel planes; N = 192 data gradient
+    (2, 32, 128, (20, 20)),
+]
+
+
+@pytest.mark.parametrize("case", S2_CASES)
+def test_s2_halo_fprop(case):
+    """Conv k3 s2 p1 (forward of the down convolutions == data gradient of a ConvTranspose) through the space-to-depth
+    halo engine: input and output are channel slices of wider buffers, bias, fused statistics where the engine has them."""
+    n, cx, cy, (xh, xw) = case
+    x = rnd(n, cx, xh, xw, seed=21).bfloat16()
+    w = (rnd(cy, cx, 3, 3, seed=22) * 0.1).bfloat16()
+    b = rnd(cy, seed=23)
+    ref = F.conv2d(x.float(), w.float(), b, stride=2, padding=1)
+    spec = ops.ConvSpec(2, cx, cy, 3, 2, 1)
+    big_in = torch.zeros(n, xh, xw, cx + 16, dtype=torch.bfloat16, device=DEV)
+    big_in[..., 8:8 + cx] = cl(x, torch.bfloat16)
+    big_out = torch.full((n, xh // 2, xw // 2, cy + 32), 3.0, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(2 * cy, dtype=torch.float64, device=DEV) if cy <= 64 else None
+    y, fused = ops.conv_fprop(spec, big_in[..., 8:8 + cx], oti(w, torch.bfloat16), b, out=big_out[..., 16:16 + cy], stats=stats)
+    torch.cuda.synchronize()
+    assert rel_l2(uncl(y), ref) <= 6e-3
+    assert torch.all(big_out[..., :16] == 3.0) and torch.all(big_out[..., 16 + cy:] == 3.0)
+    if stats is not None:
+        assert fused
+        yr = uncl(y).double()
+        assert rel_l2(stats[:cy], yr.sum(dim=(0, 2, 3))) <= 1e-4
+        assert rel_l2(stats[cy:], (yr * yr).sum(dim=(0, 2, 3))) <= 1e-4
+    # inference fusion: PReLU slope + residual in the epilogue
+    slope = torch.tensor([0.25], device=DEV)
+    r = rnd(n, xh // 2, xw // 2, cy, seed=24).bfloat16()
+    ya = ops.conv_act(spec, cl(x, torch.bfloat16), oti(w, torch.bfloat16), b, slope, res=r)
+    assert ya is not None
+    assert rel_l2(uncl(ya), F.prelu(ref, slope) + uncl(r)) <= 6e-3
+
+
+@pytest.mark.parametrize("case", S2_CASES)
+def test_s2_halo_bprop(case):
+    """ConvTranspose k3 s2 p1 op1 forward == data gradient of a stride-2 convolution, through the pixel-shuffle halo
+    engine: bias + fused statistics (the ConvTranspose forward of a training step), and the residual-add form."""
+    n, cx, cy, (xh, xw) = case
+    yh, yw = xh // 2, xw // 2
+    dy = rnd(n, cy, yh, yw, seed=25).bfloat16()
+    w = (rnd(cy, cx, 3, 3, seed=26) * 0.1).bfloat16()
+    b = rnd(cx, seed=27)
+    ref = torch.nn.grad.conv2d_input((n, cx, xh, xw), w.float(), dy.float(), stride=2, padding=1)
+    spec = ops.ConvSpec(2, cx, cy, 3, 2, 1)
+    wt = torch.empty(w.numel(), dtype=torch.bfloat16, device=DEV)
+    ops.weight_transpose(oti(w, torch.bfloat16), wt, cy, 9, cx)
+    big_in = torch.zeros(n, yh, yw, cy + 8, dtype=torch.bfloat16, device=DEV)
+    big_in[..., 8:] = cl(dy, torch.bfloat16)
+    stats = torch.zeros(2 * cx, dtype=torch.float64, device=DEV)
+    dx, fused = ops.conv_bprop(spec, big_in[..., 8:], oti(w, torch.bfloat16), wt, b, xs=(xh, xw), stats=stats)
+    torch.cuda.synchronize()
+    assert fused
+    assert rel_l2(uncl(dx), ref + b.view(1, -1, 1, 1)) <= 6e-3
+    xr = uncl(dx).double()
+    assert rel_l2(stats[:cx], xr.sum(dim=(0, 2, 3))) <= 1e-4
+    assert rel_l2(stats[cx:], (xr * xr).sum(dim=(0, 2, 3))) <= 1e-4
+    r = rnd(n, xh, xw, cx, seed=28).bfloat16()
+    dx2, _ = ops.conv_bprop(spec, cl(dy, torch.bfloat16), oti(w, torch.bfloat16), wt, None, xs=(xh, xw), res=r)
+    assert rel_l2(uncl(dx2), ref + uncl(r)) <= 6e-3
+    slope = torch.tensor([0.25], device=DEV)
+    spec_t = ops.ConvSpec(2, cx, cy, 3, 2, 1, transposed=True, output_padding=1)
+    ya = ops.conv_act(spec_t, cl(dy, torch.bfloat16), wt, b, slope, res=r)
+    assert ya is not None
+    assert rel_l2(uncl(ya), F.prelu(ref + b.view(1, -1, 1, 1), slope) + uncl(r)) <= 6e-3
+
+
 # ------------------------------------------------------------------ tcgen05 path, rank 3 (NDHWC, 5-D TMA boxes)
 TC3_CASES = [
     # n, cin, cout, (d, h, w), k, s, p

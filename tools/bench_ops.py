@@ -20,7 +20,8 @@ from mpgan import ops  # noqa: E402
 from mpgan._lib import ACT_LEAKY, ACT_PRELU  # noqa: E402
 
 DEV = "cuda"
-B = 32
+B = int(os.environ.get("OPS_BATCH", "32"))      # OPS_BATCH=64 OPS_SCALE=2: the inference shapes of BASELINE configs[4]
+SCALE = int(os.environ.get("OPS_SCALE", "1"))
 
 
 def timeit(fn, reps=20, warm=3):
@@ -58,6 +59,8 @@ def conv_case(name, cin, cout, k, s, p, xs, transposed=False, dirs=("f", "b", "w
     """Underlying conv X(cin) -> Y(cout); for a ConvTranspose pass the underlying conv's cin/cout.  rank 3: the
     reference's literal volumes (NDHWC, rank-3 tcgen05 path)."""
     n = batch or B
+    if rank == 2 and name.startswith("G"):
+        xs *= SCALE
     spec = ops.ConvSpec(rank, cin, cout, k, s, p, transposed, s - 1 if transposed else 0)
     ys = spec.y_of_x((xs,) * rank)[0]
     x = rnd(n, *([xs] * rank), cin)

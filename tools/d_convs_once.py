@@ -1,6 +1,7 @@
 """The nine FLOP-dominant launches of the training step -- D layers 2-4 (batch 32, 256x256 input) x {fprop with fused
-BatchNorm statistics, data gradient, weight gradient} -- three eager launches each (two warm-ups + the one profiled), for
-`ncu --set full` (tools/gpu_r2.sh ncud).  Inputs exceed L2 (264-520 MB per tensor)."""
+BatchNorm statistics, data gradient, weight gradient} -- three eager launches each; the third sits between
+cudaProfilerStart / Stop, so `ncu --profile-from-start off --set full` (tools/gpu_r2.sh ncud) captures exactly nine warm
+launches.  Inputs exceed L2 (264-520 MB per tensor)."""
 import os
 import sys
 
@@ -21,11 +22,13 @@ for name, cin, cout, k, s, xs in (("D2", 64, 128, 3, 1, 254), ("D3", 128, 256, 4
     wt = w.permute(2, 1, 0).contiguous()
     dw = torch.zeros(cout, k * k, cin, device=DEV)
     stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
-    for _ in range(3):
-        ops.conv_fprop(spec, x, w, None, out=y, stats=stats)
-    for _ in range(3):
-        ops.conv_bprop(spec, y, w, wt, None, xs=(xs, xs), out=x)
-    for _ in range(3):
-        ops.conv_wgrad(spec, x, y, dw)
-    torch.cuda.synchronize()
+    for fn in (lambda: ops.conv_fprop(spec, x, w, None, out=y, stats=stats),
+               lambda: ops.conv_bprop(spec, y, w, wt, None, xs=(xs, xs), out=x),
+               lambda: ops.conv_wgrad(spec, x, y, dw)):
+        fn(), fn()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        fn()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     print(name, "ok")

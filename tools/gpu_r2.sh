@@ -25,6 +25,13 @@ for w in $WHAT; do
              echo "ref exit $?"; cat gpurun_out/benchref_$TAG.log;;
     phases)  timeout 600 python tools/phase_times.py 10 > gpurun_out/phase_$TAG.log 2>&1; echo "phases exit $?"; cat gpurun_out/phase_$TAG.log;;
     ops)     timeout 900 python tools/bench_ops.py ${OPS_FILTER:-} > gpurun_out/ops_$TAG.log 2>&1; echo "ops exit $?"; tail -70 gpurun_out/ops_$TAG.log;;
+    ktest)   timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 600 -k "${KFILTER:-s2_halo or tc_conv}" > gpurun_out/pytest_k_$TAG.log 2>&1
+             echo "ktest exit $?"; tail -30 gpurun_out/pytest_k_$TAG.log;;
+    opsab)   # A/B of the stride-2 halo engines against the tap-GEMM path, training and inference sizes
+             for sz in "32 1" "64 2"; do set -- $sz
+               echo "== batch $1 scale $2: halo_s2"; OPS_BATCH=$1 OPS_SCALE=$2 timeout 600 python tools/bench_ops.py ${OPS_FILTER:-g_16_32 g_32_64 gT_ g_16_16} 2>&1 | tee -a gpurun_out/opsab_$TAG.log
+               echo "== batch $1 scale $2: MPGAN_NO_HALO_S2=1"; MPGAN_NO_HALO_S2=1 OPS_BATCH=$1 OPS_SCALE=$2 timeout 600 python tools/bench_ops.py ${OPS_FILTER:-g_16_32 g_32_64 gT_} 2>&1 | tee -a gpurun_out/opsab_$TAG.log
+             done;;
     k3d)     timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 600 -k "tc3" > gpurun_out/pytest_k3d_$TAG.log 2>&1
              echo "k3d exit $?"; tail -30 gpurun_out/pytest_k3d_$TAG.log;;
     n3d)     timeout 900 python -m pytest tests/test_nets_gpu.py -m gpu -q --timeout 600 -k "3" > gpurun_out/pytest_n3d_$TAG.log 2>&1
@@ -32,9 +39,22 @@ for w in $WHAT; do
     b3d)     timeout 900 python tools/bench_3d.py ${B3D_ARGS:-1 3 128} > gpurun_out/bench3d_$TAG.log 2> gpurun_out/bench3d_$TAG.err
              echo "b3d exit $?"; cat gpurun_out/bench3d_$TAG.log; tail -5 gpurun_out/bench3d_$TAG.err;;
     ncud)    timeout 600 python tools/d_convs_once.py > gpurun_out/plain_dconv_$TAG.log 2>&1 &&
-             timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"tapgemm|halo3x3|wgrad_kernel" \
-                 -o gpurun_out/dconvs_$TAG -f python tools/d_convs_once.py > gpurun_out/ncu_dconv_$TAG.log 2>&1
-             echo "ncud exit $?"; ls -la gpurun_out/dconvs_$TAG.ncu-rep;;
+             timeout 1500 ncu --set full --clock-control none --profile-from-start off -k regex:"tapgemm|halo3x3|wgrad_kernel" \
+                 -o /tmp/dconvs_$TAG -f python tools/d_convs_once.py > gpurun_out/ncu_dconv_$TAG.log 2>&1
+             echo "ncud exit $?"; ls -la /tmp/dconvs_$TAG.ncu-rep
+             ncu -i /tmp/dconvs_$TAG.ncu-rep --page raw --csv > gpurun_out/dconvs_$TAG.csv 2> gpurun_out/dconvs_csv_$TAG.err; wc -c gpurun_out/dconvs_$TAG.csv;;
+    ncug)    # ncu --set full over the first UNet of one inference forward (batch 64, 512x512): raw + source pages as csv
+             timeout 900 ncu --set full --import-source on --clock-control none --profile-from-start off -c ${NCUG_COUNT:-24} \
+                 -o /tmp/ginf_$TAG -f python tools/infer_once.py > gpurun_out/ncu_ginf_$TAG.log 2>&1
+             echo "ncug exit $?"; ls -la /tmp/ginf_$TAG.ncu-rep
+             ncu -i /tmp/ginf_$TAG.ncu-rep --page raw --csv > gpurun_out/ginf_raw_$TAG.csv 2> /dev/null
+             ncu -i /tmp/ginf_$TAG.ncu-rep --page source --csv 2> /dev/null | gzip > gpurun_out/ginf_source_$TAG.csv.gz
+             ls -la gpurun_out/ginf_*;;
+    ncui)    CMD="python tools/infer_once.py"
+             timeout 600 $CMD > gpurun_out/plain_infer_$TAG.log 2>&1 &&
+             timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+                 --log-file gpurun_out/launches_infer_$TAG.csv $CMD > gpurun_out/ncu_infer_$TAG.log 2>&1
+             echo "ncui exit $?"; wc -l gpurun_out/launches_infer_$TAG.csv;;
     ncu)     CMD="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-extra"
              timeout 600 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
              timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-2800} -c ${NCU_COUNT:-2800} --csv \

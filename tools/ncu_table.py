@@ -1,5 +1,6 @@
 """Table of the nine discriminator conv launches from the `ncu --set full` report of tools/d_convs_once.py.
-usage: python tools/ncu_table.py gpurun_out/dconvs_<tag>.ncu-rep > profiles/ncu_r2_dconvs.md"""
+usage: python tools/ncu_table.py gpurun_out/dconvs_<tag>.{ncu-rep|csv} > profiles/ncu_r2_dconvs.md
+(the .csv is `ncu -i <rep> --page raw --csv`, made on the GPU box: the report itself is too large to travel)"""
 import csv
 import io
 import json
@@ -8,7 +9,7 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, body = rows[0], rows[2:]
 ix = {h: i for i, h in enumerate(hdr)}
@@ -17,8 +18,8 @@ LAYERS = [("D2", 64, 128, 3, 254, 252), ("D3", 128, 256, 4, 252, 125), ("D4", 25
 pk = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
 print("# ncu `--set full` over the nine FLOP-dominant launches (D layers 2-4 x fprop / dgrad / wgrad), batch 32, bf16\n")
 print(f"command (one B200, after the plain run of the same command had exited 0): `ncu --set full --clock-control none "
-      f"--import-source on -k regex:\"tapgemm|halo3x3|wgrad_kernel\" -o {rep[:-8]} python tools/d_convs_once.py`; the third launch of "
-      "each kind is tabulated (two warm-ups before it).  Times under a profiler are not bench values (`bench.py` / "
+      f"--profile-from-start off -k regex:\"tapgemm|halo3x3|wgrad_kernel\" python tools/d_convs_once.py`; the third launch of "
+      "each kind is captured (two warm-ups before it, outside the cudaProfilerStart / Stop window).  Times under a profiler are not bench values (`bench.py` / "
       "`tools/bench_ops.py` hold those); the tensor-pipe and DRAM columns are what this table is for.  fprop launches carry the fused "
       "BatchNorm statistics, data gradients do not (as in the training step).\n")
 print("| launch | kernel | us (ncu) | algorithmic TFLOP/s | `sm__pipe_tensor_cycles_active` % of peak (elapsed / active) | DRAM read + write MB | "
@@ -28,7 +29,7 @@ out = {}
 for li, (name, cin, cout, k, xs, ys) in enumerate(LAYERS):
     flop = 2.0 * B * ys * ys * cout * k * k * cin
     for di, d in enumerate(("fprop", "dgrad", "wgrad")):
-        r = body[li * 9 + di * 3 + 2]
+        r = body[li * 3 + di]
         us = float(r[ix["gpu__time_duration.sum"]])
         rd = float(r[ix["dram__bytes_read.sum"]])
         wr = float(r[ix["dram__bytes_write.sum"]])
