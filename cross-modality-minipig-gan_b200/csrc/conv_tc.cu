@@ -921,6 +921,8 @@ static int pick_bn(int n) {
 #include "conv_c1mma.cuh"
 // stride-2 3x3 layers (down-sampling convolutions, transposed convolutions and their data gradients)
 #include "conv_s2.cuh"
+// weight gradients of the 16 / 32-input-channel 3x3 layers (one X halo box per tile)
+#include "conv_wgrad_halo.cuh"
 namespace mpgan {
 namespace tc {
 
@@ -1094,6 +1096,10 @@ static int run_wgrad(const Geom2& g, const void* x, int64_t ldx, const void* y, 
   MPGAN_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, MPGAN_ERR_SHAPE, "pixel strides must be multiples of 8 elements");
   const bool r3 = g.rank == 3;
   const int sd = r3 ? g.s : 1;
+  if (!r3 && g.kh == 3 && g.kw == 3 && g.ph == g.pw) {
+    int rc = wgrad_halo_run(g.s, g.ph, g.n, g.xh, g.xw, g.yh, g.yw, g.cx, g.cy, x, ldx, y, ldy, dw, s);
+    if (rc != 1) return rc;
+  }
   WgradParams P;
   memset(&P, 0, sizeof(P));
   P.cx = g.cx; P.cy = g.cy; P.dw = dw;

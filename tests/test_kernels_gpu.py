@@ -363,6 +363,34 @@ def test_s2_halo_bprop(case):
     assert rel_l2(uncl(ya), F.prelu(ref + b.view(1, -1, 1, 1), slope) + uncl(r)) <= 6e-3
 
 
+WGH_CASES = [
+    # n, cx, cy, (xh, xw), stride, pad       -- conv_wgrad_halo.cuh: one X halo box per tile, taps as operand atoms
+    (2, 16, 16, (40, 24), 1, 1), (3, 32, 32, (19, 21), 1, 1), (2, 16, 32, (23, 17), 1, 0), (1, 32, 64, (33, 40), 1, 1),
+    (2, 16, 64, (16, 8), 1, 1),
+    (2, 16, 32, (40, 24), 2, 1), (3, 32, 64, (36, 20), 2, 1), (1, 16, 64, (64, 48), 2, 1), (2, 32, 32, (20, 20), 2, 1),
+]
+
+
+@pytest.mark.parametrize("case", WGH_CASES)
+def test_wgrad_halo(case):
+    n, cx, cy, (xh, xw), st, p = case
+    yh, yw = (xh + 2 * p - 3) // st + 1, (xw + 2 * p - 3) // st + 1
+    x = rnd(n, cx, xh, xw, seed=31).bfloat16()
+    dy = rnd(n, cy, yh, yw, seed=32).bfloat16()
+    ref = torch.nn.grad.conv2d_weight(x.float(), (cy, cx, 3, 3), dy.float(), stride=st, padding=p)
+    spec = ops.ConvSpec(2, cx, cy, 3, st, p)
+    big_x = torch.zeros(n, xh, xw, cx + 16, dtype=torch.bfloat16, device=DEV)     # channel slices of wider buffers
+    big_x[..., 16:] = cl(x, torch.bfloat16)
+    big_y = torch.zeros(n, yh, yw, cy + 8, dtype=torch.bfloat16, device=DEV)
+    big_y[..., :cy] = cl(dy, torch.bfloat16)
+    dw = torch.ones(cy, 9, cx, device=DEV)
+    ops.conv_wgrad(spec, big_x[..., 16:], big_y[..., :cy], dw)
+    torch.cuda.synchronize()
+    assert rel_l2(dw - 1.0, oti(ref)) <= 2e-3
+    ops.conv_wgrad(spec, cl(x, torch.bfloat16), cl(dy, torch.bfloat16), dw)     # accumulates
+    assert rel_l2(dw - 1.0, 2 * oti(ref)) <= 2e-3
+
+
 # ------------------------------------------------------------------ tcgen05 path, rank 3 (NDHWC, 5-D TMA boxes)
 TC3_CASES = [
     # n, cin, cout, (d, h, w), k, s, p

@@ -32,6 +32,8 @@ for w in $WHAT; do
                echo "== batch $1 scale $2: halo_s2"; OPS_BATCH=$1 OPS_SCALE=$2 timeout 600 python tools/bench_ops.py ${OPS_FILTER:-g_16_32 g_32_64 gT_ g_16_16} 2>&1 | tee -a gpurun_out/opsab_$TAG.log
                echo "== batch $1 scale $2: MPGAN_NO_HALO_S2=1"; MPGAN_NO_HALO_S2=1 OPS_BATCH=$1 OPS_SCALE=$2 timeout 600 python tools/bench_ops.py ${OPS_FILTER:-g_16_32 g_32_64 gT_} 2>&1 | tee -a gpurun_out/opsab_$TAG.log
              done;;
+    opsw)    # A/B of the halo weight-gradient kernel
+             for e in 0 1; do echo "== MPGAN_NO_WGRAD_HALO=$e"; MPGAN_NO_WGRAD_HALO=$e timeout 600 python tools/bench_ops.py g_16_16 g_16_32 g_32_32 g_32_64 gT_16 2>&1 | grep wgrad | tee -a gpurun_out/opsw_$TAG.log; done;;
     k3d)     timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 600 -k "tc3" > gpurun_out/pytest_k3d_$TAG.log 2>&1
              echo "k3d exit $?"; tail -30 gpurun_out/pytest_k3d_$TAG.log;;
     n3d)     timeout 900 python -m pytest tests/test_nets_gpu.py -m gpu -q --timeout 600 -k "3" > gpurun_out/pytest_n3d_$TAG.log 2>&1
@@ -50,6 +52,12 @@ for w in $WHAT; do
              ncu -i /tmp/ginf_$TAG.ncu-rep --page raw --csv > gpurun_out/ginf_raw_$TAG.csv 2> /dev/null
              ncu -i /tmp/ginf_$TAG.ncu-rep --page source --csv 2> /dev/null | gzip > gpurun_out/ginf_source_$TAG.csv.gz
              ls -la gpurun_out/ginf_*;;
+    ncugp)   # warm-cache launch lists of the generator's forward and backward (one eager pass each)
+             for ph in fwd bwd; do
+               timeout 900 ncu --metrics gpu__time_duration.sum --cache-control none --clock-control none --profile-from-start off --csv \
+                   --log-file gpurun_out/launches_g${ph}_$TAG.csv python tools/g_phases_once.py $ph > gpurun_out/ncu_g${ph}_$TAG.log 2>&1
+               echo "ncugp $ph exit $?"; wc -l gpurun_out/launches_g${ph}_$TAG.csv
+             done;;
     ncui)    CMD="python tools/infer_once.py"
              timeout 600 $CMD > gpurun_out/plain_infer_$TAG.log 2>&1 &&
              timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
