@@ -22,6 +22,7 @@ constexpr int kTaps = 9;
 
 struct Geom {
   int n, xh, xw, yh, yw, s, pad, C;
+  int vec;   // the one-channel tensor is contiguous bf16 with 16-byte aligned rows: window loads are 16-byte vectors
 };
 
 struct PixWalk {
@@ -238,6 +239,53 @@ __device__ __forceinline__ void load_window(const Geom& g, const T* __restrict__
   }
 }
 
+// The same window for a CONTIGUOUS one-channel bf16 image whose rows are 16-byte aligned (xw % 8 == 0): the RUN * S
+// columns starting at w0 * S are one aligned 16-byte vector (RUN * S == 8 for both strides), the one or two columns
+// beside it are scalar loads -- 2-3 load instructions per window row instead of 9-10 (ncu: 60 % of the samples of the
+// pixel-at-a-time kernels sat on their scalar 2-byte loads).  Requires w0 * S + 7 < xw (full run); PAD is 0 or 1.
+template <int S, int PAD>
+__device__ __forceinline__ void load_window_vec(const Geom& g, const bf16* __restrict__ x, int img, int h, int w0,
+                                                float (&xv)[3][RunOf<S>::WIN]) {
+  constexpr int WIN = RunOf<S>::WIN;
+  static_assert(RunOf<S>::RUN * S == 8, "one 16-byte vector per window row");
+  const int ih0 = h * S - PAD, cv0 = w0 * S;
+  const bf16* xi = x + (size_t)img * g.xh * g.xw;
+#pragma unroll
+  for (int rh = 0; rh < 3; ++rh) {
+    const int ih = ih0 + rh;
+    const bool okh = (unsigned)ih < (unsigned)g.xh;
+    const bf16* xr = xi + (size_t)(okh ? ih : 0) * g.xw;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (okh) u = *reinterpret_cast<const uint4*>(xr + cv0);
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      xv[rh][PAD + 2 * e] = __uint_as_float(uu[e] << 16);
+      xv[rh][PAD + 2 * e + 1] = __uint_as_float(uu[e] & 0xffff0000u);
+    }
+#pragma unroll
+    for (int j = 0; j < WIN; ++j) {
+      if (j < PAD || j >= PAD + 8) {
+        const int iw = cv0 - PAD + j;
+        xv[rh][j] = (okh && (unsigned)iw < (unsigned)g.xw) ? to_f(xr[iw]) : 0.f;
+      }
+    }
+  }
+}
+
+template <typename T, int S>
+__device__ __forceinline__ void load_window_any(const Geom& g, const T* __restrict__ x, int ldx, int img, int h, int w0,
+                                                float (&xv)[3][RunOf<S>::WIN]) {
+  if constexpr (sizeof(T) == 2) {
+    if (g.vec && w0 * S + 7 < g.xw) {
+      if (g.pad == 1) load_window_vec<S, 1>(g, x, img, h, w0, xv);
+      else load_window_vec<S, 0>(g, x, img, h, w0, xv);
+      return;
+    }
+  }
+  load_window<T, S>(g, x, ldx, img, h, w0, xv);
+}
+
 template <typename T, int S>
 __global__ void __launch_bounds__(kThreads, 1)
 fprop_run_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__ w, const float* __restrict__ bias,
@@ -254,12 +302,28 @@ fprop_run_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__
   const int nruns = g.n * g.yh * rpr;
   const int rstep = nthr / cv;
   float2 wr[kTaps][4], b[4];
+  bool wvec = false;
+  if constexpr (sizeof(T) == 2) wvec = (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+  if (wvec) {   // the 8 x 9 weights of the group are 144 contiguous, 16-byte aligned bytes: nine vector loads, not 72 scalar ones
+    uint4 u[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(w + c0 * kTaps) + i);
+    const uint16_t* wl = reinterpret_cast<const uint16_t*>(u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int t = 0; t < kTaps; ++t)
+        wr[t][j] = make_float2(__uint_as_float((uint32_t)wl[(2 * j) * kTaps + t] << 16),
+                               __uint_as_float((uint32_t)wl[(2 * j + 1) * kTaps + t] << 16));
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     b[j] = make_float2(bias ? bias[c0 + 2 * j] : 0.f, bias ? bias[c0 + 2 * j + 1] : 0.f);
+    if (!wvec) {
 #pragma unroll
-    for (int t = 0; t < kTaps; ++t)
-      wr[t][j] = make_float2(to_f(w[(c0 + 2 * j) * kTaps + t]), to_f(w[(c0 + 2 * j + 1) * kTaps + t]));
+      for (int t = 0; t < kTaps; ++t)
+        wr[t][j] = make_float2(to_f(w[(c0 + 2 * j) * kTaps + t]), to_f(w[(c0 + 2 * j + 1) * kTaps + t]));
+    }
   }
   constexpr bool kExact = sizeof(T) == 4;   // fp32 storage: flush the fp32 statistics partials into fp64 every run
   float2 s1[4], s2[4];
@@ -274,7 +338,7 @@ fprop_run_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__
     const int h = rr % g.yh, img = rr / g.yh;
     const int w0 = rw * RUN;
     float xv[3][WIN];
-    load_window<T, S>(g, x, ldx, img, h, w0, xv);
+    load_window_any<T, S>(g, x, ldx, img, h, w0, xv);
     T* yrow = y + ((img * g.yh + h) * g.yw + w0) * ldy + c0;
 #pragma unroll
     for (int i = 0; i < RUN; ++i) {
@@ -570,6 +634,113 @@ wgrad_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__ y, 
   }
 }
 
+// Run-based weight gradient (C % 8 == 0): a thread owns 8 channels (72 register accumulators) and walks RUN consecutive
+// Y pixels of one row; the 3 x WIN window of the one-channel X is loaded once per run (vector loads when contiguous).
+template <typename T, int S>
+__global__ void __launch_bounds__(kThreads, 2)
+wgrad_run_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__ y, int ldy, float* __restrict__ dw) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ float smf[];   // (kThreads/32) * cv * 72 floats
+  constexpr int RUN = RunOf<S>::RUN, WIN = RunOf<S>::WIN;
+  const int cv = g.C / 8;   // divides 32
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthr = gridDim.x * blockDim.x;
+  const int c0 = (tid % cv) * 8;
+  const int rpr = (g.yw + RUN - 1) / RUN;
+  const int nruns = g.n * g.yh * rpr;
+  const int rstep = nthr / cv;
+  float2 acc2[kTaps][4];
+#pragma unroll
+  for (int t = 0; t < kTaps; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc2[t][j] = make_float2(0.f, 0.f);
+  for (int run = tid / cv; run < nruns; run += rstep) {
+    const int rw = run % rpr;
+    const int rr = run / rpr;
+    const int h = rr % g.yh, img = rr / g.yh;
+    const int w0 = rw * RUN;
+    float xv[3][WIN];
+    load_window_any<T, S>(g, x, ldx, img, h, w0, xv);
+    const T* yrow = y + ((img * g.yh + h) * g.yw + w0) * ldy + c0;
+#pragma unroll
+    for (int i = 0; i < RUN; ++i) {
+      if (w0 + i < g.yw) {
+        float gy[8];
+        IO<T, 8>::load(yrow + i * ldy, gy);
+#pragma unroll
+        for (int rh = 0; rh < 3; ++rh)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float v = xv[rh][i * S + q];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              acc2[rh * 3 + q][j] = ffma2(make_float2(v, v), make_float2(gy[2 * j], gy[2 * j + 1]), acc2[rh * 3 + q][j]);
+          }
+      }
+    }
+  }
+  float acc[kTaps * 8];
+#pragma unroll
+  for (int t = 0; t < kTaps; ++t)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[t * 8 + e] = (e & 1) ? acc2[t][e / 2].y : acc2[t][e / 2].x;
+  group_reduce<float, kTaps * 8>(acc, cv, smf);
+  for (int j = threadIdx.x; j < cv * kTaps * 8; j += kThreads) {
+    const int gq = j / (kTaps * 8), i = j - gq * (kTaps * 8);
+    const int t = i / 8, e = i - t * 8;
+    atomicAdd(&dw[(gq * 8 + e) * kTaps + t], group_total(smf, cv, kTaps * 8, j));
+  }
+}
+
+// Weight gradient of the 1 -> 1 stride-1 layer (the UNet's last convolution): dw[t] += sum_p y[p] * x[p - pad + t] over
+// two contiguous one-channel bf16 images.  A thread takes runs of 8 pixels: one 16-byte load of y, the 3 x 10 window of x
+// as vector loads, nine accumulators; block reduce, nine atomics per block.
+__global__ void __launch_bounds__(kThreads, 4)
+wgrad11_run_kernel(Geom g, const bf16* __restrict__ x, const bf16* __restrict__ y, float* __restrict__ dw) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float sred[(kThreads / 32) * kTaps];
+  constexpr int RUN = 8, WIN = 10;
+  const int rpr = g.yw / RUN;                       // yw % 8 == 0 (host)
+  const int nruns = g.n * g.yh * rpr;
+  float acc[kTaps];
+#pragma unroll
+  for (int t = 0; t < kTaps; ++t) acc[t] = 0.f;
+  for (int run = blockIdx.x * blockDim.x + threadIdx.x; run < nruns; run += gridDim.x * blockDim.x) {
+    const int rw = run % rpr;
+    const int rr = run / rpr;
+    const int h = rr % g.yh, img = rr / g.yh;
+    const int w0 = rw * RUN;
+    float xv[3][WIN];
+    if (g.pad == 1) load_window_vec<1, 1>(g, x, img, h, w0, xv);
+    else load_window_vec<1, 0>(g, x, img, h, w0, xv);
+    const uint4 u = *reinterpret_cast<const uint4*>(y + ((size_t)(img * g.yh + h) * g.yw + w0));
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < RUN; ++i) {
+      const float gy = (i & 1) ? __uint_as_float(uu[i / 2] & 0xffff0000u) : __uint_as_float(uu[i / 2] << 16);
+#pragma unroll
+      for (int rh = 0; rh < 3; ++rh)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) acc[rh * 3 + q] = fmaf(gy, xv[rh][i + q], acc[rh * 3 + q]);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < kTaps; ++t) {
+    const float v = warp_sum(acc[t]);
+    if (lane == 0) sred[warp * kTaps + t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kTaps) {
+    float v = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < kThreads / 32; ++wq) v += sred[wq * kTaps + threadIdx.x];
+    atomicAdd(&dw[threadIdx.x], v);
+  }
+}
+
 static bool geom_ok(const MpganConvGeom* g, Geom* o) {
   if (!g || g->rank != 2) return false;
   if (g->k[1] != 3 || g->k[2] != 3 || g->k[0] != 1) return false;
@@ -578,6 +749,7 @@ static bool geom_ok(const MpganConvGeom* g, Geom* o) {
   if (g->cx != 1) return false;
   o->n = g->n; o->xh = g->xs[1]; o->xw = g->xs[2]; o->yh = g->ys[1]; o->yw = g->ys[2];
   o->s = g->stride[1]; o->pad = g->pad[1]; o->C = g->cy;
+  o->vec = 0;
   return o->n > 0 && o->xh > 0 && o->xw > 0 && o->yh > 0 && o->yw > 0 && o->C > 0;
 }
 
@@ -596,6 +768,11 @@ static int grid_for(int64_t pixels, int cv, int per_thread, int bps) {
 }
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+static bool run_enabled() {   // MPGAN_NO_C1RUN=1: the pixel-at-a-time kernels (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MPGAN_NO_C1RUN"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
 
 // vector width usable for the C-channel tensor: 8 (C % 8 == 0, aligned), 1 (C == 1), 0 = not covered
 static int vec_of(int C, const void* p, int64_t ld) {
@@ -630,10 +807,13 @@ int c1f_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, con
   if (cv > 32 && (kThreads % cv) != 0) return 1;
   const int64_t P = (int64_t)q.n * q.yh * q.yw;
   if (!fits32(P, ldy) || !fits32((int64_t)q.n * q.xh * q.xw, ldx) || P * cv >= ((int64_t)1 << 30)) return 1;
-  if (V == 8 && q.s == 1 && cv <= 32 && (32 % cv) == 0) {   // run-based kernel (measured: a win for stride 1 only)
+  q.vec = (dtype == MPGAN_BF16 && ldx == 1 && q.xw % 8 == 0 && aligned16(x) && run_enabled()) ? 1 : 0;
+  // run-based kernel: a win for stride 1 always, for stride 2 when the window loads are 16-byte vectors
+  if (V == 8 && (q.s == 1 || q.vec) && cv <= 32 && (32 % cv) == 0) {
     const int run = q.s == 1 ? 8 : 4;
     const int64_t nruns = (int64_t)q.n * q.yh * ((q.yw + run - 1) / run);
-    const int gridr = grid_for(nruns, cv, 2, 4);
+    const int gridr = q.vec ? grid_for(nruns, cv, 4, 2) : grid_for(nruns, cv, 2, 4);   // fewer, fatter threads: the 72-weight
+                                                                                      // prologue and the statistics reduce are per thread
     MPGAN_DISPATCH_DTYPE(dtype, T, {
       if (q.s == 1) launch_k(fprop_run_kernel<T, 1>, gridr, kThreads, 0, s, q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y, (int)ldy, stats);
       else launch_k(fprop_run_kernel<T, 2>, gridr, kThreads, 0, s, q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y, (int)ldy, stats);
@@ -692,6 +872,27 @@ int c1f_wgrad(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, con
   const int64_t P = (int64_t)q.n * q.yh * q.yw;
   if (!fits32(P, ldy) || !fits32((int64_t)q.n * q.xh * q.xw, ldx) || P * cv >= ((int64_t)1 << 30)) return 1;
   const size_t smem = (size_t)(kThreads / 32) * cv * kTaps * V * sizeof(float);
+  q.vec = (dtype == MPGAN_BF16 && ldx == 1 && q.xw % 8 == 0 && aligned16(x) && run_enabled()) ? 1 : 0;
+  if (V == 1 && q.C == 1 && q.vec && q.s == 1 && ldy == 1 && q.yw % 8 == 0 && aligned16(y) && q.yw == q.xw + 2 * q.pad - 2 &&
+      q.xw >= 16) {
+    const int64_t nruns = (int64_t)q.n * q.yh * (q.yw / 8);
+    int grid11 = (int)ceil_div(nruns, (int64_t)kThreads * 2);
+    if (grid11 > num_sms() * 4) grid11 = num_sms() * 4;
+    launch_k(wgrad11_run_kernel, grid11, kThreads, 0, s, q, (const bf16*)x, (const bf16*)y, dw);
+    MPGAN_CHECK_LAUNCH("c1f_wgrad11_run");
+    return 0;
+  }
+  if (V == 8 && q.vec) {   // run-based kernel with vector window loads
+    const int run = q.s == 1 ? 8 : 4;
+    const int64_t nruns = (int64_t)q.n * q.yh * ((q.yw + run - 1) / run);
+    const int gridr = grid_for(nruns, cv, 4, 2);
+    MPGAN_DISPATCH_DTYPE(dtype, T, {
+      if (q.s == 1) launch_k(wgrad_run_kernel<T, 1>, gridr, kThreads, smem, s, q, (const T*)x, (int)ldx, (const T*)y, (int)ldy, dw);
+      else launch_k(wgrad_run_kernel<T, 2>, gridr, kThreads, smem, s, q, (const T*)x, (int)ldx, (const T*)y, (int)ldy, dw);
+      MPGAN_CHECK_LAUNCH("c1f_wgrad_run");
+      return 0;
+    });
+  }
   const int grid = grid_for(P, cv, 32, 4);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     C1F_LAUNCH(wgrad_kernel, V, q.s, grid, smem, s, q, (const T*)x, (int)ldx, (const T*)y, (int)ldy, dw);

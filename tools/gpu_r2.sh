@@ -34,6 +34,9 @@ for w in $WHAT; do
              done;;
     opsw)    # A/B of the halo weight-gradient kernel
              for e in 0 1; do echo "== MPGAN_NO_WGRAD_HALO=$e"; MPGAN_NO_WGRAD_HALO=$e timeout 600 python tools/bench_ops.py g_16_16 g_16_32 g_32_32 g_32_64 gT_16 2>&1 | grep wgrad | tee -a gpurun_out/opsw_$TAG.log; done;;
+    opsc1)   # A/B of the run-based one-channel kernels with vector window loads
+             for e in 0 1; do echo "== MPGAN_NO_C1RUN=$e"; MPGAN_NO_C1RUN=$e timeout 600 python tools/bench_ops.py c1_g1 c1_gT c1_11 2>&1 | tee -a gpurun_out/opsc1_$TAG.log; done
+             echo "== inference size"; OPS_BATCH=64 OPS_SCALE=2 timeout 600 python tools/bench_ops.py c1_g1 c1_gT c1_11 2>&1 | tee -a gpurun_out/opsc1_$TAG.log;;
     k3d)     timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 600 -k "tc3" > gpurun_out/pytest_k3d_$TAG.log 2>&1
              echo "k3d exit $?"; tail -30 gpurun_out/pytest_k3d_$TAG.log;;
     n3d)     timeout 900 python -m pytest tests/test_nets_gpu.py -m gpu -q --timeout 600 -k "3" > gpurun_out/pytest_n3d_$TAG.log 2>&1
