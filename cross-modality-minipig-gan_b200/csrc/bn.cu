@@ -578,6 +578,33 @@ namespace mpgan {
 // bf16 exactly as the unfused path stores it) and produces 4 output pixels; h itself is written only when the
 // backward pass needs it.  Block 0 updates the running statistics and the saved mean / invstd / scale / shift.
 // ------------------------------------------------------------------------------------------------------------
+// one window row of a contiguous one-channel bf16 image: columns w0 - 1 .. w0 + RUN, zero outside the image.  RUN == 8
+// (W % 8 == 0, 16-byte aligned image): the eight inner columns are one vector load.
+template <int RUN>
+__device__ __forceinline__ void tail_load_row(const bf16* __restrict__ img, int y, int w0, int H, int W, float (&v)[RUN + 2]) {
+  const bool oky = (unsigned)y < (unsigned)H;
+  const bf16* row = img + (int64_t)(oky ? y : 0) * W;
+  if constexpr (RUN == 8) {
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (oky) u = *reinterpret_cast<const uint4*>(row + w0);
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[1 + 2 * e] = __uint_as_float(uu[e] << 16);
+      v[2 + 2 * e] = __uint_as_float(uu[e] & 0xffff0000u);
+    }
+    v[0] = (oky && w0 > 0) ? to_f(row[w0 - 1]) : 0.f;
+    v[9] = (oky && w0 + 8 < W) ? to_f(row[w0 + 8]) : 0.f;
+  } else {
+#pragma unroll
+    for (int j = 0; j < RUN + 2; ++j) {
+      const int x = w0 - 1 + j;
+      v[j] = (oky && (unsigned)x < (unsigned)W) ? to_f(row[x]) : 0.f;
+    }
+  }
+}
+
+template <int RUN>
 __global__ void __launch_bounds__(kThreads)
 c1_tail_fwd_kernel(const bf16* __restrict__ c, int n, int H, int W, const BnTrain f, const float* __restrict__ alpha,
                    const bf16* __restrict__ w9, const float* __restrict__ bias, bf16* __restrict__ h_out,
@@ -586,49 +613,77 @@ c1_tail_fwd_kernel(const bf16* __restrict__ c, int n, int H, int W, const BnTrai
   pdl_launch();
   const int64_t P = (int64_t)n * H * W;
   float sc, sh;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && f.nbt) *f.nbt += 1;
-  bn_train_coeffs(f, 0, 1, P, blockIdx.x == 0 && threadIdx.x == 0, sc, sh);
+  if (f.stats) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && f.nbt) *f.nbt += 1;
+    bn_train_coeffs(f, 0, 1, P, blockIdx.x == 0 && threadIdx.x == 0, sc, sh);
+  } else {          // evaluation mode: scale / shift of the running statistics are given (mpgan_bn_finalize)
+    sc = f.scale_out[0];
+    sh = f.shift_out[0];
+  }
   const float slope = *alpha;
   float wt[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) wt[t] = to_f(w9[t]);
   const float b = bias ? bias[0] : 0.f;
-  const int wq = (W + 3) / 4;                       // 4-pixel runs per row
+  const int wq = (W + RUN - 1) / RUN;               // RUN-pixel runs per row
   const int64_t runs = (int64_t)n * H * wq;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < runs; r += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(r % wq);
     const int64_t row = r / wq;
     const int hh = (int)(row % H), img = (int)(row / H);
-    const int w0 = q * 4;
+    const int w0 = q * RUN;
     const bf16* ci = c + (int64_t)img * H * W;
-    float hv[3][6];
+    float hv[3][RUN + 2];
 #pragma unroll
     for (int rh = 0; rh < 3; ++rh) {
       const int y = hh - 1 + rh;
+      tail_load_row<RUN>(ci, y, w0, H, W, hv[rh]);
       const bool oky = (unsigned)y < (unsigned)H;
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
+      for (int j = 0; j < RUN + 2; ++j) {
         const int x = w0 - 1 + j;
         float v = 0.f;
         if (oky && (unsigned)x < (unsigned)W) {
-          const float z = fmaf(to_f(ci[(int64_t)y * W + x]), sc, sh);
+          const float z = fmaf(hv[rh][j], sc, sh);
           v = to_f(from_f<bf16>(z > 0.f ? z : slope * z));     // h as the unfused path stores it
         }
         hv[rh][j] = v;
       }
     }
+    const int64_t o0 = ((int64_t)img * H + hh) * W + w0;
+    if constexpr (RUN == 8) {
+      uint32_t hp[4], yp[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (w0 + i >= W) break;
-      float a = b;
+      for (int i = 0; i < 8; i += 2) {
+        float a0 = b, a1 = b;
 #pragma unroll
-      for (int rh = 0; rh < 3; ++rh)
+        for (int rh = 0; rh < 3; ++rh)
 #pragma unroll
-        for (int rw = 0; rw < 3; ++rw) a = fmaf(hv[rh][i + rw], wt[rh * 3 + rw], a);
-      const float hc = hv[1][i + 1];
-      const int64_t o = ((int64_t)img * H + hh) * W + w0 + i;
-      if (h_out) h_out[o] = from_f<bf16>(hc);
-      y_out[o] = from_f<bf16>(to_f(from_f<bf16>(a)) + hc);     // conv result rounded, then the residual add (two kernels before)
+          for (int rw = 0; rw < 3; ++rw) {
+            a0 = fmaf(hv[rh][i + rw], wt[rh * 3 + rw], a0);
+            a1 = fmaf(hv[rh][i + 1 + rw], wt[rh * 3 + rw], a1);
+          }
+        const float h0 = hv[1][i + 1], h1 = hv[1][i + 2];
+        __nv_bfloat162 hh2 = __floats2bfloat162_rn(h0, h1);
+        __nv_bfloat162 yy2 = __floats2bfloat162_rn(to_f(from_f<bf16>(a0)) + h0, to_f(from_f<bf16>(a1)) + h1);
+        hp[i / 2] = *reinterpret_cast<uint32_t*>(&hh2);
+        yp[i / 2] = *reinterpret_cast<uint32_t*>(&yy2);
+      }
+      if (h_out) *reinterpret_cast<uint4*>(h_out + o0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      *reinterpret_cast<uint4*>(y_out + o0) = make_uint4(yp[0], yp[1], yp[2], yp[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < RUN; ++i) {
+        if (w0 + i >= W) break;
+        float a = b;
+#pragma unroll
+        for (int rh = 0; rh < 3; ++rh)
+#pragma unroll
+          for (int rw = 0; rw < 3; ++rw) a = fmaf(hv[rh][i + rw], wt[rh * 3 + rw], a);
+        const float hc = hv[1][i + 1];
+        if (h_out) h_out[o0 + i] = from_f<bf16>(hc);
+        y_out[o0 + i] = from_f<bf16>(to_f(from_f<bf16>(a)) + hc);     // conv result rounded, then the residual add (two kernels before)
+      }
     }
   }
 }
@@ -640,6 +695,7 @@ c1_tail_fwd_kernel(const bf16* __restrict__ c, int n, int H, int W, const BnTrai
 // and, in the same pass, the BatchNorm(1) + PReLU backward REDUCTION of the layer below it:
 //   sums[0] += sum dz,  sums[1] += sum dz * xhat,  sums[2] += sum_{z<=0} dh * z      with z = c*scale + shift, dz = dh * prelu'(z)
 // (replaces c1f::bprop_kernel<1,1> + add_copy + bn_act_bwd_reduce_kernel<1>: three launches on the backward critical path).
+template <int RUN>
 __global__ void __launch_bounds__(kThreads)
 c1_tail_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ c, int n, int H, int W,
                           const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
@@ -652,28 +708,20 @@ c1_tail_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
   float wt[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) wt[t] = to_f(w9[8 - t]);      // flipped taps: dh[q] = sum_t w[8 - t] * dy[q - 1 + t]
-  const int wq = (W + 3) / 4;
+  const int wq = (W + RUN - 1) / RUN;
   const int64_t runs = (int64_t)n * H * wq;
   float a0 = 0.f, a1 = 0.f, fs = 0.f;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < runs; r += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(r % wq);
     const int64_t row = r / wq;
     const int hh = (int)(row % H), img = (int)(row / H);
-    const int w0 = q * 4;
+    const int w0 = q * RUN;
     const bf16* di = dy + (int64_t)img * H * W;
-    float dv[3][6];
+    float dv[3][RUN + 2];
 #pragma unroll
-    for (int rh = 0; rh < 3; ++rh) {
-      const int y = hh - 1 + rh;
-      const bool oky = (unsigned)y < (unsigned)H;
+    for (int rh = 0; rh < 3; ++rh) tail_load_row<RUN>(di, hh - 1 + rh, w0, H, W, dv[rh]);
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const int x = w0 - 1 + j;
-        dv[rh][j] = (oky && (unsigned)x < (unsigned)W) ? to_f(di[(int64_t)y * W + x]) : 0.f;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < RUN; ++i) {
       if (w0 + i >= W) break;
       float acc = 0.f;
 #pragma unroll
@@ -709,19 +757,26 @@ extern "C" int mpgan_c1_tail_fwd(const void* c_bf16, int32_t n, int32_t h, int32
                                  float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd,
                                  float* scale, float* shift, const float* alpha, const void* w9_bf16, const float* bias,
                                  void* h_out_bf16, void* y_out_bf16, void* stream) {
-  MPGAN_REQUIRE(c_bf16 && stats && scale && shift && alpha && w9_bf16 && y_out_bf16, MPGAN_ERR_SHAPE,
-                "c1_tail_fwd: null pointer");
+  // stats == nullptr: evaluation mode, scale / shift are INPUTS and no running statistic is touched
+  MPGAN_REQUIRE(c_bf16 && scale && shift && alpha && w9_bf16 && y_out_bf16, MPGAN_ERR_SHAPE, "c1_tail_fwd: null pointer");
   MPGAN_REQUIRE(n > 0 && h > 0 && w > 0, MPGAN_ERR_SHAPE, "c1_tail_fwd: empty tensor");
   BnTrain f;
   f.stats = stats; f.gamma = gamma; f.beta = beta; f.eps = eps; f.momentum = momentum;
   f.running_mean = running_mean; f.running_var = running_var; f.nbt = num_batches_tracked;
   f.mean_out = mean; f.invstd_out = invstd; f.scale_out = scale; f.shift_out = shift;
-  const int64_t runs = (int64_t)n * h * ((w + 3) / 4);
+  // rows of 8k pixels in 16-byte aligned images: 8-pixel runs with vector loads / stores
+  const bool vec = w % 8 == 0 && ((uintptr_t)c_bf16 & 15) == 0 && ((uintptr_t)y_out_bf16 & 15) == 0 &&
+                   ((uintptr_t)h_out_bf16 & 15) == 0;
+  const int64_t runs = (int64_t)n * h * ((w + (vec ? 7 : 3)) / (vec ? 8 : 4));
   int64_t blocks = ceil_div(runs, (int64_t)kThreads);
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  launch_k(c1_tail_fwd_kernel, (int)blocks, kThreads, 0, (cudaStream_t)stream, (const bf16*)c_bf16, (int)n, (int)h, (int)w, f,
-           alpha, (const bf16*)w9_bf16, bias, (bf16*)h_out_bf16, (bf16*)y_out_bf16);
+  if (vec)
+    launch_k(c1_tail_fwd_kernel<8>, (int)blocks, kThreads, 0, (cudaStream_t)stream, (const bf16*)c_bf16, (int)n, (int)h, (int)w, f,
+             alpha, (const bf16*)w9_bf16, bias, (bf16*)h_out_bf16, (bf16*)y_out_bf16);
+  else
+    launch_k(c1_tail_fwd_kernel<4>, (int)blocks, kThreads, 0, (cudaStream_t)stream, (const bf16*)c_bf16, (int)n, (int)h, (int)w, f,
+             alpha, (const bf16*)w9_bf16, bias, (bf16*)h_out_bf16, (bf16*)y_out_bf16);
   MPGAN_CHECK_LAUNCH("c1_tail_fwd_kernel");
   return 0;
 }
@@ -733,13 +788,19 @@ extern "C" int mpgan_c1_tail_bwd_reduce(const void* dy_bf16, const void* c_bf16,
   MPGAN_REQUIRE(dy_bf16 && c_bf16 && mean && invstd && scale && shift && alpha && w9_bf16 && dh_bf16 && sums3,
                 MPGAN_ERR_SHAPE, "c1_tail_bwd_reduce: null pointer");
   MPGAN_REQUIRE(n > 0 && h > 0 && w > 0, MPGAN_ERR_SHAPE, "c1_tail_bwd_reduce: empty tensor");
-  const int64_t runs = (int64_t)n * h * ((w + 3) / 4);
+  const bool vec = w % 8 == 0 && ((uintptr_t)dy_bf16 & 15) == 0;
+  const int64_t runs = (int64_t)n * h * ((w + (vec ? 7 : 3)) / (vec ? 8 : 4));
   int64_t blocks = ceil_div(runs, (int64_t)kThreads * 2);
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  launch_k(c1_tail_bwd_reduce_kernel, (int)blocks, kThreads, 0, (cudaStream_t)stream, (const bf16*)dy_bf16,
-           (const bf16*)c_bf16, (int)n, (int)h, (int)w, mean, invstd, scale, shift, alpha, (const bf16*)w9_bf16,
-           (bf16*)dh_bf16, sums3);
+  if (vec)
+    launch_k(c1_tail_bwd_reduce_kernel<8>, (int)blocks, kThreads, 0, (cudaStream_t)stream, (const bf16*)dy_bf16,
+             (const bf16*)c_bf16, (int)n, (int)h, (int)w, mean, invstd, scale, shift, alpha, (const bf16*)w9_bf16,
+             (bf16*)dh_bf16, sums3);
+  else
+    launch_k(c1_tail_bwd_reduce_kernel<4>, (int)blocks, kThreads, 0, (cudaStream_t)stream, (const bf16*)dy_bf16,
+             (const bf16*)c_bf16, (int)n, (int)h, (int)w, mean, invstd, scale, shift, alpha, (const bf16*)w9_bf16,
+             (bf16*)dh_bf16, sums3);
   MPGAN_CHECK_LAUNCH("c1_tail_bwd_reduce_kernel");
   return 0;
 }

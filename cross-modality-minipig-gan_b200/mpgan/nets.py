@@ -408,11 +408,20 @@ class UNet(nn.Module):
         only) run as the ConvTranspose (with fused statistics) plus ONE stencil kernel; the tape is the one the
         unfused layers would have recorded.  Returns None when the pattern does not apply."""
         conv0, ru = up[0], up[1]
-        if (out is not None or not plan.training or plan.dtype != torch.bfloat16 or conv0.out_channels != 1
+        if (out is not None or plan.dtype != torch.bfloat16 or conv0.out_channels != 1
                 or conv0.conv_only or cat.dim() != 4 or len(ru.conv) != 1 or not ru.conv[0].conv_only
                 or not isinstance(ru.residual, nn.Identity) or os.environ.get("MPGAN_NO_TAIL_FUSION", "0") == "1"):
             return None
         rec0, rec1 = plan.rt.rec[conv0.conv], plan.rt.rec[ru.conv[0].conv]
+        if not plan.training:
+            # evaluation mode (inference): the same stencil kernel with the scale / shift of the running statistics
+            if plan.save:
+                return None
+            c, _ = conv_apply(rec0, cat)
+            saved = torch.empty((4, 1), dtype=torch.float32, device=c.device)
+            ops.bn_finalize(None, ops.pixels(c), conv0.norm, False, saved[0], saved[1], saved[2], saved[3])
+            _, y = ops.c1_tail_fwd(c, None, conv0.norm, saved, conv0.act.weight, rec1.w, rec1.bias, False)
+            return y
         stats = plan.zeros64(2, cat.device)
         c, fused_stats = conv_apply(rec0, cat, stats=stats)
         if not fused_stats:

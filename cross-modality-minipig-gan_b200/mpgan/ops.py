@@ -364,7 +364,8 @@ def bn_train_apply(x, stats, bn, saved, act, alpha, leaky, res, out):
 
 
 def c1_tail_fwd(c, stats, bn, saved, alpha, w9, bias, want_h):
-    """Fused UNet tail on a one-channel bf16 image (n, h, w, 1): returns (hmap or None, y)."""
+    """Fused UNet tail on a one-channel bf16 image (n, h, w, 1): returns (hmap or None, y).  ``stats=None``:
+    evaluation mode -- ``saved[2]`` / ``saved[3]`` hold the scale / shift of the running statistics (``bn_finalize``)."""
     lib = _lib.require_device()
     assert c.dtype == torch.bfloat16 and c.is_contiguous() and c.shape[-1] == 1 and c.dim() == 4
     n, h, w = c.shape[0], c.shape[1], c.shape[2]

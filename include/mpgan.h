@@ -218,7 +218,8 @@ int mpgan_patch_scatter_add(int dtype, const void* dpatch, int32_t batch, int32_
  * conv only), call site GAN_final.py:106-114) on a one-channel (n, h, w) bf16 image, training mode:
  *   hmap = prelu(batchnorm(c));  y = conv3x3(hmap, w9, pad 1) + bias + hmap
  * stats: the fp64 {sum, sum of squares} of c; running statistics / saved mean, invstd, scale, shift are updated as by
- * mpgan_bn_train_apply.  h_out may be NULL (no backward pass will follow). */
+ * mpgan_bn_train_apply.  h_out may be NULL (no backward pass will follow).  stats == NULL: evaluation mode -- scale /
+ * shift are INPUTS (mpgan_bn_finalize of the running statistics) and no statistic is written. */
 int mpgan_c1_tail_fwd(const void* c_bf16, int32_t n, int32_t h, int32_t w, const double* stats, const float* gamma,
                       const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                       int64_t* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
