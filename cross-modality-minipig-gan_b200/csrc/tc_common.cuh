@@ -221,31 +221,48 @@ __device__ __forceinline__ void epi_chunk_store_rq(const uint32_t (&r)[CH], cons
                                                    bool do_stats, unsigned long long (&s1)[CH / 2],
                                                    unsigned long long (&s2)[CH / 2], const uint32_t (&rq)[CH / 2],
                                                    bool has_res, bool wide = false, const float* slope = nullptr) {
+  // All flags are warp-uniform.  The residual is folded in without per-column branches (a missing residual is a row of
+  // zeros) and the activation is ONE uniform branch around two straight-line loops: the previous form (a branch per
+  // group of four columns) made this epilogue ~250 dependent instructions per 16-column tile, which bounded the
+  // 16-channel layers (ncu source view: the MMA issuer spinning on the accumulator-empty barrier).
   const unsigned long long ones = pack_f32x2(1.f, 1.f);
   uint32_t packed[CH / 2];
-  const bool has_act = slope != nullptr;
-  const float a = has_act ? __ldg(slope) : 1.f;
+  uint32_t q[CH / 2];
 #pragma unroll
-  for (int j = 0; j < CH / 4; ++j) {
-    float4 b = *reinterpret_cast<const float4*>(s_bias_c0 + 4 * j);
-    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_res) {
-      rr.x = __uint_as_float(rq[2 * j] << 16); rr.y = __uint_as_float(rq[2 * j] & 0xffff0000u);
-      rr.z = __uint_as_float(rq[2 * j + 1] << 16); rr.w = __uint_as_float(rq[2 * j + 1] & 0xffff0000u);
-      if (!has_act) { b.x += rr.x; b.y += rr.y; b.z += rr.z; b.w += rr.w; }
+  for (int j = 0; j < CH / 2; ++j) q[j] = has_res ? rq[j] : 0u;
+  if (slope != nullptr) {
+    const float a = __ldg(slope);
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) {
+      const float4 b = *reinterpret_cast<const float4*>(s_bias_c0 + 4 * j);
+      float2 v0 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), ones,
+                                         pack_f32x2(b.x, b.y)));
+      float2 v1 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), ones,
+                                         pack_f32x2(b.z, b.w)));
+      v0.x = (v0.x > 0.f ? v0.x : a * v0.x) + __uint_as_float(q[2 * j] << 16);
+      v0.y = (v0.y > 0.f ? v0.y : a * v0.y) + __uint_as_float(q[2 * j] & 0xffff0000u);
+      v1.x = (v1.x > 0.f ? v1.x : a * v1.x) + __uint_as_float(q[2 * j + 1] << 16);
+      v1.y = (v1.y > 0.f ? v1.y : a * v1.y) + __uint_as_float(q[2 * j + 1] & 0xffff0000u);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(v1.x, v1.y);
+      packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+      packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
     }
-    float2 v0 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), ones,
-                                       pack_f32x2(b.x, b.y)));
-    float2 v1 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), ones,
-                                       pack_f32x2(b.z, b.w)));
-    if (has_act) {
-      v0.x = (v0.x > 0.f ? v0.x : a * v0.x) + rr.x; v0.y = (v0.y > 0.f ? v0.y : a * v0.y) + rr.y;
-      v1.x = (v1.x > 0.f ? v1.x : a * v1.x) + rr.z; v1.y = (v1.y > 0.f ? v1.y : a * v1.y) + rr.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) {
+      float4 b = *reinterpret_cast<const float4*>(s_bias_c0 + 4 * j);
+      b.x += __uint_as_float(q[2 * j] << 16); b.y += __uint_as_float(q[2 * j] & 0xffff0000u);
+      b.z += __uint_as_float(q[2 * j + 1] << 16); b.w += __uint_as_float(q[2 * j + 1] & 0xffff0000u);
+      const float2 v0 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), ones,
+                                               pack_f32x2(b.x, b.y)));
+      const float2 v1 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), ones,
+                                               pack_f32x2(b.z, b.w)));
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(v1.x, v1.y);
+      packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+      packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
     }
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y);
-    __nv_bfloat162 h1 = __floats2bfloat162_rn(v1.x, v1.y);
-    packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
-    packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
   }
   if (valid) {
     if (wide) {   // row address 32-byte aligned
