@@ -151,8 +151,16 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int tiles_per_img = P.tiles_w * P.tiles_h;
+  if constexpr (N >= 128) {
+    // Register re-partition (setmaxnreg): the producer / issuer warpgroup gives up registers so that every epilogue thread
+    // can keep the BatchNorm statistics of its 64 columns in 128 fp32 registers for the whole kernel -- the per-chunk warp
+    // transpose-reductions they replace were 60 % of the 11 500 warp-instructions per tile that made D layer 2's forward
+    // epilogue-bound (ncu: 39.5 % tensor-pipe active, the MMA issuer spinning on the accumulator-empty barrier).
+    // (the instructions sit at the head of the two role regions below)
+  }
 
+  if (warp < 4) {
+  if constexpr (N >= 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     if (elect_one()) {  // ================= TMA producer: one box per (tile, 64-channel plane) =================
       int pbuf = 0;
@@ -222,7 +230,9 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         for (int i = 1; i < nissue; ++i) skip_tile();
       }
     }
-  } else if (warp >= 4) {  // ================= epilogue (8 warps) =================
+  }
+  } else {  // ================= epilogue (8 warps) =================
+    if constexpr (N >= 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int ew = warp - 4;
     const int q = ew & 3;          // TMEM lane quarter (== warp % 4)
     const int half = ew >> 2;      // alternating column chunks
@@ -309,6 +319,20 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
         if (lane < CH) { sl[c0 + lane] = t1; sl[N + c0 + lane] = t2; }
       }
     } else {
+    // N = 128: both warp groups take every tile, two 32-column chunks each (columns half * 32 + {0, 64}); the statistics
+    // of those 64 columns live in per-thread packed fp32 registers (thread = tile row, fixed tile order => reproducible)
+    // and are transposed / reduced ONCE, after the last tile.
+    static_assert(CH == 32, "N = 128 path works on 32-column chunks");
+    constexpr int NCK = N / (2 * CH);                  // chunks per thread: 2
+    unsigned long long S1[NCK][CH / 2], S2[NCK][CH / 2];
+#pragma unroll
+    for (int k = 0; k < NCK; ++k)
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) { S1[k][j] = 0ull; S2[k][j] = 0ull; }
+    const unsigned long long ones = pack_f32x2(1.f, 1.f);
+    const bool has_slope = P.slope != nullptr;
+    const float slope_a = has_slope ? __ldg(P.slope) : 1.f;
+    const bool do_stats = P.stats != nullptr;
     int it = 0;
     TileWalk<3> tw;
     { const int radix[3] = {P.tiles_w, P.tiles_h, 1 << 30}; tw.init((int)blockIdx.x, (int)gridDim.x, radix); }
@@ -322,28 +346,45 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
       mbar_wait(&tfull[acc], par);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
-      const bool has_slope = P.slope != nullptr;
-      const float slope_a = has_slope ? __ldg(P.slope) : 1.f;
       const bf16* res_row = (P.res && valid) ? P.res + (long long)img * P.res_sn + (long long)oh * P.res_sh + (long long)ow * P.res_sw
                                              : nullptr;
-#pragma unroll 1
-      for (int c0 = half * CH; c0 < N; c0 += 2 * CH) {
-        uint32_t r[32];
-        if (CH == 32) tmem_ld_32x32(t_addr + c0, r);
-        else tmem_ld_32x16(t_addr + c0, r);
-        tmem_ld_wait();
-        uint32_t packed[CH / 2];
 #pragma unroll
-        for (int j = 0; j < CH / 2; ++j) {
-          float f0 = __uint_as_float(r[2 * j]), f1 = __uint_as_float(r[2 * j + 1]);
-          f0 += s_bias[c0 + 2 * j]; f1 += s_bias[c0 + 2 * j + 1];
-          if (has_slope) { f0 = f0 > 0.f ? f0 : slope_a * f0; f1 = f1 > 0.f ? f1 : slope_a * f1; }
-          if (res_row) {
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(res_row + c0 + 2 * j);
-            f0 += __uint_as_float(u << 16); f1 += __uint_as_float(u & 0xffff0000u);
+      for (int k = 0; k < NCK; ++k) {
+        const int c0 = half * CH + k * 2 * CH;
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c0, r);
+        tmem_ld_wait();
+        if (k == NCK - 1) {   // the accumulator is in registers: hand it back before the arithmetic
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        uint32_t packed[CH / 2];
+        if (!has_slope && res_row == nullptr) {      // training forward: bias only (uniform branch)
+#pragma unroll
+          for (int j = 0; j < CH / 4; ++j) {
+            const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j);
+            const float2 v0 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), ones,
+                                                     pack_f32x2(b.x, b.y)));
+            const float2 v1 = unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), ones,
+                                                     pack_f32x2(b.z, b.w)));
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y), h1 = __floats2bfloat162_rn(v1.x, v1.y);
+            packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+            packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
           }
-          __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-          packed[j] = *reinterpret_cast<uint32_t*>(&h);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) {
+            float f0 = __uint_as_float(r[2 * j]), f1 = __uint_as_float(r[2 * j + 1]);
+            f0 += s_bias[c0 + 2 * j]; f1 += s_bias[c0 + 2 * j + 1];
+            if (has_slope) { f0 = f0 > 0.f ? f0 : slope_a * f0; f1 = f1 > 0.f ? f1 : slope_a * f1; }
+            if (res_row) {
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(res_row + c0 + 2 * j);
+              f0 += __uint_as_float(u << 16); f1 += __uint_as_float(u & 0xffff0000u);
+            }
+            __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+            packed[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
         }
         if (valid) {
           if (P.wide) {
@@ -357,28 +398,31 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
               *reinterpret_cast<uint4*>(orow + c0 + j * 8) =
                   make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
           }
-        }
-        if (P.stats) {  // statistics of the values as stored: register transpose-reduce (lane l ends up with column c0 + l)
-          float v[32], sq[32];
+          if (do_stats) {  // statistics of the values as stored
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint32_t u = (j < CH / 2 && valid) ? packed[j < CH / 2 ? j : 0] : 0u;
-            v[2 * j] = __uint_as_float(u << 16);
-            v[2 * j + 1] = __uint_as_float(u & 0xffff0000u);
-            sq[2 * j] = v[2 * j] * v[2 * j];
-            sq[2 * j + 1] = v[2 * j + 1] * v[2 * j + 1];
-          }
-          const float t1 = warp_transpose_reduce32(v, lane);
-          const float t2 = warp_transpose_reduce32(sq, lane);
-          if (lane < CH) {   // slots owned by (this warp, this lane): fixed accumulation order
-            sl[c0 + lane] += t1;
-            sl[N + c0 + lane] += t2;
+            for (int j = 0; j < CH / 2; ++j) {
+              const unsigned long long f = pack_f32x2(__uint_as_float(packed[j] << 16), __uint_as_float(packed[j] & 0xffff0000u));
+              S1[k][j] = fma_f32x2(f, ones, S1[k][j]);
+              S2[k][j] = fma_f32x2(f, f, S2[k][j]);
+            }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    if (do_stats) {
+#pragma unroll
+      for (int k = 0; k < NCK; ++k) {
+        const int c0 = half * CH + k * 2 * CH;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (j & 1) ? unpack_f32x2(S1[k][j / 2]).y : unpack_f32x2(S1[k][j / 2]).x;
+        const float t1 = warp_transpose_reduce32(v, lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (j & 1) ? unpack_f32x2(S2[k][j / 2]).y : unpack_f32x2(S2[k][j / 2]).x;
+        const float t2 = warp_transpose_reduce32(v, lane);
+        sl[c0 + lane] = t1;
+        sl[N + c0 + lane] = t2;
+      }
     }
     }
   }
