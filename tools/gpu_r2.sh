@@ -44,7 +44,7 @@ for w in $WHAT; do
     b3d)     timeout 900 python tools/bench_3d.py ${B3D_ARGS:-1 3 128} > gpurun_out/bench3d_$TAG.log 2> gpurun_out/bench3d_$TAG.err
              echo "b3d exit $?"; cat gpurun_out/bench3d_$TAG.log; tail -5 gpurun_out/bench3d_$TAG.err;;
     ncud)    timeout 600 python tools/d_convs_once.py > gpurun_out/plain_dconv_$TAG.log 2>&1 &&
-             timeout 1500 ncu --set full --clock-control none --profile-from-start off -k regex:"tapgemm|halo3x3|wgrad_kernel" \
+             timeout 1500 ncu --set full --clock-control none --profile-from-start off -k regex:"tapgemm|halo3x3|wgrad" \
                  -o /tmp/dconvs_$TAG -f python tools/d_convs_once.py > gpurun_out/ncu_dconv_$TAG.log 2>&1
              echo "ncud exit $?"; ls -la /tmp/dconvs_$TAG.ncu-rep
              ncu -i /tmp/dconvs_$TAG.ncu-rep --page raw --csv > gpurun_out/dconvs_$TAG.csv 2> gpurun_out/dconvs_csv_$TAG.err; wc -c gpurun_out/dconvs_$TAG.csv;;

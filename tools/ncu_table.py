@@ -18,7 +18,7 @@ LAYERS = [("D2", 64, 128, 3, 254, 252), ("D3", 128, 256, 4, 252, 125), ("D4", 25
 pk = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
 print("# ncu `--set full` over the nine FLOP-dominant launches (D layers 2-4 x fprop / dgrad / wgrad), batch 32, bf16\n")
 print(f"command (one B200, after the plain run of the same command had exited 0): `ncu --set full --clock-control none "
-      f"--profile-from-start off -k regex:\"tapgemm|halo3x3|wgrad_kernel\" python tools/d_convs_once.py`; the third launch of "
+      f"--profile-from-start off -k regex:\"tapgemm|halo3x3|wgrad\" python tools/d_convs_once.py`; the third launch of "
       "each kind is captured (two warm-ups before it, outside the cudaProfilerStart / Stop window).  Times under a profiler are not bench values (`bench.py` / "
       "`tools/bench_ops.py` hold those); the tensor-pipe and DRAM columns are what this table is for.  fprop launches carry the fused "
       "BatchNorm statistics, data gradients do not (as in the training step).\n")

@@ -22,7 +22,9 @@ def main(path, out=None, title=""):
         tot[name] += t
         cnt[name] += 1
     s = sum(tot.values())
-    rows = [f"# {title}", "", f"source: `{path}` ({sum(cnt.values())} launches, {s / 1e6:.2f} ms summed device time; ncu "
+    import os
+    shown = os.path.relpath(path, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))) if os.path.isabs(path) else path
+    rows = [f"# {title}", "", f"source: `{shown}` ({sum(cnt.values())} launches, {s / 1e6:.2f} ms summed device time; ncu "
             "serialises launches and runs them cold-cache, so read SHARES, not absolutes)", "",
             "| ms | share | launches | kernel |", "|---:|---:|---:|---|"]
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
