@@ -7,9 +7,9 @@ Arithmetic runs in libmpgan_sm100.so (hand-written CUDA, C ABI in include/mpgan.
 memory, streams and torch.distributed only.  There is no CPU fallback.
 """
 from . import _lib, ops  # noqa: F401
-from .gan import GAN  # noqa: F401
+from .gan import GAN, HostFedStep  # noqa: F401
 from .nets import CasNetGenerator, Discriminator, PatchDiscriminator, UNet, DEFAULT_PRECISION  # noqa: F401
 from .runtime import FlatAdam, Runtime  # noqa: F401
 from . import inference, transforms  # noqa: F401,E402
 
-__all__ = ["GAN", "CasNetGenerator", "Discriminator", "PatchDiscriminator", "UNet", "FlatAdam", "Runtime"]
+__all__ = ["GAN", "HostFedStep", "CasNetGenerator", "Discriminator", "PatchDiscriminator", "UNet", "FlatAdam", "Runtime"]

@@ -533,6 +533,45 @@ class GAN(_Base):
             rt.refresh_shadows(force=True)
 
 
+class HostFedStep:
+    """Drives the captured training step (``GAN.capture``) from HOST batches, the way a data loader feeds it: the pinned
+    host -> device copies of step i run on a copy stream into one of two device staging sets while step i - 1's graph is
+    still executing; the step then copies the staging set into the graph's static inputs (device to device), replays
+    the graph and sends the loss scalars to pinned host memory.  Nothing synchronises the host: ``step`` returns the
+    pinned ``logs_host`` tensor, valid after ``torch.cuda.synchronize()`` (or an event the caller records)."""
+
+    def __init__(self, model, example_batch):
+        if model._graph is None:
+            model.capture(example_batch)
+        self.model = model
+        self.graph, self.static, self.logs = model._graph
+        self.keys = [k for k in ("t1w", "t2w") if k in self.static]
+        self.copy_stream = torch.cuda.Stream()
+        self.stage = [{k: torch.empty_like(self.static[k]) for k in self.keys} for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.logs_host = torch.zeros(self.logs.numel()).pin_memory()
+        self.i = 0
+
+    def step(self, host_batch):
+        """``host_batch``: {"t1w", "t2w"} pinned fp32 host tensors of the captured shape."""
+        j = self.i & 1
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[j])       # staging set j was consumed by step i - 2
+            for k in self.keys:
+                self.stage[j][k].copy_(host_batch[k], non_blocking=True)
+            self.ready[j].record(self.copy_stream)
+        cur.wait_event(self.ready[j])
+        for k in self.keys:
+            self.static[k].copy_(self.stage[j][k], non_blocking=True)
+        self.free[j].record(cur)
+        self.graph.replay()
+        self.logs_host.copy_(self.logs, non_blocking=True)
+        self.i += 1
+        return self.logs_host
+
+
 class _PatchGather(torch.autograd.Function):
     """RandSpatialCropSamplesd + torch.cat (test_runs/GAN.py:313-337): bit-exact gather, deterministic scatter-add."""
 

@@ -273,6 +273,40 @@ def test_training_step_pass_vs_oracle(precision, opt_idx):
             assert int(b1) == int(b2), n1
 
 
+def test_host_fed_step_equals_direct_replay():
+    """mpgan.HostFedStep (pinned host batches, H2D on a copy stream into double-buffered staging, D2D into the graph's
+    inputs, replay, async D2H of the losses) runs the same steps as copying into the static inputs by hand."""
+    from mpgan import HostFedStep
+    B, S = 2, 64
+    torch.manual_seed(0)
+    kw = dict(precision="fp32", g_lr=0.0, d_lr=0.0)
+    a, b = GAN(1, S, S, **kw), GAN(1, S, S, **kw)
+    b.load_state_dict(a.state_dict())
+    hosts = [{k: v.pin_memory() for k, v in synthetic_batch(B, 2, S, seed=s).items()} for s in (1, 2, 3, 4, 5)]
+    graph, static, logs = a.capture(to_dev(hosts[0]))
+    want = []
+    for h in hosts:
+        static["t1w"].copy_(h["t1w"]), static["t2w"].copy_(h["t2w"])
+        graph.replay()
+        want.append(logs.cpu().clone())
+    fed = HostFedStep(b, to_dev(hosts[0]))
+    got = []
+    for h in hosts:
+        lh = fed.step(h)
+        torch.cuda.synchronize()
+        got.append(lh.clone())
+    for w, g in zip(want, got):
+        assert torch.allclose(g, w, rtol=2e-5, atol=1e-6)
+    # back-to-back steps without host synchronisation: the double-buffered staging must not be overwritten early
+    c = GAN(1, S, S, **kw)
+    c.load_state_dict(a.state_dict())
+    fed2 = HostFedStep(c, to_dev(hosts[0]))
+    for h in hosts:
+        lh = fed2.step(h)
+    torch.cuda.synchronize()
+    assert torch.allclose(lh, want[-1], rtol=2e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_fused_step_and_graph_replay_equal_the_protocol(precision):
     """fit_batch (reference protocol through autograd), fused_step (static plan) and the captured CUDA graph run the
