@@ -20,4 +20,8 @@ batch["origins"] = torch.as_tensor(origins.reshape(-1, 2), dtype=torch.int32, de
 for _ in range(n):
     logs = model.fused_step(batch)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()      # ncu --profile-from-start off: one more step is recorded
+logs = model.fused_step(batch)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print(logs.tolist())
