@@ -181,7 +181,7 @@ wgrad_x1_kernel(C1Geom p, const T* __restrict__ x, int64_t ldx, const T* __restr
 namespace mpgan {
 // conv_c1_fast.cu: rank-2 3x3 fast paths; return 1 when they do not cover the call
 int c1f_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* w, const float* bias, void* y,
-              int64_t ldy, double* stats, cudaStream_t s);
+              int64_t ldy, double* stats, cudaStream_t s, const float* slope = nullptr);
 int c1f_bprop(const MpganConvGeom* g, int dtype, const void* y, int64_t ldy, const void* w, const float* bias, void* x,
               int64_t ldx, double* stats, cudaStream_t s);
 int c1f_wgrad(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* y, int64_t ldy, float* dw,
@@ -243,6 +243,20 @@ extern "C" int mpgan_c1_conv_fprop(const MpganConvGeom* g, int dtype, const void
   }
   if (rc || !stats) return rc;
   return mpgan_bn_stats(dtype, y, ldy, (int64_t)p.n * p.ys[0] * p.ys[1] * p.ys[2], p.cy, stats, stream);
+}
+
+// Inference-mode fused one-input-channel layer: y = prelu(conv(x, w_folded) + bias_folded), BatchNorm folded into w / bias
+// by the caller (MONAI Convolution in model.eval(), /root/reference/code/GAN/inferrence.py:107-109).  Covered: rank-2 3x3
+// layers the run-based kernel takes (8 | cy; stride 1, or stride 2 on a contiguous bf16 image with 8 | width).
+extern "C" int mpgan_c1_conv_act(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* w,
+                                 const float* bias, const float* slope, void* y, int64_t ldy, void* stream) {
+  C1Geom p;
+  int rc = make_c1(g, &p);
+  if (rc) return rc;
+  MPGAN_REQUIRE(slope != nullptr, MPGAN_ERR_SHAPE, "c1_conv_act: slope must be given (use mpgan_c1_conv_fprop otherwise)");
+  rc = c1f_fprop(g, dtype, x, ldx, w, bias, y, ldy, nullptr, (cudaStream_t)stream, slope);
+  MPGAN_REQUIRE(rc != 1, MPGAN_ERR_UNSUPPORTED, "c1_conv_act: layer not covered by the run-based one-channel kernel");
+  return rc;
 }
 
 extern "C" int mpgan_c1_conv_bprop(const MpganConvGeom* g, int dtype, const void* y, int64_t ldy, const void* w,

@@ -289,7 +289,7 @@ __device__ __forceinline__ void load_window_any(const Geom& g, const T* __restri
 template <typename T, int S>
 __global__ void __launch_bounds__(kThreads, 1)
 fprop_run_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__ w, const float* __restrict__ bias,
-                 T* __restrict__ y, int ldy, double* __restrict__ stats) {
+                 T* __restrict__ y, int ldy, double* __restrict__ stats, const float* __restrict__ slope) {
   pdl_wait();
   pdl_launch();
   constexpr int RUN = RunOf<S>::RUN, WIN = RunOf<S>::WIN;
@@ -326,6 +326,7 @@ fprop_run_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__
     }
   }
   constexpr bool kExact = sizeof(T) == 4;   // fp32 storage: flush the fp32 statistics partials into fp64 every run
+  const float slope_a = slope ? __ldg(slope) : 1.f;
   float2 s1[4], s2[4];
   double d1[kExact ? 8 : 1], d2[kExact ? 8 : 1];
 #pragma unroll
@@ -351,6 +352,13 @@ fprop_run_kernel(Geom g, const T* __restrict__ x, int ldx, const T* __restrict__
 #pragma unroll
           for (int q = 0; q < 3; ++q) a = ffma2(make_float2(xv[rh][i * S + q], xv[rh][i * S + q]), wr[rh * 3 + q][j], a);
         o2[j] = a;
+      }
+      if (slope) {   // inference fusion: BatchNorm folded into (w, bias) by the caller, PReLU here (uniform branch)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o2[j].x = o2[j].x > 0.f ? o2[j].x : slope_a * o2[j].x;
+          o2[j].y = o2[j].y > 0.f ? o2[j].y : slope_a * o2[j].y;
+        }
       }
       if (w0 + i < g.yw) {
         float o[8];
@@ -795,8 +803,10 @@ static inline bool fits32(int64_t pixels, int64_t ld) { return pixels * ld < ((i
 }  // namespace c1f
 
 // Return 0 on success, MPGAN_ERR_* on failure, 1 when the fast path does not cover the call (caller falls back).
+// slope (optional, device scalar): PReLU on (conv + bias) -- the inference fusion; only the run-based kernel has it, so
+// with a slope the call returns 1 (not covered) instead of falling back to the pixel-at-a-time kernel.
 int c1f_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* w, const float* bias, void* y,
-              int64_t ldy, double* stats, cudaStream_t s) {
+              int64_t ldy, double* stats, cudaStream_t s, const float* slope) {
   using namespace c1f;
   Geom q;
   if (!geom_ok(g, &q)) return 1;
@@ -815,12 +825,13 @@ int c1f_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, con
     const int gridr = q.vec ? grid_for(nruns, cv, 4, 2) : grid_for(nruns, cv, 2, 4);   // fewer, fatter threads: the 72-weight
                                                                                       // prologue and the statistics reduce are per thread
     MPGAN_DISPATCH_DTYPE(dtype, T, {
-      if (q.s == 1) launch_k(fprop_run_kernel<T, 1>, gridr, kThreads, 0, s, q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y, (int)ldy, stats);
-      else launch_k(fprop_run_kernel<T, 2>, gridr, kThreads, 0, s, q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y, (int)ldy, stats);
+      if (q.s == 1) launch_k(fprop_run_kernel<T, 1>, gridr, kThreads, 0, s, q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y, (int)ldy, stats, slope);
+      else launch_k(fprop_run_kernel<T, 2>, gridr, kThreads, 0, s, q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y, (int)ldy, stats, slope);
       MPGAN_CHECK_LAUNCH("c1f_fprop_run");
       return 0;
     });
   }
+  if (slope) return 1;
   const int grid = grid_for(P, cv, 8, 8);
   MPGAN_DISPATCH_DTYPE(dtype, T, {
     C1F_LAUNCH(fprop_kernel, V, q.s, grid, 0, s, q, (const T*)x, (int)ldx, (const T*)w, bias, (T*)y,

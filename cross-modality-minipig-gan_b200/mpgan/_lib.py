@@ -31,6 +31,7 @@ _SIGS = {
     "mpgan_conv_wgrad": (c_int, [_G, c_int, _P, c_int64, _P, c_int64, _P, _P]),
     "mpgan_c1_supported": (c_int, [_G, c_int]),
     "mpgan_c1_conv_fprop": (c_int, [_G, c_int, _P, c_int64, _P, _P, _P, c_int64, _P, _P]),
+    "mpgan_c1_conv_act": (c_int, [_G, c_int, _P, c_int64, _P, _P, _P, _P, c_int64, _P]),
     "mpgan_c1_conv_bprop": (c_int, [_G, c_int, _P, c_int64, _P, _P, _P, c_int64, _P, _P]),
     "mpgan_c1_conv_wgrad": (c_int, [_G, c_int, _P, c_int64, _P, c_int64, _P, _P]),
     "mpgan_tc_supported": (c_int, [_G, c_int]),

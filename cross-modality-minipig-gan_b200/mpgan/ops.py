@@ -172,6 +172,15 @@ def conv_act(spec, x, w, bias, slope, res=None, out=None):
     else:
         xs, ys, direction, cout = ins, spec.y_of_x(ins), 0, spec.cy
     g = spec.geom(n, xs, ys)
+    if (not spec.transposed and spec.cx == 1 and spec.rank == 2 and res is None and spec.cy % 8 == 0 and x.is_contiguous()
+            and os.environ.get("MPGAN_NO_C1ACT", "0") != "1"):
+        # one input channel (the UNet's first layer): the run-based CUDA-core kernel with the PReLU in its store path
+        o = out if out is not None else torch.empty((n,) + tuple(ys) + (cout,), dtype=x.dtype, device=x.device)
+        rc = lib.mpgan_c1_conv_act(ctypes.byref(g), dt(x), ptr(x), ld(x), ptr(w), ptr(bias), ptr(slope), ptr(o), ld(o), _stream())
+        if rc == 0:
+            return o
+        if rc != -2:
+            check(rc, "c1_conv_act")
     if not tc_supported(g, direction):
         return None
     if out is None:

@@ -104,6 +104,10 @@ int mpgan_c1_supported(const MpganConvGeom* g, int direction /*0 fprop,1 bprop,2
 int mpgan_c1_conv_fprop(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* w,
                         const float* bias, void* y, int64_t ldy, double* stats /* nullable: BN sums of y */,
                         void* stream);
+/* inference fusion of a one-input-channel layer: y = prelu(conv(x, w) + bias), BatchNorm folded into (w, bias) by the caller
+ * (MONAI Convolution in model.eval(), inferrence.py:107-109); returns -2 when the run-based kernel does not cover the layer */
+int mpgan_c1_conv_act(const MpganConvGeom* g, int dtype, const void* x, int64_t ldx, const void* w, const float* bias,
+                      const float* slope, void* y, int64_t ldy, void* stream);
 int mpgan_c1_conv_bprop(const MpganConvGeom* g, int dtype, const void* y, int64_t ldy, const void* w,
                         const float* bias, void* x, int64_t ldx, double* stats /* nullable: BN sums of x */,
                         void* stream);

@@ -133,6 +133,24 @@ def test_c1_dgrad_through_tensor_cores(n, cout, size, p):
     assert rel_l2(dx2.float() - r.float(), dx.float()) <= 6e-3
 
 
+@pytest.mark.parametrize("n,cout,size,s", [(2, 16, 64, 2), (3, 32, 32, 2), (2, 16, 24, 1), (2, 16, 30, 2)])
+def test_c1_conv_act_inference_fusion(n, cout, size, s):
+    """One-input-channel layer in evaluation mode: conv + folded bias + PReLU in one launch (mpgan_c1_conv_act); layers the
+    run-based kernel does not take (width not a multiple of 8 at stride 2) report "not covered" and conv_act returns None."""
+    x = rnd(n, 1, size, size, seed=1).bfloat16()
+    w = (rnd(cout, 1, 3, 3, seed=2) * 0.3).bfloat16()
+    b = rnd(cout, seed=3)
+    slope = torch.tensor([0.2], device=DEV)
+    ref = F.prelu(F.conv2d(x.float(), w.float(), b, stride=s, padding=1), slope)
+    spec = ops.ConvSpec(2, 1, cout, 3, s, 1)
+    y = ops.conv_act(spec, cl(x, torch.bfloat16), oti(w, torch.bfloat16), b, slope)
+    if s == 2 and size % 8 != 0:
+        assert y is None
+        return
+    assert y is not None and y.shape == (n, ref.shape[2], ref.shape[3], cout)
+    assert rel_l2(uncl(y), ref) <= 6e-3
+
+
 @pytest.mark.parametrize("n,cin,size", [(2, 32, 24), (3, 16, 40), (1, 64, 16)])
 def test_convt_into_one_channel_through_tensor_cores(n, cin, size):
     """ConvTranspose2d(cin -> 1, k3 s2 p1 op1) forward (== data gradient of a 1 -> cin stride-2 conv) through the halo
