@@ -250,10 +250,19 @@ halo3x3_kernel(const __grid_constant__ HaloParams P, const __grid_constant__ CUt
 #pragma unroll
       for (int j = 0; j < CH / 2; ++j) { s1[j] = 0ull; s2[j] = 0ull; }
       int it = 0;
-      TileWalk<3> tw;
-      { const int radix[3] = {P.tiles_w, P.tiles_h, 1 << 30}; tw.init((int)blockIdx.x, (int)gridDim.x, radix); }
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, tw.next()) {
+      TileWalk<3> tw, twa;     // twa runs kResAhead tiles ahead: L2 prefetch of the residual rows (cold 134 MB tensors at inference size)
+      constexpr int kResAhead = 4;
+      { const int radix[3] = {P.tiles_w, P.tiles_h, 1 << 30}; tw.init((int)blockIdx.x, (int)gridDim.x, radix);
+        twa.init((int)blockIdx.x + kResAhead * (int)gridDim.x, (int)gridDim.x, radix); }
+      const bool res_pf = P.res != nullptr && P.n_store == 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, tw.next(), twa.next()) {
         if (NCH == 1 && (it & 1) != half) continue;
+        if (res_pf && tile + kResAhead * (int)gridDim.x < P.total_tiles) {
+          const int oha = twa.d[1] * HT_H + lh, owa = twa.d[0] * HT_W + lw;
+          if (oha < P.oh && owa < P.ow)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.res + (long long)twa.d[2] * P.res_sn + (long long)oha * P.res_sh +
+                                                          (long long)owa * P.res_sw + c0));
+        }
         const int twi = tw.d[0], thi = tw.d[1], img = tw.d[2];
         const int oh = thi * HT_H + lh, ow = twi * HT_W + lw;
         const bool valid = oh < P.oh && ow < P.ow;
