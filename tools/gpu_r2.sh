@@ -61,6 +61,14 @@ for w in $WHAT; do
                    --log-file gpurun_out/launches_g${ph}_$TAG.csv python tools/g_phases_once.py $ph > gpurun_out/ncu_g${ph}_$TAG.log 2>&1
                echo "ncugp $ph exit $?"; wc -l gpurun_out/launches_g${ph}_$TAG.csv
              done;;
+    ncugt)   # ncu --set full (warm caches) over the first UNet of the generator forward and the last UNet's backward, training size
+             timeout 900 ncu --set full --cache-control none --clock-control none --profile-from-start off -c 32 \
+                 -o /tmp/gtf_$TAG -f python tools/g_phases_once.py fwd > gpurun_out/ncu_gtf_$TAG.log 2>&1
+             timeout 1200 ncu --set full --cache-control none --clock-control none --profile-from-start off -c 76 \
+                 -o /tmp/gtb_$TAG -f python tools/g_phases_once.py bwd > gpurun_out/ncu_gtb_$TAG.log 2>&1
+             ncu -i /tmp/gtf_$TAG.ncu-rep --page raw --csv > gpurun_out/gtrain_fwd_raw_$TAG.csv 2> /dev/null
+             ncu -i /tmp/gtb_$TAG.ncu-rep --page raw --csv > gpurun_out/gtrain_bwd_raw_$TAG.csv 2> /dev/null
+             ls -la gpurun_out/gtrain_*;;
     ncui)    CMD="python tools/infer_once.py"
              timeout 600 $CMD > gpurun_out/plain_infer_$TAG.log 2>&1 &&
              timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
